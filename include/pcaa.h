@@ -1,0 +1,170 @@
+/* libpcaa_sm100 -- C ABI of the B200-native PCAA train / open-set-inference hot path.
+ *
+ * The reference (rmazzier/OpenSetGaitRecognition_PCAA) is 100 % Python and has no FFI; the seam
+ * this library plugs into is the Python module surface of its models.py / utils.py.
+ * Every entry point below names the reference code (file:line) whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers owned by the caller (PyTorch allocations); the library never
+ *    allocates or frees device memory and keeps no pointers across calls;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no internal synchronisation;
+ *  - return value: 0 = PCAA_OK, otherwise a pcaa_status; text via pcaa_last_error() (thread local);
+ *  - "rows" matrices are channels-last: X[R, C] with C contiguous; point rows are ordered (b, t, n);
+ *  - dtype arguments are pcaa_dtype values; statistics accumulators are double and are ADDED to
+ *    (the caller zeroes them), everything else is overwritten unless stated.
+ */
+#ifndef PCAA_H_
+#define PCAA_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PCAA_OK = 0,
+    PCAA_ERR_SHAPE = 1,
+    PCAA_ERR_ALIGN = 2,
+    PCAA_ERR_UNSUPPORTED = 3,
+    PCAA_ERR_LAUNCH = 4,
+    PCAA_ERR_DRIVER = 5
+} pcaa_status;
+
+typedef enum { PCAA_F32 = 0, PCAA_BF16 = 1 } pcaa_dtype;
+typedef enum { PCAA_ACT_NONE = 0, PCAA_ACT_ELU = 1 } pcaa_act;
+
+typedef void* pcaa_stream; /* cudaStream_t */
+
+const char* pcaa_version(void);
+const char* pcaa_last_error(void);
+
+/* ---- generic CUDA-core GEMM (small layers: TCN, heads, discriminator; bring-up comparator) -------------
+ * C(m,n) = act( sum_k A(m,k) B(k,n) + bias[n] ) [+ C(m,n) if accumulate]; element (i,j) of X at X[i*s0 + j*s1].
+ * Replaces torch.nn.Linear / Conv1d matmuls of models.py:59-67, 252-277, 344-371, 409-415. */
+int pcaa_gemm_simt(const void* A, int a_dtype, int64_t sam, int64_t sak,
+                   const void* B, int b_dtype, int64_t sbk, int64_t sbn,
+                   void* C, int c_dtype, int64_t scm, int64_t scn,
+                   int64_t M, int64_t N, int64_t K,
+                   const float* bias, int act, int accumulate, pcaa_stream stream);
+
+/* ---- tensor-core GEMMs (tcgen05 + TMA + TMEM), bf16 x bf16 -> fp32 ---------------------------------------
+ * mode PCAA_TC_BIAS_STATS : Y = A W^T + bias (bf16 out) and per-column sum / sum-of-squares of the fp32 result
+ *                           added to stats[2N] (BatchNorm batch statistics of models.py:29 fused in the epilogue)
+ * mode PCAA_TC_BIAS_ELU   : Y = ELU(A W^T + bias)       (eval mode with BatchNorm folded into W, bias)
+ * mode PCAA_TC_PLAIN      : Y = A W^T                    (bf16 out)
+ * mode PCAA_TC_DGRAD_ELUBN: dZ = (A W^T) * ELU'(scale*Yprev + shift) (bf16 out) and sum dZ, sum dZ*xhat added to
+ *                           stats[2N]  (backward of models.py:33-34 fused in the data-gradient GEMM's epilogue)
+ * A [M,K] (lda), W [N,K] (ldw), out [M,N] (ldo); all bf16, leading dims multiples of 8 elements. */
+typedef enum { PCAA_TC_BIAS_STATS = 0, PCAA_TC_BIAS_ELU = 1, PCAA_TC_PLAIN = 2, PCAA_TC_DGRAD_ELUBN = 3 } pcaa_tc_mode;
+int pcaa_gemm_tc_tn(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                    int64_t M, int64_t N, int64_t K, int mode,
+                    const float* bias, double* stats,
+                    const void* yprev, const float* scale, const float* shift, const float* mean, const float* invstd,
+                    pcaa_stream stream);
+/* weight gradient: dW[N1,N2] (fp32, ADDED to) = A^T B with A [K,N1] (lda), B [K,N2] (ldb) bf16, K = rows (points). */
+int pcaa_gemm_tc_nt_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
+                          int64_t N1, int64_t N2, int64_t K, pcaa_stream stream);
+/* number of SMs the persistent kernels size their grids with (0 if no device) */
+int pcaa_sm_count(void);
+
+/* ---- PointNet layer 1 (Cin = 4: CUDA cores), models.py:86-88 -----------------------------------------------
+ * x (B,4,T,N) fp32 NCHW -> y [B*TN, Cout] bf16 = W x + b, and column statistics of y added to stats[2*Cout]. */
+int pcaa_pointnet_l1_fwd(const float* x, const float* w, const float* bias, void* y, double* stats,
+                         int64_t B, int64_t TN, int Cout, pcaa_stream stream);
+/* dW[Cout,4] = dy^T x (overwritten). */
+int pcaa_pointnet_l1_wgrad(const float* x, const void* dy, float* dW, int64_t B, int64_t TN, int Cout,
+                           pcaa_stream stream);
+
+/* ---- BatchNorm (train) + ELU on channels-last rows, models.py:29,33-34,72-78 ------------------------------ */
+int pcaa_colstats(const void* y, int dtype, int64_t R, int C, double* stats, pcaa_stream stream);
+/* scale = gamma*invstd, shift = beta - mean*scale; running stats updated in place when non-null
+ * (momentum, unbiased variance) exactly as torch.nn.BatchNorm does in training mode. */
+int pcaa_bn_finalize(const double* stats, int64_t R, int C, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps,
+                     float* scale, float* shift, float* mean, float* invstd, pcaa_stream stream);
+/* eval mode: scale/shift from running statistics */
+int pcaa_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                        float eps, float* scale, float* shift, int C, pcaa_stream stream);
+/* out = ELU(scale*y + shift) */
+int pcaa_bn_elu_apply(const void* y, int y_dtype, const float* scale, const float* shift, void* out, int out_dtype,
+                      int64_t R, int C, pcaa_stream stream);
+/* pooled[g,c] = mean_{i<n} ELU(scale*y[g*n+i,c] + shift)   (AvgPool2d((1,nmax)), models.py:242-243,282) */
+int pcaa_bn_elu_meanpool(const void* y, int y_dtype, const float* scale, const float* shift, float* pooled,
+                         int64_t G, int n, int C, pcaa_stream stream);
+/* dz = dout * ELU'(scale*y+shift); stats2 += [sum dz, sum dz*xhat].  pooled_n > 0: dout is fp32 [R/pooled_n, C]
+ * (gradient of the mean pool, broadcast and divided by pooled_n), else dout is [R,C] of dout_dtype. */
+int pcaa_elu_bwd_colstats(const void* dout, int dout_dtype, int pooled_n, const void* y, int y_dtype,
+                          const float* scale, const float* shift, const float* mean, const float* invstd,
+                          void* dz, int dz_dtype, double* stats2, int64_t R, int C, pcaa_stream stream);
+/* dy = c1*dz + c2*y + c3 (BatchNorm backward); dgamma = sum dz*xhat, dbeta = sum dz */
+int pcaa_bn_bwd_finalize(const double* stats2, int64_t R, int C, const float* scale, const float* mean,
+                         const float* invstd, float* c1, float* c2, float* c3, float* dgamma, float* dbeta,
+                         pcaa_stream stream);
+int pcaa_bn_bwd_apply(const void* dz, int dz_dtype, const void* y, int y_dtype, const float* c1, const float* c2,
+                      const float* c3, void* dy, int dy_dtype, int64_t R, int C, pcaa_stream stream);
+
+/* ---- small helpers ----------------------------------------------------------------------------------------- */
+/* dz = dout * (out > 0 ? 1 : out + 1): ELU backward from the saved OUTPUT (Linear+ELU heads, decoder) */
+int pcaa_elu_bwd_from_out(const float* dout, const float* out, float* dz, int64_t n, pcaa_stream stream);
+int pcaa_colsum(const float* x, int64_t R, int C, float* out, pcaa_stream stream);
+int pcaa_convert(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, pcaa_stream stream);
+/* out[r, c] (ld_out, bf16) = in[r, c] (ld_in, fp32), or the transpose when transpose != 0; pad columns zeroed */
+int pcaa_pack_bf16(const float* in, int64_t R, int64_t C, int64_t ld_in, void* out, int64_t ld_out, int transpose,
+                   pcaa_stream stream);
+/* causal dilated Conv1d as GEMM: col[(b,t), ci*3+k] = x[b, t-(2-k)*dil, ci] (0 for negative time), models.py:59-76 */
+int pcaa_tcn_im2col(const float* x, float* col, int64_t B, int T, int Cin, int dil, pcaa_stream stream);
+int pcaa_tcn_col2im(const float* dcol, float* dx, int64_t B, int T, int Cin, int dil, pcaa_stream stream);
+/* out[g,c] = mean_i x[g,i,c] (AvgPool1d(NSTEPS), models.py:249,284) and its backward */
+int pcaa_mean_rows(const float* x, float* out, int64_t G, int n, int C, pcaa_stream stream);
+int pcaa_mean_rows_bwd(const float* g, float* dx, int64_t G, int n, int C, pcaa_stream stream);
+/* mean cross-entropy of torch.nn.CrossEntropyLoss (PCAA_ablation.py:1009), its gradient * gscale, argmax class */
+int pcaa_softmax_ce(const float* logits, const int64_t* gt, float* loss, float* dlogits, float gscale, int32_t* pred,
+                    int64_t B, int C, pcaa_stream stream);
+
+/* ---- SeqChamferLoss, utils.py:98-132 ------------------------------------------------------------------------
+ * preds, gts (B,F,T,N) fp32.  frame_loss[b,t] = sum_j min_i P + sum_i min_j P with
+ * P[i,j] = |gt_i|^2 + |pred_j|^2 - 2 gt_i.pred_j; argmins (lowest index on ties) are optional outputs. */
+int pcaa_chamfer_fwd(const float* preds, const float* gts, int64_t B, int F, int T, int N, float* frame_loss,
+                     int32_t* idx_gt_for_pred, int32_t* idx_pred_for_gt, pcaa_stream stream);
+/* avg_out != 0: out[0] = mean over (b,t); else out[b] = mean over t (utils.py:104-107) */
+int pcaa_chamfer_reduce(const float* frame_loss, int64_t B, int T, int avg_out, float* out, pcaa_stream stream);
+/* grad_preds = gout * d loss / d preds through the saved argmins (gout: scalar if avg_out else [B]) */
+int pcaa_chamfer_bwd(const float* preds, const float* gts, const int32_t* idx_gt_for_pred,
+                     const int32_t* idx_pred_for_gt, const float* gout, int avg_out, int64_t B, int F, int T, int N,
+                     float* grad_preds, pcaa_stream stream);
+
+/* ---- conditional critic (CGDiscriminator, models.py:405-421) and the WGAN-GP step ---------------------------
+ * Weights: W1 [64, 32+C], W2 [32,64], W3 [1,32].  labels int64 [B]; one-hot is formed in-kernel.
+ * pcaa_wgangp_dstep = PCAA_ablation.py:905-973: z = z0 + means[label]; d_loss = mean D(fv) - mean D(z)
+ *   + gp_weight * mean((||grad_x D(z + alpha (fv - z))|| - 1)^2), gradients w.r.t. all critic weights in closed
+ *   form (double backward through Linear/ELU done analytically).  losses[4] = {d_loss, gp, mean_fake, mean_real}.
+ *   grads (ADDED to, caller zeroes): gW1,gb1,gW2,gb2,gW3,gb3. */
+int pcaa_wgangp_dstep(const float* fv, const float* z0, const float* means, const int64_t* labels,
+                      const float* alphas, const float* W1, const float* b1, const float* W2, const float* b2,
+                      const float* W3, const float* b3, float gp_weight, float* losses,
+                      float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
+                      int64_t B, int C, pcaa_stream stream);
+/* out[b] = D(x_b, onehot(label_b)); dx[b,:] = d out[b] / d x_b (either output may be null) */
+int pcaa_disc_fwd(const float* x, const int64_t* labels, const float* W1, const float* b1, const float* W2,
+                  const float* b2, const float* W3, const float* b3, float* out, float* dx, int64_t B, int C,
+                  pcaa_stream stream);
+
+/* ---- Adam, torch.optim.Adam defaults as used at PCAA_ablation.py:821-833 ------------------------------------
+ * flat buffers of n floats; step is the 1-based step count; g is multiplied by grad_scale first (1/world for DP);
+ * when shadow_bf16 is non-null the updated parameter is also written there as bf16 (tensor-core operand copy). */
+int pcaa_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, int step, float grad_scale, void* shadow_bf16, pcaa_stream stream);
+
+/* ---- open-set scoring, inference_PCAA.py:129-136, 255-271 ---------------------------------------------------
+ * loglik[i] = log( (1/C) sum_c N(emb_i; mu_c, I_D) ) in float64 (log-domain restatement).
+ * vote: windows of k consecutive samples; n_above = #(loglik > log_thr); n_above > k/2 -> lowest most-frequent
+ * class among pred, else n_labels ("unknown"). */
+int pcaa_openset_score(const float* emb, const float* means, int64_t M, int C, int D, double* loglik,
+                       pcaa_stream stream);
+int pcaa_openset_vote(const double* loglik, const int32_t* pred, int64_t n_windows, int k, double log_thr,
+                      int n_labels, int32_t* out, pcaa_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCAA_H_ */

@@ -1,0 +1,84 @@
+"""ctypes binding of libpcaa_sm100.so (the C ABI declared in include/pcaa.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpcaa_sm100.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_ELU = 0, 1
+TC_BIAS_STATS, TC_BIAS_ELU, TC_PLAIN, TC_DGRAD_ELUBN = 0, 1, 2, 3
+
+_p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+
+# name -> argument ctypes (return type is always int except the two string getters / sm_count)
+SIGNATURES = {
+    "pcaa_gemm_simt": [_p, _i, _l, _l, _p, _i, _l, _l, _p, _i, _l, _l, _l, _l, _l, _p, _i, _i, _p],
+    "pcaa_gemm_tc_tn": [_p, _l, _p, _l, _p, _l, _l, _l, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "pcaa_gemm_tc_nt_wgrad": [_p, _l, _p, _l, _p, _l, _l, _l, _l, _p],
+    "pcaa_pointnet_l1_fwd": [_p, _p, _p, _p, _p, _l, _l, _i, _p],
+    "pcaa_pointnet_l1_wgrad": [_p, _p, _p, _l, _l, _i, _p],
+    "pcaa_colstats": [_p, _i, _l, _i, _p, _p],
+    "pcaa_bn_finalize": [_p, _l, _i, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p],
+    "pcaa_bn_eval_coeffs": [_p, _p, _p, _p, _f, _p, _p, _i, _p],
+    "pcaa_bn_elu_apply": [_p, _i, _p, _p, _p, _i, _l, _i, _p],
+    "pcaa_bn_elu_meanpool": [_p, _i, _p, _p, _p, _l, _i, _i, _p],
+    "pcaa_elu_bwd_colstats": [_p, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _l, _i, _p],
+    "pcaa_bn_bwd_finalize": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "pcaa_bn_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _l, _i, _p],
+    "pcaa_elu_bwd_from_out": [_p, _p, _p, _l, _p],
+    "pcaa_colsum": [_p, _l, _i, _p, _p],
+    "pcaa_convert": [_p, _i, _p, _i, _l, _p],
+    "pcaa_pack_bf16": [_p, _l, _l, _l, _p, _l, _i, _p],
+    "pcaa_tcn_im2col": [_p, _p, _l, _i, _i, _i, _p],
+    "pcaa_tcn_col2im": [_p, _p, _l, _i, _i, _i, _p],
+    "pcaa_mean_rows": [_p, _p, _l, _i, _i, _p],
+    "pcaa_mean_rows_bwd": [_p, _p, _l, _i, _i, _p],
+    "pcaa_softmax_ce": [_p, _p, _p, _p, _f, _p, _l, _i, _p],
+    "pcaa_chamfer_fwd": [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p],
+    "pcaa_chamfer_reduce": [_p, _l, _i, _i, _p, _p],
+    "pcaa_chamfer_bwd": [_p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _p, _p],
+    "pcaa_wgangp_dstep": [_p] * 11 + [_f] + [_p] * 7 + [_l, _i, _p],
+    "pcaa_disc_fwd": [_p] * 10 + [_l, _i, _p],
+    "pcaa_adam_flat": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _i, _f, _p, _p],
+    "pcaa_openset_score": [_p, _p, _l, _i, _i, _p, _p],
+    "pcaa_openset_vote": [_p, _p, _l, _i, _d, _i, _p, _p],
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library (once).  Raises if it has not been built -- there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m opensetgaitrecognition_pcaa_b200.build` "
+                "(the PCAA B200 path has no CPU / PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.pcaa_version.restype = C.c_char_p
+        lib.pcaa_last_error.restype = C.c_char_p
+        lib.pcaa_sm_count.restype = C.c_int
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (status {rc}): {lib.pcaa_last_error().decode()}")
+
+
+def version() -> str:
+    return load().pcaa_version().decode()

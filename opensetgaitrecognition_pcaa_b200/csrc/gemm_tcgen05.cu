@@ -1,0 +1,567 @@
+// Blackwell tensor-core GEMMs of the PCAA hot path: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands staged
+// by TMA into 128B-swizzled shared memory, mbarrier producer/consumer pipeline, persistent warp-specialised CTAs.
+//
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
+//   warps 2..5  : epilogue (TMEM -> registers -> fused epilogue -> global), one TMEM lane quarter each
+//
+// Two 128 x BN fp32 accumulators live in TMEM (2*BN <= 512 columns) so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  Work items are (m-tile, n-tile, k-split) triples strided over the persistent grid.
+//
+// Replaces the per-point 1x1 Conv2d contractions of the reference (models.py:21-28, 86-98) and their autograd
+// backward (data gradient with fused ELU'/BatchNorm-statistics epilogue, weight gradient with split-K).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pcaa {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+
+enum { MODE_BIAS_STATS = 0, MODE_BIAS_ELU = 1, MODE_PLAIN = 2, MODE_DGRAD_ELUBN = 3, MODE_WGRAD = 4 };
+
+struct GemmParams {
+    int64_t M, N;                 // output extent (rows, cols)
+    int m_tiles, n_tiles, k_splits;
+    int kb_total, kb_per_split;   // K blocks of BK
+    void* out;                    // bf16 [M, ldo]  or fp32 (MODE_WGRAD)
+    int64_t ldo;
+    const float* bias;
+    double* stats;                // [2*N]
+    const __nv_bfloat16* yprev;   // [M, ldy] (MODE_DGRAD_ELUBN)
+    int64_t ldy;
+    const float *scale, *shift, *mean, *invstd;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("pcaa gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    // the registers are only valid after wait::ld: tie them to the wait so no consumer is scheduled above it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// shared-memory matrix descriptor (sm_100 UMMA), 128-byte swizzle
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;   // descriptor version (Blackwell)
+    d |= 2ull << 61;   // SWIZZLE_128B
+    return d;
+}
+
+// butterfly reduce-scatter: v[j] (j = column within a 32-column chunk) summed over the 32 lanes (rows);
+// afterwards lane l holds the total of column l in v[0].
+__device__ __forceinline__ float warp_col_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            float send = upper ? v[i] : v[i + s];
+            float keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+template <int BN>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int COLP_FLOATS = 5 * BN;          // bias | scale, shift, mean, invstd
+    static constexpr int STAT_FLOATS = 4 * 2 * BN;      // per epilogue warp: sum, sum2
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + (COLP_FLOATS + STAT_FLOATS) * 4 + 256 + 1024;
+};
+
+template <int BN, bool A_MN, bool B_MN, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using L = SmemLayout<BN>;
+    constexpr int STAGES = L::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* tiles = smem;
+    float* colp = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES);
+    float* wstat = colp + L::COLP_FLOATS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wstat + L::STAT_FLOATS);
+    uint64_t* full = bars;                   // [STAGES]
+    uint64_t* empty = bars + STAGES;         // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;     // [2]
+    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], EPI_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(2 * BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_items = p.m_tiles * p.n_tiles * p.k_splits;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int ks = item % p.k_splits;
+                const int tile = item / p.k_splits;
+                const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = tiles + stage * L::STAGE_BYTES;
+                    uint8_t* sb = sa + L::A_BYTES;
+                    mbar_expect_tx(&full[stage], L::STAGE_BYTES);
+                    if constexpr (!A_MN) {
+                        tma_load_2d(&tmA, &full[stage], sa, kb * BK, m_blk * BM);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            tma_load_2d(&tmA, &full[stage], sa + i * (BK * 128), m_blk * BM + i * 64, kb * BK);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(&tmB, &full[stage], sb, kb * BK, n_blk * BN);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            tma_load_2d(&tmB, &full[stage], sb + i * (BK * 128), n_blk * BN + i * 64, kb * BK);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                       ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                       ((uint32_t)(BM >> 4) << 24);
+            // K-major: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major: 64-element column groups BK*128 B apart
+            // (LBO), 8-k-row groups 1024 B apart (SBO).
+            constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, B_LBO = B_MN ? BK * 128 : 16;
+            constexpr uint32_t A_KSTEP = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+            constexpr uint32_t B_KSTEP = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int ks = item % p.k_splits;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int buf = it & 1;
+                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + stage * L::STAGE_BYTES);
+                    const uint32_t sb = sa + L::A_BYTES;
+                    const uint64_t da = make_desc(sa, A_LBO, 1024);
+                    const uint64_t db = make_desc(sb, B_LBO, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        tc_mma_bf16(tmem_d, da + (uint64_t)(k * A_KSTEP), db + (uint64_t)(k * B_KSTEP), idesc,
+                                    (kb > kb0 || k > 0) ? 1u : 0u);
+                    tc_commit(&empty[stage]);          // smem slot free once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[buf]);                // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===================================================================== epilogue warps
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int et = threadIdx.x - 64;                // 0..127
+        float* my_s1 = wstat + (warp - 2) * 2 * BN;
+        float* my_s2 = my_s1 + BN;
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int tile = item / p.k_splits;
+            const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+            const int64_t n0 = (int64_t)n_blk * BN;
+            const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const int buf = it & 1;
+            // stage the per-column parameters of this tile
+            if constexpr (MODE == MODE_BIAS_STATS || MODE == MODE_BIAS_ELU) {
+                for (int c = et; c < BN; c += EPI_THREADS) colp[c] = (n0 + c < p.N && p.bias) ? p.bias[n0 + c] : 0.f;
+            }
+            if constexpr (MODE == MODE_DGRAD_ELUBN) {
+                for (int c = et; c < BN; c += EPI_THREADS) {
+                    const bool ok = n0 + c < p.N;
+                    colp[BN + c] = ok ? p.scale[n0 + c] : 0.f;
+                    colp[2 * BN + c] = ok ? p.shift[n0 + c] : 0.f;
+                    colp[3 * BN + c] = ok ? p.mean[n0 + c] : 0.f;
+                    colp[4 * BN + c] = ok ? p.invstd[n0 + c] : 0.f;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                const int64_t col0 = n0 + c * 32;
+                if constexpr (MODE == MODE_WGRAD) {
+                    if (row_ok) {
+                        float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (col0 + j < p.N) atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    }
+                } else {
+                    float s2v[32];
+                    if constexpr (MODE == MODE_BIAS_STATS) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            v[j] += colp[c * 32 + j];
+                        }
+                    } else if constexpr (MODE == MODE_BIAS_ELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = elu_f(v[j] + colp[c * 32 + j]);
+                    } else if constexpr (MODE == MODE_DGRAD_ELUBN) {
+                        float yv[32];
+                        if (row_ok) {
+                            const uint4* yp = reinterpret_cast<const uint4*>(p.yprev + row * p.ldy + col0);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 u = __ldg(yp + g);
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 f = __bfloat1622float2(h[e]);
+                                    yv[g * 8 + 2 * e] = f.x;
+                                    yv[g * 8 + 2 * e + 1] = f.y;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) yv[j] = 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int cc = c * 32 + j;
+                            float z = fmaf(yv[j], colp[BN + cc], colp[2 * BN + cc]);
+                            float g = v[j] * elu_grad_f(z);
+                            float xh = (yv[j] - colp[3 * BN + cc]) * colp[4 * BN + cc];
+                            v[j] = g;
+                            s2v[j] = g * xh;
+                        }
+                    }
+                    // bf16 store of this thread's 32 consecutive columns (64 B)
+                    if (row_ok) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (col0 + g * 8 < p.N) {
+                                uint4 u;
+                                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                                *reinterpret_cast<uint4*>(o + g * 8) = u;
+                            }
+                        }
+                    }
+                    if constexpr (MODE == MODE_BIAS_STATS || MODE == MODE_DGRAD_ELUBN) {
+                        if constexpr (MODE == MODE_BIAS_STATS) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                v[j] = row_ok ? v[j] : 0.f;
+                                s2v[j] = v[j] * v[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                v[j] = row_ok ? v[j] : 0.f;
+                                s2v[j] = row_ok ? s2v[j] : 0.f;
+                            }
+                        }
+                        float t1 = warp_col_reduce32(v, lane);
+                        float t2 = warp_col_reduce32(s2v, lane);
+                        my_s1[c * 32 + lane] = t1;
+                        my_s2[c * 32 + lane] = t2;
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator are complete -> hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+            // every epilogue warp is done with colp / has published its partial statistics
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if constexpr (MODE == MODE_BIAS_STATS || MODE == MODE_DGRAD_ELUBN) {
+                for (int c = et; c < 2 * BN; c += EPI_THREADS) {
+                    const int which = c / BN, cc = c % BN;
+                    if (n0 + cc < p.N) {
+                        float s = wstat[(0 * 2 + which) * BN + cc] + wstat[(1 * 2 + which) * BN + cc] +
+                                  wstat[(2 * 2 + which) * BN + cc] + wstat[(3 * 2 + which) * BN + cc];
+                        atomicAdd(&p.stats[(int64_t)which * p.N + n0 + cc], (double)s);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, outer stride ld elements; box = b0 x b1
+static int make_map(CUtensorMap* m, const void* ptr, int64_t d0, int64_t d1, int64_t ld, int b0, int b1) {
+    EncodeTiledFn enc = get_encode();
+    PCAA_REQUIRE(enc != nullptr, PCAA_ERR_DRIVER, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    PCAA_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, PCAA_ERR_ALIGN,
+                 "tensor-core operand must be 16-byte aligned with a leading dimension multiple of 8 (ld=%lld)",
+                 (long long)ld);
+    cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)b0, (cuuint32_t)b1};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PCAA_REQUIRE(r == CUDA_SUCCESS, PCAA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return PCAA_OK;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, bool A_MN, bool B_MN, int MODE>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, MODE>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::TOTAL);
+        if (e != cudaSuccess) {
+            set_error("gemm_tc: cannot reserve %d bytes of shared memory: %s", SmemLayout<BN>::TOTAL,
+                      cudaGetErrorString(e));
+            return PCAA_ERR_LAUNCH;
+        }
+        attr = true;
+    }
+    int items = p.m_tiles * p.n_tiles * p.k_splits;
+    int grid = items < num_sms() ? items : num_sms();
+    kern<<<grid, NUM_THREADS, SmemLayout<BN>::TOTAL, st>>>(ta, tb, p);
+    return check_launch("gemm_tc");
+}
+
+}  // namespace pcaa
+
+using namespace pcaa;
+
+extern "C" int pcaa_gemm_tc_tn(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int64_t M,
+                               int64_t N, int64_t K, int mode, const float* bias, double* stats, const void* yprev,
+                               const float* scale, const float* shift, const float* mean, const float* invstd,
+                               pcaa_stream stream) {
+    if (M == 0 || N == 0) return PCAA_OK;
+    PCAA_REQUIRE(M > 0 && N > 0 && K > 0, PCAA_ERR_SHAPE, "gemm_tc_tn: bad shape");
+    PCAA_REQUIRE(N % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)out & 15) == 0, PCAA_ERR_ALIGN,
+                 "gemm_tc_tn: N and ldo must be multiples of 8 and out 16-byte aligned");
+    PCAA_REQUIRE(mode >= 0 && mode <= 3, PCAA_ERR_UNSUPPORTED, "gemm_tc_tn: unknown mode %d", mode);
+    if (mode == PCAA_TC_BIAS_STATS || mode == PCAA_TC_DGRAD_ELUBN)
+        PCAA_REQUIRE(stats != nullptr, PCAA_ERR_SHAPE, "gemm_tc_tn: stats buffer required for mode %d", mode);
+    if (mode == PCAA_TC_DGRAD_ELUBN)
+        PCAA_REQUIRE(yprev && scale && shift && mean && invstd, PCAA_ERR_SHAPE, "gemm_tc_tn: dgrad mode needs yprev/coefficients");
+    constexpr int BN = 256;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, A, K, M, lda, BK, BM);
+    if (rc) return rc;
+    rc = make_map(&tb, W, K, N, ldw, BK, BN);
+    if (rc) return rc;
+    GemmParams p{};
+    p.M = M;
+    p.N = N;
+    p.m_tiles = ceil_div(M, BM);
+    p.n_tiles = ceil_div(N, BN);
+    p.k_splits = 1;
+    p.kb_total = ceil_div(K, BK);
+    p.kb_per_split = p.kb_total;
+    p.out = out;
+    p.ldo = ldo;
+    p.bias = bias;
+    p.stats = stats;
+    p.yprev = (const __nv_bfloat16*)yprev;
+    p.ldy = N;
+    p.scale = scale;
+    p.shift = shift;
+    p.mean = mean;
+    p.invstd = invstd;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mode) {
+        case PCAA_TC_BIAS_STATS: return launch_tc<BN, false, false, MODE_BIAS_STATS>(ta, tb, p, st);
+        case PCAA_TC_BIAS_ELU: return launch_tc<BN, false, false, MODE_BIAS_ELU>(ta, tb, p, st);
+        case PCAA_TC_PLAIN: return launch_tc<BN, false, false, MODE_PLAIN>(ta, tb, p, st);
+        default: return launch_tc<BN, false, false, MODE_DGRAD_ELUBN>(ta, tb, p, st);
+    }
+}
+
+extern "C" int pcaa_gemm_tc_nt_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
+                                     int64_t N1, int64_t N2, int64_t K, pcaa_stream stream) {
+    if (N1 == 0 || N2 == 0 || K == 0) return PCAA_OK;
+    PCAA_REQUIRE(N1 > 0 && N2 > 0 && K > 0, PCAA_ERR_SHAPE, "gemm_tc_nt_wgrad: bad shape");
+    PCAA_REQUIRE(N2 % 4 == 0 && ldw % 4 == 0 && ((uintptr_t)dW & 15) == 0, PCAA_ERR_ALIGN,
+                 "gemm_tc_nt_wgrad: N2 and ldw must be multiples of 4 and dW 16-byte aligned");
+    constexpr int BN = 256;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, A, N1, K, lda, 64, BK);
+    if (rc) return rc;
+    rc = make_map(&tb, B, N2, K, ldb, 64, BK);
+    if (rc) return rc;
+    GemmParams p{};
+    p.M = N1;
+    p.N = N2;
+    p.m_tiles = ceil_div(N1, BM);
+    p.n_tiles = ceil_div(N2, BN);
+    p.kb_total = ceil_div(K, BK);
+    int tiles = p.m_tiles * p.n_tiles;
+    int splits = num_sms() / tiles;
+    if (splits < 1) splits = 1;
+    if (splits > p.kb_total) splits = p.kb_total;
+    p.kb_per_split = ceil_div(p.kb_total, splits);
+    p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
+    p.out = dW;
+    p.ldo = ldw;
+    return launch_tc<BN, true, true, MODE_WGRAD>(ta, tb, p, (cudaStream_t)stream);
+}

@@ -1,0 +1,320 @@
+"""Thin torch-tensor front-ends of the C-ABI kernels (device memory, streams: PyTorch; arithmetic: libpcaa_sm100).
+
+Every function enqueues on torch's current CUDA stream and returns torch tensors it allocated with torch.empty
+(so the caching allocator and CUDA graphs stay valid).  No function here computes with torch ops.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_ELU, ACT_NONE, BF16, F32, call
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _s() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype=None, contiguous=True) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("PCAA B200 ops need CUDA tensors (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise ValueError("expected a contiguous tensor")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ GEMM (CUDA cores)
+def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias: Optional[torch.Tensor] = None,
+         act: int = ACT_NONE, out: Optional[torch.Tensor] = None, accumulate=False,
+         out_dtype=torch.float32) -> torch.Tensor:
+    """out = act(op(a) @ op(b) + bias); a, b 2-D (any strides), fp32 or bf16."""
+    _chk(a, contiguous=False), _chk(b, contiguous=False)
+    am = a.t() if trans_a else a
+    bm = b.t() if trans_b else b
+    M, K = am.shape
+    K2, N = bm.shape
+    if K != K2:
+        raise ValueError(f"gemm: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    call("pcaa_gemm_simt", _p(am), _DT[am.dtype], am.stride(0), am.stride(1), _p(bm), _DT[bm.dtype], bm.stride(0),
+         bm.stride(1), _p(out), _DT[out.dtype], out.stride(0), out.stride(1), M, N, K, _p(bias), act,
+         1 if accumulate else 0, _s())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm family
+def colstats(y: torch.Tensor, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(y)
+    R, Cc = y.shape
+    if stats is None:
+        stats = torch.zeros(2 * Cc, device=y.device, dtype=torch.float64)
+    call("pcaa_colstats", _p(y), _DT[y.dtype], R, Cc, _p(stats), _s())
+    return stats
+
+
+def bn_finalize(stats, R, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5):
+    Cc = gamma.numel()
+    dev = gamma.device
+    coef = torch.empty((4, Cc), device=dev, dtype=torch.float32)   # scale, shift, mean, invstd
+    call("pcaa_bn_finalize", _p(stats), R, Cc, _p(gamma), _p(beta), _p(running_mean), _p(running_var), momentum, eps,
+         _p(coef[0]), _p(coef[1]), _p(coef[2]), _p(coef[3]), _s())
+    return coef
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps=1e-5):
+    Cc = gamma.numel()
+    coef = torch.empty((2, Cc), device=gamma.device, dtype=torch.float32)
+    call("pcaa_bn_eval_coeffs", _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps, _p(coef[0]), _p(coef[1]),
+         Cc, _s())
+    return coef
+
+
+def bn_elu_apply(y, scale, shift, out_dtype=None):
+    _chk(y)
+    R, Cc = y.shape
+    out = torch.empty((R, Cc), device=y.device, dtype=out_dtype or y.dtype)
+    call("pcaa_bn_elu_apply", _p(y), _DT[y.dtype], _p(scale), _p(shift), _p(out), _DT[out.dtype], R, Cc, _s())
+    return out
+
+
+def bn_elu_meanpool(y, scale, shift, n: int):
+    _chk(y)
+    R, Cc = y.shape
+    G = R // n
+    pooled = torch.empty((G, Cc), device=y.device, dtype=torch.float32)
+    call("pcaa_bn_elu_meanpool", _p(y), _DT[y.dtype], _p(scale), _p(shift), _p(pooled), G, n, Cc, _s())
+    return pooled
+
+
+def elu_bwd_colstats(dout, y, coef, pooled_n: int = 0, dz_dtype=None):
+    """dz = dout * ELU'(scale*y+shift) and stats2 = [sum dz, sum dz*xhat]; coef = bn_finalize output."""
+    _chk(y), _chk(dout)
+    R, Cc = y.shape
+    dz = torch.empty((R, Cc), device=y.device, dtype=dz_dtype or y.dtype)
+    stats2 = torch.zeros(2 * Cc, device=y.device, dtype=torch.float64)
+    call("pcaa_elu_bwd_colstats", _p(dout), _DT[dout.dtype], pooled_n, _p(y), _DT[y.dtype], _p(coef[0]), _p(coef[1]),
+         _p(coef[2]), _p(coef[3]), _p(dz), _DT[dz.dtype], _p(stats2), R, Cc, _s())
+    return dz, stats2
+
+
+def bn_bwd_finalize(stats2, R, coef, dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None):
+    Cc = coef.shape[1]
+    c = torch.empty((3, Cc), device=coef.device, dtype=torch.float32)
+    if dgamma is None:
+        dgamma = torch.empty(Cc, device=coef.device, dtype=torch.float32)
+    if dbeta is None:
+        dbeta = torch.empty(Cc, device=coef.device, dtype=torch.float32)
+    call("pcaa_bn_bwd_finalize", _p(stats2), R, Cc, _p(coef[0]), _p(coef[2]), _p(coef[3]), _p(c[0]), _p(c[1]), _p(c[2]),
+         _p(dgamma), _p(dbeta), _s())
+    return c, dgamma, dbeta
+
+
+def bn_bwd_apply(dz, y, c, out: Optional[torch.Tensor] = None):
+    R, Cc = y.shape
+    if out is None:
+        out = torch.empty_like(dz)
+    call("pcaa_bn_bwd_apply", _p(dz), _DT[dz.dtype], _p(y), _DT[y.dtype], _p(c[0]), _p(c[1]), _p(c[2]), _p(out),
+         _DT[out.dtype], R, Cc, _s())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def elu_bwd_from_out(dout, out):
+    _chk(dout, torch.float32), _chk(out, torch.float32)
+    dz = torch.empty_like(out)
+    call("pcaa_elu_bwd_from_out", _p(dout), _p(out), _p(dz), out.numel(), _s())
+    return dz
+
+
+def colsum(x, out: Optional[torch.Tensor] = None):
+    _chk(x, torch.float32)
+    R, Cc = x.shape
+    if out is None:
+        out = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    call("pcaa_colsum", _p(x), R, Cc, _p(out), _s())
+    return out
+
+
+def convert(x, dtype):
+    _chk(x)
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    call("pcaa_convert", _p(x), _DT[x.dtype], _p(out), _DT[dtype], x.numel(), _s())
+    return out
+
+
+def pack_bf16(w: torch.Tensor, ld_out: Optional[int] = None, transpose=False, out: Optional[torch.Tensor] = None):
+    """bf16 copy of a 2-D fp32 matrix (optionally transposed) with the leading dimension padded to ld_out."""
+    _chk(w, torch.float32)
+    R, Cc = w.shape
+    rows, cols = (Cc, R) if transpose else (R, Cc)
+    if ld_out is None:
+        ld_out = (cols + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((rows, ld_out), device=w.device, dtype=torch.bfloat16)
+    call("pcaa_pack_bf16", _p(w), R, Cc, w.stride(0), _p(out), ld_out, 1 if transpose else 0, _s())
+    return out
+
+
+def tcn_im2col(x, dil: int):
+    _chk(x, torch.float32)
+    B, T, Cin = x.shape
+    col = torch.empty((B * T, Cin * 3), device=x.device, dtype=torch.float32)
+    call("pcaa_tcn_im2col", _p(x), _p(col), B, T, Cin, dil, _s())
+    return col
+
+
+def tcn_col2im(dcol, B: int, T: int, Cin: int, dil: int):
+    dx = torch.empty((B, T, Cin), device=dcol.device, dtype=torch.float32)
+    call("pcaa_tcn_col2im", _p(dcol), _p(dx), B, T, Cin, dil, _s())
+    return dx
+
+
+def mean_rows(x):
+    _chk(x, torch.float32)
+    G, n, Cc = x.shape
+    out = torch.empty((G, Cc), device=x.device, dtype=torch.float32)
+    call("pcaa_mean_rows", _p(x), _p(out), G, n, Cc, _s())
+    return out
+
+
+def mean_rows_bwd(g, n: int):
+    _chk(g, torch.float32)
+    G, Cc = g.shape
+    dx = torch.empty((G, n, Cc), device=g.device, dtype=torch.float32)
+    call("pcaa_mean_rows_bwd", _p(g), _p(dx), G, n, Cc, _s())
+    return dx
+
+
+def softmax_ce(logits, gt, want_grad=True, gscale: float = 1.0):
+    _chk(logits, torch.float32), _chk(gt, torch.int64)
+    B, Cc = logits.shape
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    dl = torch.empty_like(logits) if want_grad else None
+    pred = torch.empty(B, device=logits.device, dtype=torch.int32)
+    call("pcaa_softmax_ce", _p(logits), _p(gt), _p(loss), _p(dl), gscale, _p(pred), B, Cc, _s())
+    return loss, dl, pred
+
+
+# ------------------------------------------------------------------------------------------------ PointNet layer 1
+def pointnet_l1_fwd(x, w, bias, want_stats=True):
+    _chk(x, torch.float32), _chk(w, torch.float32)
+    B, F, T, N = x.shape
+    Cout = w.shape[0]
+    y = torch.empty((B * T * N, Cout), device=x.device, dtype=torch.bfloat16)
+    stats = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64) if want_stats else None
+    call("pcaa_pointnet_l1_fwd", _p(x), _p(w), _p(bias), _p(y), _p(stats), B, T * N, Cout, _s())
+    return y, stats
+
+
+def pointnet_l1_wgrad(x, dy, out: Optional[torch.Tensor] = None):
+    B, F, T, N = x.shape
+    Cout = dy.shape[1]
+    if out is None:
+        out = torch.empty((Cout, 4), device=x.device, dtype=torch.float32)
+    call("pcaa_pointnet_l1_wgrad", _p(x), _p(dy), _p(out), B, T * N, Cout, _s())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core GEMMs
+def gemm_tc_tn(a, w, mode: int, *, bias=None, stats=None, yprev=None, coef=None, out=None):
+    """out[M,N] (bf16) = epilogue(a[M,K] @ w[N,K]^T); tcgen05 kernel (see include/pcaa.h for the modes)."""
+    _chk(a, torch.bfloat16), _chk(w, torch.bfloat16)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+    sc = sh = mu = inv = None
+    if coef is not None:
+        sc, sh, mu, inv = coef[0], coef[1], coef[2], coef[3]
+    call("pcaa_gemm_tc_tn", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, mode, _p(bias),
+         _p(stats), _p(yprev), _p(sc), _p(sh), _p(mu), _p(inv), _s())
+    return out
+
+
+def gemm_tc_nt_wgrad(a, b, dW):
+    """dW[N1,N2] (fp32) += a[K,N1]^T @ b[K,N2]  (bf16 operands, K = number of rows)."""
+    _chk(a, torch.bfloat16), _chk(b, torch.bfloat16), _chk(dW, torch.float32)
+    K, N1 = a.shape
+    N2 = b.shape[1]
+    call("pcaa_gemm_tc_nt_wgrad", _p(a), a.stride(0), _p(b), b.stride(0), _p(dW), dW.stride(0), N1, N2, K, _s())
+    return dW
+
+
+# ------------------------------------------------------------------------------------------------ Chamfer
+def chamfer_fwd(preds, gts, want_idx=True):
+    _chk(preds, torch.float32), _chk(gts, torch.float32)
+    B, F, T, N = preds.shape
+    fl = torch.empty((B, T), device=preds.device, dtype=torch.float32)
+    i1 = torch.empty((B, T, N), device=preds.device, dtype=torch.int32) if want_idx else None
+    i2 = torch.empty((B, T, N), device=preds.device, dtype=torch.int32) if want_idx else None
+    call("pcaa_chamfer_fwd", _p(preds), _p(gts), B, F, T, N, _p(fl), _p(i1), _p(i2), _s())
+    return fl, i1, i2
+
+
+def chamfer_reduce(frame_loss, avg_out=True):
+    B, T = frame_loss.shape
+    out = torch.empty(() if avg_out else (B,), device=frame_loss.device, dtype=torch.float32)
+    call("pcaa_chamfer_reduce", _p(frame_loss), B, T, 1 if avg_out else 0, _p(out), _s())
+    return out
+
+
+def chamfer_bwd(preds, gts, i1, i2, gout, avg_out=True):
+    B, F, T, N = preds.shape
+    g = torch.empty_like(preds)
+    call("pcaa_chamfer_bwd", _p(preds), _p(gts), _p(i1), _p(i2), _p(gout), 1 if avg_out else 0, B, F, T, N, _p(g), _s())
+    return g
+
+
+# ------------------------------------------------------------------------------------------------ critic
+def wgangp_dstep(fv, z0, means, labels, alphas, W1, b1, W2, b2, W3, b3, gp_weight, grads):
+    """grads = (gW1,gb1,gW2,gb2,gW3,gb3) pre-zeroed fp32 tensors (added to).  Returns losses[4] on device."""
+    B = fv.shape[0]
+    Cc = means.shape[0]
+    losses = torch.empty(4, device=fv.device, dtype=torch.float32)
+    call("pcaa_wgangp_dstep", _p(fv), _p(z0), _p(means), _p(labels), _p(alphas), _p(W1), _p(b1), _p(W2), _p(b2), _p(W3),
+         _p(b3), float(gp_weight), _p(losses), *[_p(g) for g in grads], B, Cc, _s())
+    return losses
+
+
+def disc_fwd(x, labels, W1, b1, W2, b2, W3, b3, n_classes: int, want_out=True, want_dx=False):
+    B = x.shape[0]
+    out = torch.empty((B, 1), device=x.device, dtype=torch.float32) if want_out else None
+    dx = torch.empty((B, 32), device=x.device, dtype=torch.float32) if want_dx else None
+    call("pcaa_disc_fwd", _p(x), _p(labels), _p(W1), _p(b1), _p(W2), _p(b2), _p(W3), _p(b3), _p(out), _p(dx), B,
+         n_classes, _s())
+    return out, dx
+
+
+# ------------------------------------------------------------------------------------------------ Adam / scoring
+def adam_flat(p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0, shadow=None):
+    call("pcaa_adam_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale, _p(shadow), _s())
+
+
+def openset_score(emb, means):
+    _chk(emb, torch.float32), _chk(means, torch.float32)
+    M, D = emb.shape
+    ll = torch.empty(M, device=emb.device, dtype=torch.float64)
+    call("pcaa_openset_score", _p(emb), _p(means), M, means.shape[0], D, _p(ll), _s())
+    return ll
+
+
+def openset_vote(loglik, pred, k: int, log_thr: float, n_labels: int):
+    nw = loglik.numel() // k
+    out = torch.empty(nw, device=loglik.device, dtype=torch.int32)
+    call("pcaa_openset_vote", _p(loglik), _p(pred), nw, k, float(log_thr), n_labels, _p(out), _s())
+    return out
+
+
+def sm_count() -> int:
+    return _lib.load().pcaa_sm_count()

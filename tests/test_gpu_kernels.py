@@ -1,0 +1,356 @@
+"""Parity of every C-ABI kernel against the CPU oracle / explicit fp32 torch-CPU formulas (B200 only)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pcaa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from opensetgaitrecognition_pcaa_b200 import ops as _ops
+    return _ops
+
+
+def cuda(t):
+    return t.cuda().contiguous()
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------ CUDA-core GEMM
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (64, 64, 16), (130, 70, 33), (960, 48, 3072), (5, 18000, 77)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_simt(ops, M, N, K, ta, tb):
+    g = torch.Generator().manual_seed(M * 131 + N * 7 + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (a.t() if ta else a) @ (b.t() if tb else b) + bias
+    out = ops.gemm(cuda(a), cuda(b), trans_a=ta, trans_b=tb, bias=cuda(bias))
+    assert rel_err(out, ref) < 2e-5          # fp32, different summation order only
+    out2 = ops.gemm(cuda(a), cuda(b), trans_a=ta, trans_b=tb, bias=cuda(bias), act=ops.ACT_ELU, out=out.clone(),
+                    accumulate=True)
+    assert rel_err(out2, O.elu(ref) + ref) < 2e-5
+
+
+def test_gemm_simt_bf16_inputs(ops):
+    g = torch.Generator().manual_seed(3)
+    a, b = bf16_round(torch.randn(100, 200, generator=g)), bf16_round(torch.randn(50, 200, generator=g))
+    out = ops.gemm(cuda(a).bfloat16(), cuda(b).bfloat16(), trans_b=True)
+    assert rel_err(out, a @ b.t()) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 GEMMs
+TC_SHAPES = [(128, 256, 64), (6000, 512, 512), (4500, 1024, 512), (1000, 1024, 1024), (300, 512, 72), (129, 264, 520)]
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+def test_gemm_tc_bias_stats(ops, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = bf16_round(torch.randn(M, K, generator=g))
+    w = bf16_round(torch.randn(N, K, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, generator=g)
+    ref = a @ w.t() + bias
+    stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    out = ops.gemm_tc_tn(cuda(a).bfloat16(), cuda(w).bfloat16(), ops._lib.TC_BIAS_STATS, bias=cuda(bias), stats=stats)
+    torch.cuda.synchronize()
+    # bf16 output rounding: relative 2^-8 per element; accumulation is fp32 (tolerance stated: 1e-2 of max |ref|)
+    assert rel_err(out.float(), ref) < 1e-2
+    s = stats.cpu()
+    assert rel_err(s[:N], ref.double().sum(0)) < 1e-4
+    assert rel_err(s[N:], (ref.double() ** 2).sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES[:4])
+def test_gemm_tc_bias_elu_and_plain(ops, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K + 1)
+    a = bf16_round(torch.randn(M, K, generator=g))
+    w = bf16_round(torch.randn(N, K, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, generator=g)
+    out = ops.gemm_tc_tn(cuda(a).bfloat16(), cuda(w).bfloat16(), ops._lib.TC_BIAS_ELU, bias=cuda(bias))
+    assert rel_err(out.float(), O.elu(a @ w.t() + bias)) < 1e-2
+    out = ops.gemm_tc_tn(cuda(a).bfloat16(), cuda(w).bfloat16(), ops._lib.TC_PLAIN)
+    assert rel_err(out.float(), a @ w.t()) < 1e-2
+    # the CUDA-core GEMM on the same device agrees too (full-size on-device comparator)
+    cmp = ops.gemm(cuda(a).bfloat16(), cuda(w).bfloat16(), trans_b=True)
+    assert rel_err(out.float(), cmp) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES[:4])
+def test_gemm_tc_dgrad_elubn(ops, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K + 2)
+    dy = bf16_round(torch.randn(M, K, generator=g))
+    wt = bf16_round(torch.randn(N, K, generator=g) / math.sqrt(K))
+    yprev = bf16_round(torch.randn(M, N, generator=g))
+    coef = torch.stack([1 + 0.1 * torch.randn(N, generator=g), 0.1 * torch.randn(N, generator=g),
+                        0.1 * torch.randn(N, generator=g), 1 + 0.1 * torch.rand(N, generator=g)])
+    z = yprev * coef[0] + coef[1]
+    dz = (dy @ wt.t()) * torch.where(z > 0, torch.ones_like(z), torch.exp(z))
+    xh = (yprev - coef[2]) * coef[3]
+    stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    out = ops.gemm_tc_tn(cuda(dy).bfloat16(), cuda(wt).bfloat16(), ops._lib.TC_DGRAD_ELUBN, stats=stats,
+                         yprev=cuda(yprev).bfloat16(), coef=cuda(coef))
+    assert rel_err(out.float(), dz) < 1e-2
+    s = stats.cpu()
+    assert rel_err(s[:N], dz.double().sum(0)) < 1e-3
+    assert rel_err(s[N:], (dz.double() * xh.double()).sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize("K,N1,N2", [(64, 128, 256), (6000, 512, 512), (4500, 1024, 512), (20000, 1024, 1024), (333, 136, 264)])
+def test_gemm_tc_wgrad(ops, K, N1, N2):
+    g = torch.Generator().manual_seed(K + N1 + N2)
+    a = bf16_round(torch.randn(K, N1, generator=g))
+    b = bf16_round(torch.randn(K, N2, generator=g))
+    dW = torch.zeros(N1, N2, device="cuda")
+    ops.gemm_tc_nt_wgrad(cuda(a).bfloat16(), cuda(b).bfloat16(), dW)
+    ref = a.double().t() @ b.double()
+    assert rel_err(dW, ref) < 1e-4
+    ops.gemm_tc_nt_wgrad(cuda(a).bfloat16(), cuda(b).bfloat16(), dW)      # accumulates
+    assert rel_err(dW, 2 * ref) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm family
+@pytest.mark.parametrize("R,C,dtype", [(960, 16, torch.float32), (6000, 512, torch.bfloat16), (1234, 1024, torch.bfloat16),
+                                        (90, 64, torch.float32)])
+def test_bn_forward_backward(ops, R, C, dtype):
+    g = torch.Generator().manual_seed(R + C)
+    y = torch.randn(R, C, generator=g) * 1.5 + 0.3
+    if dtype == torch.bfloat16:
+        y = bf16_round(y)
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    rm, rv = 0.1 * torch.randn(C, generator=g), 0.5 + torch.rand(C, generator=g)
+    upd = {}
+    yy = y.clone().requires_grad_(True)
+    gg, bb = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = O.batchnorm_rows(yy, gg, bb, rm, rv, True, upd, "")
+    a = O.elu(z)
+    dout = torch.randn(R, C, generator=g)
+    if dtype == torch.bfloat16:
+        dout = bf16_round(dout)
+    a.backward(dout)
+    yd = cuda(y).to(dtype)
+    stats = ops.colstats(yd)
+    rmd, rvd = cuda(rm), cuda(rv)
+    coef = ops.bn_finalize(stats, R, cuda(gamma), cuda(beta), rmd, rvd)
+    out = ops.bn_elu_apply(yd, coef[0], coef[1], out_dtype=torch.float32)
+    assert rel_err(out, a.detach()) < 2e-5
+    assert rel_err(rmd, upd["running_mean"]) < 1e-5 and rel_err(rvd, upd["running_var"]) < 1e-5
+    dz, st2 = ops.elu_bwd_colstats(cuda(dout).to(dtype), yd, coef, dz_dtype=dtype)
+    c, dgamma, dbeta = ops.bn_bwd_finalize(st2, R, coef)
+    dy = ops.bn_bwd_apply(dz, yd, c)
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert rel_err(dy.float(), yy.grad) < tol
+    assert rel_err(dgamma, gg.grad) < (5e-3 if dtype == torch.bfloat16 else 1e-4)
+    assert rel_err(dbeta, bb.grad) < (5e-3 if dtype == torch.bfloat16 else 1e-4)
+    # eval coefficients
+    ce = ops.bn_eval_coeffs(cuda(gamma), cuda(beta), cuda(rm), cuda(rv))
+    oe = ops.bn_elu_apply(yd, ce[0], ce[1], out_dtype=torch.float32)
+    assert rel_err(oe, O.elu(O.batchnorm_rows(y, gamma, beta, rm, rv, False))) < 2e-5
+
+
+@pytest.mark.parametrize("G,n,C", [(120, 50, 1024), (90, 150, 1024), (7, 70, 512)])
+def test_bn_elu_meanpool_and_backward(ops, G, n, C):
+    g = torch.Generator().manual_seed(G + n)
+    y = bf16_round(torch.randn(G * n, C, generator=g))
+    sc, sh = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ref = O.elu(y * sc + sh).reshape(G, n, C).mean(1)
+    out = ops.bn_elu_meanpool(cuda(y).bfloat16(), cuda(sc), cuda(sh), n)
+    assert rel_err(out, ref) < 1e-5
+    gp = torch.randn(G, C, generator=g)
+    coef = torch.stack([sc, sh, 0.05 * torch.randn(C, generator=g), 1 + 0.1 * torch.rand(C, generator=g)])
+    dz, st2 = ops.elu_bwd_colstats(cuda(gp), cuda(y).bfloat16(), cuda(coef), pooled_n=n)
+    z = y * sc + sh
+    dz_ref = (gp / n).repeat_interleave(n, dim=0) * torch.where(z > 0, torch.ones_like(z), torch.exp(z))
+    assert rel_err(dz.float(), dz_ref) < 1e-2
+    assert rel_err(st2[:C], dz_ref.double().sum(0)) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ PointNet layer 1
+@pytest.mark.parametrize("B,N", [(2, 50), (3, 150)])
+def test_pointnet_l1(ops, B, N):
+    x, _ = O.synth_batch(B, N, 2, seed=5)
+    g = torch.Generator().manual_seed(1)
+    w, b = torch.randn(512, 4, generator=g) * 0.5, torch.randn(512, generator=g)
+    x2 = x.permute(0, 2, 3, 1).reshape(-1, 4)
+    ref = x2 @ w.t() + b
+    y, stats = ops.pointnet_l1_fwd(cuda(x), cuda(w), cuda(b))
+    assert rel_err(y.float(), ref) < 1e-2
+    assert rel_err(stats[:512], ref.double().sum(0)) < 1e-4
+    assert rel_err(stats[512:], (ref.double() ** 2).sum(0)) < 1e-4
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    dW = ops.pointnet_l1_wgrad(cuda(x), cuda(dy).bfloat16())
+    assert rel_err(dW, dy.t() @ x2) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ TCN pieces
+@pytest.mark.parametrize("dil", [1, 2, 4])
+def test_tcn_conv_as_gemm(ops, dil):
+    g = torch.Generator().manual_seed(dil)
+    B, T, Cin, Cout = 3, 30, 24, 16
+    x = torch.randn(B, T, Cin, generator=g)
+    w, b = torch.randn(Cout, Cin, 3, generator=g), torch.randn(Cout, generator=g)
+    xx, ww = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = O.causal_dilated_conv(xx, ww, b, dil)
+    col = ops.tcn_im2col(cuda(x), dil)
+    y = ops.gemm(col, cuda(w).reshape(Cout, Cin * 3), trans_b=True, bias=cuda(b))
+    assert rel_err(y, ref.detach().reshape(B * T, Cout)) < 1e-5
+    dy = torch.randn(B, T, Cout, generator=g)
+    ref.backward(dy)
+    dcol = ops.gemm(cuda(dy).reshape(B * T, Cout), cuda(w).reshape(Cout, Cin * 3))
+    dx = ops.tcn_col2im(dcol, B, T, Cin, dil)
+    assert rel_err(dx, xx.grad) < 1e-5
+    dW = ops.gemm(cuda(dy).reshape(B * T, Cout), col, trans_a=True)
+    assert rel_err(dW.reshape(Cout, Cin, 3), ww.grad) < 1e-5
+
+
+def test_small_helpers(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(11, 30, 40, generator=g)
+    assert rel_err(ops.mean_rows(cuda(x)), x.mean(1)) < 1e-6
+    gg = torch.randn(11, 40, generator=g)
+    assert rel_err(ops.mean_rows_bwd(cuda(gg), 30), (gg / 30)[:, None, :].expand(11, 30, 40)) < 1e-6
+    out = O.elu(torch.randn(50, 33, generator=g))
+    dout = torch.randn(50, 33, generator=g)
+    ref = dout * torch.where(out > 0, torch.ones_like(out), out + 1)
+    assert rel_err(ops.elu_bwd_from_out(cuda(dout), cuda(out)), ref) < 1e-6
+    assert rel_err(ops.colsum(cuda(dout)), dout.sum(0)) < 1e-5
+    w = torch.randn(37, 1125, generator=g)
+    pk = ops.pack_bf16(cuda(w), ld_out=1152)
+    assert pk.shape == (37, 1152) and rel_err(pk[:, :1125].float(), bf16_round(w)) == 0 and float(pk[:, 1125:].float().abs().max()) == 0
+    pt = ops.pack_bf16(cuda(w), ld_out=40, transpose=True)
+    assert pt.shape == (1125, 40) and rel_err(pt[:, :37].float(), bf16_round(w.t())) == 0
+    logits = torch.randn(9, 4, generator=g)
+    gt = torch.randint(0, 4, (9,), generator=g)
+    ll = logits.clone().requires_grad_(True)
+    ce = O.cross_entropy(ll, gt)
+    ce.backward()
+    loss, dl, pred = ops.softmax_ce(cuda(logits), cuda(gt))
+    assert abs(float(loss) - float(ce)) < 1e-5 and rel_err(dl, ll.grad) < 1e-5
+    assert torch.equal(pred.cpu().long(), logits.argmax(1))
+
+
+# ------------------------------------------------------------------------------------------------ Chamfer
+def _check_idx(P, idx, ref_idx, dim):
+    """argmins equal, or (listed exception class: fp near-ties) the chosen distances agree to 1e-5 relative."""
+    idx, ref_idx = idx.cpu().long(), ref_idx.long()
+    bad = idx != ref_idx
+    if bad.any():
+        d_ours = torch.gather(P, dim, idx.unsqueeze(dim)).squeeze(dim)
+        d_ref = torch.gather(P, dim, ref_idx.unsqueeze(dim)).squeeze(dim)
+        assert float(((d_ours - d_ref).abs()[bad] / (d_ref.abs()[bad] + 1e-6)).max()) < 1e-4
+    return int(bad.sum())
+
+
+@pytest.mark.parametrize("B,N", [(2, 50), (3, 150), (1, 1), (2, 7)])
+def test_chamfer(ops, B, N):
+    gts, _ = O.synth_batch(B, N, 2, seed=N)
+    g = torch.Generator().manual_seed(N)
+    preds = torch.randn(gts.shape, generator=g) * 0.6
+    pp = preds.clone().requires_grad_(True)
+    loss, i1, i2 = O.chamfer(pp, gts)
+    loss.backward()
+    fl, j1, j2 = ops.chamfer_fwd(cuda(preds), cuda(gts))
+    out = ops.chamfer_reduce(fl, True)
+    assert abs(float(out) - float(loss)) / abs(float(loss)) < 1e-5
+    per = ops.chamfer_reduce(fl, False)
+    assert rel_err(per, O.chamfer(preds, gts, avg_out=False)[0]) < 1e-5
+    P = O.pairwise_dist(gts, preds)
+    nbad = _check_idx(P, j1, i1, 2) + _check_idx(P, j2, i2, 3)
+    assert nbad <= 0.01 * i1.numel()           # duplicated (padded) gt points tie exactly; both sides pick the first
+    grad = ops.chamfer_bwd(cuda(preds), cuda(gts), j1, j2, torch.ones((), device="cuda"), True)
+    if nbad == 0:
+        assert rel_err(grad, pp.grad) < 1e-5
+
+
+def test_chamfer_golden(ops, golden_dir):
+    for name in ("n50_c2_b4", "n70_c4_b3"):
+        gd = np.load(os.path.join(golden_dir, f"modules_{name}.npz"))
+        B, nmax, C, seed = int(gd["B"]), int(gd["nmax"]), int(gd["C"]), int(gd["seed"])
+        pcs, _ = O.synth_batch(B, nmax, C, seed=1234 + seed)
+        rng = np.random.default_rng(77 + seed)
+        pr = torch.from_numpy(rng.normal(0, 0.6, pcs.shape).astype(np.float32))
+        fl, j1, j2 = ops.chamfer_fwd(cuda(pr), cuda(pcs))
+        out = float(ops.chamfer_reduce(fl, True))
+        assert abs(out - float(gd["chamfer2"])) / float(gd["chamfer2"]) < 1e-5
+        P = O.pairwise_dist(pcs, pr)
+        n1 = _check_idx(P, j1, torch.from_numpy(gd["chamfer2_idx_gt_for_pred"].astype(np.int64)), 2)
+        n2 = _check_idx(P, j2, torch.from_numpy(gd["chamfer2_idx_pred_for_gt"].astype(np.int64)), 3)
+        assert n1 + n2 <= 0.002 * j1.numel()
+
+
+# ------------------------------------------------------------------------------------------------ critic
+@pytest.mark.parametrize("B,C", [(4, 2), (16, 4), (37, 8), (300, 4)])
+def test_wgangp_dstep(ops, B, C):
+    g = torch.Generator().manual_seed(B + C)
+    p = {k: v for k, v in O.det_params(C, 50, seed=B).items() if k.startswith("D.")}
+    fv, z0 = torch.randn(B, 32, generator=g), torch.randn(B, 32, generator=g)
+    means = O.sample_distant_points(32, C, 10, 10).float()
+    gt = torch.randint(0, C, (B,), generator=g)
+    alphas = torch.rand(B, 1, generator=g)
+    oh = torch.nn.functional.one_hot(gt, C).float()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    dl, gp = O.d_loss_fn(leaves, fv, z0 + oh @ means, oh, alphas, 15.0)
+    names = list(leaves)
+    ref = dict(zip(names, torch.autograd.grad(dl, [leaves[n] for n in names])))
+    W = [cuda(p[f"D.model.{i}.{s}"]) for i in (0, 2, 4) for s in ("weight", "bias")]
+    grads = [torch.zeros_like(w) for w in W]
+    losses = ops.wgangp_dstep(cuda(fv), cuda(z0), cuda(means), cuda(gt), cuda(alphas), *W, 15.0, grads).cpu()
+    assert abs(float(losses[0]) - float(dl)) < 2e-4 * max(1.0, abs(float(dl)))
+    assert abs(float(losses[1]) - float(gp)) < 2e-4 * max(1.0, abs(float(gp)))
+    for gr, (i, s) in zip(grads, [(i, s) for i in (0, 2, 4) for s in ("weight", "bias")]):
+        r = ref[f"D.model.{i}.{s}"]
+        assert float((gr.cpu() - r).abs().max()) < 2e-4 * (float(r.abs().max()) + 1e-3), (i, s)
+    # critic forward + input gradient
+    x = fv.clone().requires_grad_(True)
+    o = O.disc_forward(p, x, oh)
+    o.sum().backward()
+    out, dx = ops.disc_fwd(cuda(fv), cuda(gt), *W, C, want_dx=True)
+    assert rel_err(out, o.detach()) < 1e-5 and rel_err(dx, x.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ Adam / scoring
+def test_adam_flat(ops):
+    g = torch.Generator().manual_seed(0)
+    n = 100003
+    p, m, v = torch.randn(n, generator=g), torch.zeros(n), torch.zeros(n)
+    pd, md, vd = cuda(p), cuda(m), cuda(v)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    pr = [p.clone()]
+    st = [dict()]
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=g) * 10 ** float(torch.randint(-6, 1, (1,), generator=g))
+        O.adam_update(pr, [gr], st, 1e-4, 0.9, 0.99)
+        ops.adam_flat(pd, cuda(gr), md, vd, 1e-4, 0.9, 0.99, 1e-8, step, 1.0, shadow)
+        assert float((pd.cpu() - pr[0]).abs().max()) < 2e-7
+    assert torch.equal(shadow.cpu(), pd.cpu().bfloat16())
+
+
+def test_openset_scoring(ops, golden_dir):
+    gd = np.load(os.path.join(golden_dir, "scoring.npz"))
+    emb, means = torch.from_numpy(gd["emb"]), torch.from_numpy(gd["means"])
+    ll = ops.openset_score(cuda(emb), cuda(means)).cpu().numpy()
+    ref = O.joint_log_likelihood(gd["emb"], gd["means"])
+    assert np.max(np.abs(ll - ref)) < 1e-9                      # float64 on both sides
+    lik = gd["lik"]
+    nz = lik > 0
+    assert np.max(np.abs(ll[nz] - np.log(lik[nz]))) < 1e-9      # == log of the reference's scipy pdf
+    thr = float(gd["threshold"])
+    preds = torch.from_numpy(gd["preds"].astype(np.int32))
+    C = means.shape[0]
+    for k in (1, 2, 4, 6):
+        n = (len(lik) // k) * k
+        votes = ops.openset_vote(cuda(torch.from_numpy(ll[:n])), cuda(preds[:n]), k, math.log(thr), C).cpu().numpy()
+        assert np.array_equal(votes, gd[f"votes_k{k}"])          # bit-exact integer labels vs the reference
