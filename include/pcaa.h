@@ -51,7 +51,7 @@ int pcaa_gemm_simt(const void* A, int a_dtype, int64_t sam, int64_t sak,
  * mode PCAA_TC_BIAS_STATS : Y = A W^T + bias (bf16 out) and per-column sum / sum-of-squares of the fp32 result
  *                           added to stats[2N] (BatchNorm batch statistics of models.py:29 fused in the epilogue)
  * mode PCAA_TC_BIAS_ELU   : Y = ELU(A W^T + bias)       (eval mode with BatchNorm folded into W, bias)
- * mode PCAA_TC_PLAIN      : Y = A W^T                    (bf16 out)
+ * mode PCAA_TC_PLAIN      : Y = A W^T (+ bias when non-null)  (bf16 out)
  * mode PCAA_TC_DGRAD_ELUBN: dZ = (A W^T) * ELU'(scale*Yprev + shift) (bf16 out) and sum dZ, sum dZ*xhat added to
  *                           stats[2N]  (backward of models.py:33-34 fused in the data-gradient GEMM's epilogue)
  * A [M,K] (lda), W [N,K] (ldw), out [M,N] (ldo); all bf16, leading dims multiples of 8 elements. */
@@ -111,6 +111,12 @@ int pcaa_convert(const void* in, int in_dtype, void* out, int out_dtype, int64_t
 /* out[r, c] (ld_out, bf16) = in[r, c] (ld_in, fp32), or the transpose when transpose != 0; pad columns zeroed */
 int pcaa_pack_bf16(const float* in, int64_t R, int64_t C, int64_t ld_in, void* out, int64_t ld_out, int transpose,
                    pcaa_stream stream);
+/* element-wise family for the twice-differentiable critic path (create_graph=True, PCAA_ablation.py:955-962):
+ * out = a*b | a+b | ELU(a) | ELU'(a) | ELU''(a) | a + b[col]  (b is a row vector of ncols for ADD_ROWVEC; a may be
+ * null = zeros for ADD_ROWVEC, which then broadcasts b over the rows) */
+typedef enum { PCAA_EW_MUL = 0, PCAA_EW_ADD = 1, PCAA_EW_ELU = 2, PCAA_EW_ELU_GRAD = 3, PCAA_EW_ELU_GRAD2 = 4,
+               PCAA_EW_ADD_ROWVEC = 5 } pcaa_ew_op;
+int pcaa_ew(int op, const float* a, const float* b, float* out, int64_t n, int ncols, pcaa_stream stream);
 /* causal dilated Conv1d as GEMM: col[(b,t), ci*3+k] = x[b, t-(2-k)*dil, ci] (0 for negative time), models.py:59-76 */
 int pcaa_tcn_im2col(const float* x, float* col, int64_t B, int T, int Cin, int dil, pcaa_stream stream);
 int pcaa_tcn_col2im(const float* dcol, float* dx, int64_t B, int T, int Cin, int dil, pcaa_stream stream);
@@ -133,6 +139,9 @@ int pcaa_chamfer_bwd(const float* preds, const float* gts, const int32_t* idx_gt
                      const int32_t* idx_pred_for_gt, const float* gout, int avg_out, int64_t B, int F, int T, int N,
                      float* grad_preds, pcaa_stream stream);
 
+/* P[b,t,i,j] of SeqChamferLoss.batch_pairwise_dist(x, y), utils.py:109-132; x, y (B,F,T,N) -> P (B,T,N,N) */
+int pcaa_pairwise_dist(const float* x, const float* y, int64_t B, int F, int T, int N, float* P, pcaa_stream stream);
+
 /* ---- conditional critic (CGDiscriminator, models.py:405-421) and the WGAN-GP step ---------------------------
  * Weights: W1 [64, 32+C], W2 [32,64], W3 [1,32].  labels int64 [B]; one-hot is formed in-kernel.
  * pcaa_wgangp_dstep = PCAA_ablation.py:905-973: z = z0 + means[label]; d_loss = mean D(fv) - mean D(z)
@@ -144,10 +153,12 @@ int pcaa_wgangp_dstep(const float* fv, const float* z0, const float* means, cons
                       const float* W3, const float* b3, float gp_weight, float* losses,
                       float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
                       int64_t B, int C, pcaa_stream stream);
-/* out[b] = D(x_b, onehot(label_b)); dx[b,:] = d out[b] / d x_b (either output may be null) */
+/* out[b] = D(x_b, onehot(label_b)); dx[b,:] = dx_scale * d out[b] / d x_b; out_sum[0] = out_scale * sum_b out[b]
+ * (any of the three outputs may be null).  With dx_scale = out_scale = -ADV_WEIGHT/B this is the generator's
+ * adversarial loss and its gradient w.r.t. the embeddings (PCAA_ablation.py:996-1000). */
 int pcaa_disc_fwd(const float* x, const int64_t* labels, const float* W1, const float* b1, const float* W2,
-                  const float* b2, const float* W3, const float* b3, float* out, float* dx, int64_t B, int C,
-                  pcaa_stream stream);
+                  const float* b2, const float* W3, const float* b3, float* out, float* dx, float dx_scale,
+                  float* out_sum, float out_scale, int64_t B, int C, pcaa_stream stream);
 
 /* ---- Adam, torch.optim.Adam defaults as used at PCAA_ablation.py:821-833 ------------------------------------
  * flat buffers of n floats; step is the 1-based step count; g is multiplied by grad_scale first (1/world for DP);

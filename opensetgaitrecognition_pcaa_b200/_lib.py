@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libpcaa_sm100.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_ELU = 0, 1
+EW_MUL, EW_ADD, EW_ELU, EW_ELU_GRAD, EW_ELU_GRAD2, EW_ADD_ROWVEC = range(6)
 TC_BIAS_STATS, TC_BIAS_ELU, TC_PLAIN, TC_DGRAD_ELUBN = 0, 1, 2, 3
 
 _p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
@@ -43,8 +44,10 @@ SIGNATURES = {
     "pcaa_chamfer_fwd": [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p],
     "pcaa_chamfer_reduce": [_p, _l, _i, _i, _p, _p],
     "pcaa_chamfer_bwd": [_p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _p, _p],
+    "pcaa_pairwise_dist": [_p, _p, _l, _i, _i, _i, _p, _p],
+    "pcaa_ew": [_i, _p, _p, _p, _l, _i, _p],
     "pcaa_wgangp_dstep": [_p] * 11 + [_f] + [_p] * 7 + [_l, _i, _p],
-    "pcaa_disc_fwd": [_p] * 10 + [_l, _i, _p],
+    "pcaa_disc_fwd": [_p] * 10 + [_f, _p, _f, _l, _i, _p],
     "pcaa_adam_flat": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _i, _f, _p, _p],
     "pcaa_openset_score": [_p, _p, _l, _i, _i, _p, _p],
     "pcaa_openset_vote": [_p, _p, _l, _i, _d, _i, _p, _p],

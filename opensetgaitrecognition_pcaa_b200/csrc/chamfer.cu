@@ -152,9 +152,60 @@ chamfer_bwd_kernel(const float* __restrict__ preds, const float* __restrict__ gt
     }
 }
 
+// P[b,t,i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  (SeqChamferLoss.batch_pairwise_dist, utils.py:109-132)
+__global__ void __launch_bounds__(256)
+pairwise_dist_kernel(const float* __restrict__ x, const float* __restrict__ y, int F, int T, int N,
+                     float* __restrict__ P) {
+    extern __shared__ float sm[];
+    float* xs = sm;            // [F][N]
+    float* ys = xs + F * N;    // [F][N]
+    float* rx = ys + F * N;
+    float* ry = rx + N;
+    const int bt = blockIdx.x;
+    const int b = bt / T, t = bt % T;
+    const int64_t base = ((int64_t)b * F * T + t) * N;
+    const int64_t fstride = (int64_t)T * N;
+    for (int i = threadIdx.x; i < F * N; i += blockDim.x) {
+        xs[i] = x[base + (i / N) * fstride + (i % N)];
+        ys[i] = y[base + (i / N) * fstride + (i % N)];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float a = 0.f, c = 0.f;
+        for (int f = 0; f < F; ++f) {
+            a = fmaf(xs[f * N + i], xs[f * N + i], a);
+            c = fmaf(ys[f * N + i], ys[f * N + i], c);
+        }
+        rx[i] = a;
+        ry[i] = c;
+    }
+    __syncthreads();
+    float* out = P + (int64_t)bt * N * N;
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        int i = e / N, j = e % N;
+        float zz = 0.f;
+        for (int f = 0; f < F; ++f) zz = fmaf(xs[f * N + i], ys[f * N + j], zz);
+        out[e] = (rx[i] + ry[j]) - 2.f * zz;
+    }
+}
+
 }  // namespace pcaa
 
 using namespace pcaa;
+
+extern "C" int pcaa_pairwise_dist(const float* x, const float* y, int64_t B, int F, int T, int N, float* P,
+                                  pcaa_stream stream) {
+    PCAA_REQUIRE(F >= 1 && F <= MAXF && N >= 1 && N <= 2048, PCAA_ERR_SHAPE, "pairwise_dist: unsupported F=%d N=%d", F, N);
+    if (B * T == 0) return PCAA_OK;
+    size_t smem = (size_t)(2 * F * N + 2 * N) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(pairwise_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr = true;
+    }
+    pairwise_dist_kernel<<<(unsigned)(B * T), 256, smem, (cudaStream_t)stream>>>(x, y, F, T, N, P);
+    return check_launch("pairwise_dist");
+}
 
 extern "C" int pcaa_chamfer_fwd(const float* preds, const float* gts, int64_t B, int F, int T, int N, float* frame_loss,
                                 int32_t* idx_gt_for_pred, int32_t* idx_pred_for_gt, pcaa_stream stream) {

@@ -503,6 +503,27 @@ __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict_
     }
 }
 
+// tiny element-wise family used by the twice-differentiable critic path (models.CGDiscriminator under
+// torch.autograd.grad(create_graph=True), reference PCAA_ablation.py:955-962)
+__global__ void ew_kernel(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                          int64_t n, int ncols) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float x = a ? a[i] : 0.f, r;
+        switch (op) {
+            case PCAA_EW_MUL: r = x * b[i]; break;
+            case PCAA_EW_ADD: r = x + b[i]; break;
+            case PCAA_EW_ELU: r = elu_f(x); break;
+            case PCAA_EW_ELU_GRAD: r = x > 0.f ? 1.f : expf(x); break;
+            case PCAA_EW_ELU_GRAD2: r = x > 0.f ? 0.f : expf(x); break;
+            case PCAA_EW_ADD_ROWVEC: r = x + b[i % ncols]; break;
+            default: r = x;
+        }
+        out[i] = r;
+    }
+}
+
 // ---- PointNet layer 1 -------------------------------------------------------------------------------------
 // block: (Cout/8) channel groups x PL point lanes (256 threads for Cout = 512 -> 64 x 4)
 template <int PL>
@@ -804,6 +825,13 @@ int pcaa_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, floa
                                                              (float)(1.0 / sqrt(bc2)), grad_scale,
                                                              (__nv_bfloat16*)shadow_bf16);
     return check_launch("adam_flat");
+}
+
+int pcaa_ew(int op, const float* a, const float* b, float* out, int64_t n, int ncols, pcaa_stream stream) {
+    if (n == 0) return PCAA_OK;
+    PCAA_REQUIRE(op >= 0 && op <= PCAA_EW_ADD_ROWVEC, PCAA_ERR_UNSUPPORTED, "ew: unknown op %d", op);
+    ew_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(op, a, b, out, n, ncols > 0 ? ncols : 1);
+    return check_launch("ew");
 }
 
 int pcaa_pointnet_l1_fwd(const float* x, const float* w, const float* bias, void* y, double* stats, int64_t B,

@@ -286,7 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool row_ok = row < p.M;
             const int buf = it & 1;
             // stage the per-column parameters of this tile
-            if constexpr (MODE == MODE_BIAS_STATS || MODE == MODE_BIAS_ELU) {
+            if constexpr (MODE == MODE_BIAS_STATS || MODE == MODE_BIAS_ELU || MODE == MODE_PLAIN) {
                 for (int c = et; c < BN; c += EPI_THREADS) colp[c] = (n0 + c < p.N && p.bias) ? p.bias[n0 + c] : 0.f;
             }
             if constexpr (MODE == MODE_DGRAD_ELUBN) {
@@ -319,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else {
                     float s2v[32];
-                    if constexpr (MODE == MODE_BIAS_STATS) {
+                    if constexpr (MODE == MODE_BIAS_STATS || MODE == MODE_PLAIN) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             v[j] += colp[c * 32 + j];

@@ -229,8 +229,8 @@ wgangp_dstep_kernel(const float* __restrict__ fv, const float* __restrict__ z0, 
 
 __global__ void __launch_bounds__(NT)
 disc_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels, const float* W1, const float* b1,
-                const float* W2, const float* b2, const float* W3, const float* b3, float* out, float* dx, int B, int C,
-                int spb) {
+                const float* W2, const float* b2, const float* W3, const float* b3, float* out, float* dx,
+                float dx_scale, float* out_sum, float out_scale, int B, int C, int spb) {
     extern __shared__ float smem[];
     const int D = XD + C;
     CriticSmem m = carve(smem, D);
@@ -238,6 +238,7 @@ disc_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels,
     __syncthreads();
     const float bias3 = b3[0];
     const int t = threadIdx.x;
+    float acc = 0.f;
     int s0 = blockIdx.x * spb, s1 = min(B, s0 + spb);
     for (int s = s0; s < s1; ++s) {
         const int lab = (int)labels[s];
@@ -246,12 +247,14 @@ disc_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels,
         critic_forward(m, D);
         float o = critic_output(m, bias3);
         if (out && t == 0) out[s] = o;
+        acc += o;
         if (dx) {
             critic_input_grad(m, D);
-            if (t < XD) dx[s * XD + t] = m.gx[t];
+            if (t < XD) dx[s * XD + t] = dx_scale * m.gx[t];
         }
         __syncthreads();
     }
+    if (out_sum && t == 0) atomicAdd(out_sum, out_scale * acc);
 }
 
 }  // namespace pcaa
@@ -283,8 +286,8 @@ extern "C" int pcaa_wgangp_dstep(const float* fv, const float* z0, const float* 
 }
 
 extern "C" int pcaa_disc_fwd(const float* x, const int64_t* labels, const float* W1, const float* b1, const float* W2,
-                             const float* b2, const float* W3, const float* b3, float* out, float* dx, int64_t B, int C,
-                             pcaa_stream stream) {
+                             const float* b2, const float* W3, const float* b3, float* out, float* dx, float dx_scale,
+                             float* out_sum, float out_scale, int64_t B, int C, pcaa_stream stream) {
     PCAA_REQUIRE(B > 0 && C > 0 && C <= 32, PCAA_ERR_SHAPE, "disc_fwd: need 0 < C <= 32 (got %d), B > 0", C);
     cudaStream_t st = (cudaStream_t)stream;
     int D = XD + C;
@@ -297,6 +300,8 @@ extern "C" int pcaa_disc_fwd(const float* x, const int64_t* labels, const float*
     int spb = (int)((B + 147) / 148);
     if (spb < 1) spb = 1;
     int grid = (int)((B + spb - 1) / spb);
-    disc_fwd_kernel<<<grid, NT, smem, st>>>(x, labels, W1, b1, W2, b2, W3, b3, out, dx, (int)B, C, spb);
+    if (out_sum) cudaMemsetAsync(out_sum, 0, sizeof(float), st);
+    disc_fwd_kernel<<<grid, NT, smem, st>>>(x, labels, W1, b1, W2, b2, W3, b3, out, dx, dx_scale, out_sum, out_scale,
+                                           (int)B, C, spb);
     return check_launch("disc_fwd");
 }

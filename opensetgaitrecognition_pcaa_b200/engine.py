@@ -1,0 +1,247 @@
+"""Block-level forward / backward of the PCAA networks on top of the C-ABI kernels.
+
+Everything here is orchestration: which kernel runs on which buffer.  Parameters come as dicts keyed with the
+reference's ``state_dict`` names (relative to the module: e.g. ``pc_block.pointnet2.module.0.weight``), so the same
+functions serve the drop-in ``nn.Module``s (models.py) and the fused trainer (train.py).
+
+Layouts: point activations are channels-last bf16 ``[B*T*N, C]`` (rows ordered (b, t, n)); TCN / head / decoder
+activations are fp32 ``[rows, C]``.  Reference: models.py:82-160, 232-292, 340-385.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from ._lib import ACT_ELU, ACT_NONE, TC_BIAS_STATS, TC_DGRAD_ELUBN, TC_PLAIN
+
+T_STEPS = 30
+DTC_DILATIONS = (1, 2, 4, 1, 2, 4)
+BN_MOMENTUM = 0.1
+BN_EPS = 1e-5
+
+Params = Dict[str, torch.Tensor]
+Grads = Dict[str, torch.Tensor]
+
+
+def _out(gradbuf: Optional[Grads], name: str):
+    return None if gradbuf is None else gradbuf.get(name)
+
+
+def _zeros_like_param(gradbuf, name, ref):
+    t = _out(gradbuf, name)
+    if t is None:
+        return torch.zeros_like(ref)
+    t.zero_()
+    return t
+
+
+# ====================================================================================================== PointNet
+def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_block."):
+    """x (B,4,T,N) fp32 -> pooled [B*T, 1024] fp32 (mean over the N points of ELU(BN(conv))), saved state."""
+    B, F, T, N = x.shape
+    R = B * T * N
+    sv = {"x": x, "N": N, "R": R, "y": [None] * 5, "a": [None] * 5, "coef": [None] * 5}
+
+    def bn_coef(l, stats):
+        k = f"{pre}pointnet{l}.module.1."
+        if training:
+            return ops.bn_finalize(stats, R, P[k + "weight"], P[k + "bias"], P[k + "running_mean"], P[k + "running_var"],
+                                   BN_MOMENTUM, BN_EPS)
+        return ops.bn_eval_coeffs(P[k + "weight"], P[k + "bias"], P[k + "running_mean"], P[k + "running_var"], BN_EPS)
+
+    k1 = f"{pre}pointnet1.module.0."
+    w1 = P[k1 + "weight"].view(P[k1 + "weight"].shape[0], 4)
+    y, st = ops.pointnet_l1_fwd(x, w1, P[k1 + "bias"], want_stats=training)
+    coef = bn_coef(1, st)
+    sv["y"][1], sv["coef"][1] = y, coef
+    a = ops.bn_elu_apply(y, coef[0], coef[1])
+    sv["a"][1] = a
+    for l in (2, 3, 4):
+        k = f"{pre}pointnet{l}.module.0."
+        W = P[k + "weight"]
+        wb = ops.pack_bf16(W.view(W.shape[0], W.shape[1]))
+        if training:
+            st = torch.zeros(2 * W.shape[0], device=x.device, dtype=torch.float64)
+            y = ops.gemm_tc_tn(a, wb, TC_BIAS_STATS, bias=P[k + "bias"], stats=st)
+        else:
+            st = None
+            y = ops.gemm_tc_tn(a, wb, TC_PLAIN, bias=P[k + "bias"])
+        coef = bn_coef(l, st)
+        sv["y"][l], sv["coef"][l] = y, coef
+        if l < 4:
+            a = ops.bn_elu_apply(y, coef[0], coef[1])
+            sv["a"][l] = a
+    pooled = ops.bn_elu_meanpool(y, coef[0], coef[1], N)
+    return pooled, sv
+
+
+def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = None,
+                      pre: str = "pc_block.") -> Grads:
+    """gpool [B*T, 1024] fp32 = d loss / d pooled.  Returns parameter gradients (written into gradbuf when given)."""
+    G: Grads = {}
+    R, N = sv["R"], sv["N"]
+    dz, st2 = ops.elu_bwd_colstats(gpool, sv["y"][4], sv["coef"][4], pooled_n=N)
+    for l in (4, 3, 2):
+        kb = f"{pre}pointnet{l}.module.1."
+        kc = f"{pre}pointnet{l}.module.0."
+        c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][l], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
+        G[kb + "weight"], G[kb + "bias"] = dgam, dbet
+        dy = ops.bn_bwd_apply(dz, sv["y"][l], c, out=dz)
+        W = P[kc + "weight"]
+        dW = _zeros_like_param(gradbuf, kc + "weight", W)
+        ops.gemm_tc_nt_wgrad(dy, sv["a"][l - 1], dW.view(W.shape[0], W.shape[1]))
+        G[kc + "weight"] = dW
+        # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero
+        G[kc + "bias"] = _zeros_like_param(gradbuf, kc + "bias", P[kc + "bias"])
+        wT = ops.pack_bf16(W.view(W.shape[0], W.shape[1]), transpose=True)          # [Cin, Cout]
+        st2 = torch.zeros(2 * W.shape[1], device=gpool.device, dtype=torch.float64)
+        dz = ops.gemm_tc_tn(dy, wT, TC_DGRAD_ELUBN, stats=st2, yprev=sv["y"][l - 1], coef=sv["coef"][l - 1])
+    kb, kc = f"{pre}pointnet1.module.1.", f"{pre}pointnet1.module.0."
+    c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][1], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
+    G[kb + "weight"], G[kb + "bias"] = dgam, dbet
+    dy = ops.bn_bwd_apply(dz, sv["y"][1], c, out=dz)
+    W1 = P[kc + "weight"]
+    o = _out(gradbuf, kc + "weight")
+    dW1 = ops.pointnet_l1_wgrad(sv["x"], dy, None if o is None else o.view(W1.shape[0], 4))
+    G[kc + "weight"] = dW1.view(W1.shape) if o is None else o
+    G[kc + "bias"] = _zeros_like_param(gradbuf, kc + "bias", P[kc + "bias"])
+    return G
+
+
+# ====================================================================================================== TCN
+def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block."):
+    """h [B, T, 1024] fp32 -> [B, T, 512]; causal dilated conv (im2col GEMM) + BatchNorm1d + ELU, six times."""
+    B, T, _ = h.shape
+    R = B * T
+    sv = {"B": B, "T": T, "col": [], "y": [], "coef": [], "cin": []}
+    for l in range(1, 7):
+        k = f"{pre}dtc{l}."
+        W = P[k + "conv1d.weight"]
+        Cout, Cin, _ = W.shape
+        col = ops.tcn_im2col(h, DTC_DILATIONS[l - 1])
+        y = ops.gemm(col, W.view(Cout, Cin * 3), trans_b=True, bias=P[k + "conv1d.bias"])
+        if training:
+            st = ops.colstats(y)
+            coef = ops.bn_finalize(st, R, P[k + "batch_norm.weight"], P[k + "batch_norm.bias"],
+                                   P[k + "batch_norm.running_mean"], P[k + "batch_norm.running_var"], BN_MOMENTUM, BN_EPS)
+        else:
+            coef = ops.bn_eval_coeffs(P[k + "batch_norm.weight"], P[k + "batch_norm.bias"],
+                                      P[k + "batch_norm.running_mean"], P[k + "batch_norm.running_var"], BN_EPS)
+        a = ops.bn_elu_apply(y, coef[0], coef[1])
+        sv["col"].append(col), sv["y"].append(y), sv["coef"].append(coef), sv["cin"].append(Cin)
+        h = a.view(B, T, Cout)
+    return h, sv
+
+
+def tcn_backward(dout: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = None, pre: str = "tc_block."):
+    """dout [B, T, 512] -> (d input [B, T, 1024], parameter gradients)."""
+    G: Grads = {}
+    B, T = sv["B"], sv["T"]
+    R = B * T
+    d = dout.reshape(R, -1)
+    for l in range(6, 0, -1):
+        k = f"{pre}dtc{l}."
+        W = P[k + "conv1d.weight"]
+        Cout, Cin, _ = W.shape
+        y, coef, col = sv["y"][l - 1], sv["coef"][l - 1], sv["col"][l - 1]
+        dz, st2 = ops.elu_bwd_colstats(d, y, coef)
+        c, dgam, dbet = ops.bn_bwd_finalize(st2, R, coef, _out(gradbuf, k + "batch_norm.weight"),
+                                            _out(gradbuf, k + "batch_norm.bias"))
+        G[k + "batch_norm.weight"], G[k + "batch_norm.bias"] = dgam, dbet
+        dy = ops.bn_bwd_apply(dz, y, c, out=dz)
+        o = _out(gradbuf, k + "conv1d.weight")
+        dW = ops.gemm(dy, col, trans_a=True, out=None if o is None else o.view(Cout, Cin * 3))
+        G[k + "conv1d.weight"] = dW.view(W.shape) if o is None else o
+        G[k + "conv1d.bias"] = ops.colsum(dy, _out(gradbuf, k + "conv1d.bias"))
+        dcol = ops.gemm(dy, W.view(Cout, Cin * 3))
+        d = ops.tcn_col2im(dcol, B, T, Cin, DTC_DILATIONS[l - 1]).view(R, Cin)
+    return d.view(B, T, -1), G
+
+
+# ====================================================================================================== Linear+ELU
+def linear_forward(x: torch.Tensor, W: torch.Tensor, b: torch.Tensor, act: int = ACT_ELU) -> torch.Tensor:
+    return ops.gemm(x, W, trans_b=True, bias=b, act=act)
+
+
+def linear_backward(dout: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor], W: torch.Tensor, wname: str,
+                    bname: str, G: Grads, gradbuf: Optional[Grads], need_dx: bool = True, dx_out=None, dx_acc=False):
+    """Backward of out = act(x W^T + b); `out` is the saved OUTPUT when the layer has an ELU, else None."""
+    dz = ops.elu_bwd_from_out(dout, out) if out is not None else dout
+    G[wname] = ops.gemm(dz, x, trans_a=True, out=_out(gradbuf, wname))
+    G[bname] = ops.colsum(dz, _out(gradbuf, bname))
+    if not need_dx:
+        return None
+    return ops.gemm(dz, W, out=dx_out, accumulate=dx_acc)
+
+
+# ====================================================================================================== heads
+def heads_forward(h6: torch.Tensor, P: Params, use_projection_head: bool):
+    """h6 [B, T, 512] -> logits (B,C), sup_fv (B,32) (models.py:284-292)."""
+    g = ops.mean_rows(h6)
+    fv = linear_forward(g, P["MLP_sup1.0.weight"], P["MLP_sup1.0.bias"])
+    hh = linear_forward(fv, P["MLP_head.0.weight"], P["MLP_head.0.bias"]) if use_projection_head else fv
+    logits = linear_forward(hh, P["MLP_sup2.0.weight"], P["MLP_sup2.0.bias"])
+    return logits, fv, {"g": g, "fv": fv, "hh": hh, "logits": logits, "T": h6.shape[1], "head": use_projection_head}
+
+
+def heads_backward(dlogits: Optional[torch.Tensor], dfv_ext: Optional[torch.Tensor], sv, P: Params,
+                   gradbuf: Optional[Grads] = None):
+    """Returns (d h6 [B,T,512], grads).  dfv_ext is the gradient reaching sup_fv from outside the encoder."""
+    G: Grads = {}
+    fv = sv["fv"]
+    dfv = None if dfv_ext is None else dfv_ext.clone()
+    if dlogits is not None:
+        dhh = linear_backward(dlogits, sv["hh"], sv["logits"], P["MLP_sup2.0.weight"], "MLP_sup2.0.weight",
+                              "MLP_sup2.0.bias", G, gradbuf, dx_out=None if sv["head"] else dfv,
+                              dx_acc=(not sv["head"]) and dfv is not None)
+        if sv["head"]:
+            dfv = linear_backward(dhh, fv, sv["hh"], P["MLP_head.0.weight"], "MLP_head.0.weight", "MLP_head.0.bias", G,
+                                  gradbuf, dx_out=dfv, dx_acc=dfv is not None)
+        else:
+            dfv = dhh
+    else:
+        for n in ("MLP_sup2.0.weight", "MLP_sup2.0.bias") + (("MLP_head.0.weight", "MLP_head.0.bias") if sv["head"] else ()):
+            G[n] = _zeros_like_param(gradbuf, n, P[n])
+    dg = linear_backward(dfv, sv["g"], fv, P["MLP_sup1.0.weight"], "MLP_sup1.0.weight", "MLP_sup1.0.bias", G, gradbuf)
+    return ops.mean_rows_bwd(dg, sv["T"]), G
+
+
+# ====================================================================================================== encoder
+def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_head: bool):
+    B, F, T, N = x.shape
+    pooled, sv_p = pointnet_forward(x, P, training)
+    h6, sv_t = tcn_forward(pooled.view(B, T, -1), P, training)
+    logits, fv, sv_h = heads_forward(h6, P, use_projection_head)
+    return logits, fv, (sv_p, sv_t, sv_h)
+
+
+def encoder_backward(dlogits, dfv, saved, P: Params, gradbuf: Optional[Grads] = None) -> Grads:
+    sv_p, sv_t, sv_h = saved
+    dh6, G = heads_backward(dlogits, dfv, sv_h, P, gradbuf)
+    dpool, Gt = tcn_backward(dh6, sv_t, P, gradbuf)
+    G.update(Gt)
+    G.update(pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf))
+    return G
+
+
+# ====================================================================================================== decoder
+def decoder_forward(h: torch.Tensor, P: Params, pre: str = ""):
+    """h [B, input_dim] -> [B, 4*30*nmax] (five Linear layers, ELU after the first four; models.py:373-382)."""
+    acts = [h]
+    x = h
+    for l in range(1, 6):
+        x = linear_forward(x, P[f"{pre}dense{l}.weight"], P[f"{pre}dense{l}.bias"], ACT_ELU if l < 5 else ACT_NONE)
+        acts.append(x)
+    return x, acts
+
+
+def decoder_backward(dout: torch.Tensor, acts, P: Params, gradbuf: Optional[Grads] = None, pre: str = "",
+                     need_dx: bool = True):
+    G: Grads = {}
+    d = dout
+    for l in range(5, 0, -1):
+        d = linear_backward(d, acts[l - 1], acts[l] if l < 5 else None, P[f"{pre}dense{l}.weight"],
+                            f"{pre}dense{l}.weight", f"{pre}dense{l}.bias", G, gradbuf, need_dx=(l > 1 or need_dx))
+    return d, G

@@ -1,0 +1,372 @@
+"""Drop-in replacements of the reference's ``models.py`` classes (same names, constructor arguments,
+sub-module / ``state_dict`` keys and forward signatures), computing through libpcaa_sm100 on a B200.
+
+Reference: models.py:6-34 (PointNetModule), 37-79 (DilTempConv1d), 82-160 (blocks), 232-292 (CGEncoder),
+340-385 (CGDecoder), 405-421 (CGDiscriminator), 424-443 (GaussianMeanLearner).
+
+The torch.nn layer objects are kept purely as parameter / buffer containers (so initialisation, ``.to()``,
+``.parameters()``, ``state_dict()`` and checkpoints interchange with the reference); ``forward`` never calls
+them -- it calls one autograd.Function per network whose forward/backward are sequences of C-ABI kernels
+(engine.py).  CUDA only: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import constants as _c
+from . import engine, ops
+from ._lib import EW_ADD, EW_ADD_ROWVEC, EW_ELU, EW_ELU_GRAD, EW_ELU_GRAD2, EW_MUL
+
+constants = _c.get()
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: the PCAA B200 implementation runs on CUDA tensors only (no CPU fallback)")
+
+
+def _named_tensors(module: torch.nn.Module):
+    d = {k: v for k, v in module.named_parameters()}
+    d.update({k: v for k, v in module.named_buffers()})
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ containers
+class PointNetModule(torch.nn.Module):
+    """Parameter container with the reference layout: module.0 = Conv2d(1x1), module.1 = BatchNorm2d, module.2 = act."""
+
+    def __init__(self, in_chs, out_chs, activation=torch.nn.ELU()):
+        super().__init__()
+        self.module = torch.nn.Sequential(
+            torch.nn.Conv2d(in_chs, out_chs, (1, 1), stride=1, padding="valid", dilation=1),
+            torch.nn.BatchNorm2d(num_features=out_chs),
+            activation,
+        )
+
+    def forward(self, x):
+        raise NotImplementedError("PointNetModule is computed inside CGEncoder's fused path; call the encoder")
+
+
+class DilTempConv1d(torch.nn.Module):
+    def __init__(self, in_chs, out_chs, dilation, kernel_size=3, stride=1, use_bias=True, activation=torch.nn.ELU()):
+        super().__init__()
+        self.padding = int(np.floor((kernel_size - 1) * dilation))
+        self.conv1d = torch.nn.Conv1d(in_chs, out_chs, kernel_size=kernel_size, stride=stride, padding=self.padding,
+                                      dilation=dilation, bias=True)
+        self.activation = activation
+        self.batch_norm = torch.nn.BatchNorm1d(out_chs)
+
+    def forward(self, x):
+        raise NotImplementedError("DilTempConv1d is computed inside CGEncoder's fused path; call the encoder")
+
+
+class PointNetBlock(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        d = constants.POINTNET_OUT_DIM
+        self.pointnet1 = PointNetModule(in_chs=constants.NFEATURES, out_chs=d // 2)
+        self.pointnet2 = PointNetModule(in_chs=d // 2, out_chs=d // 2)
+        self.pointnet3 = PointNetModule(in_chs=d // 2, out_chs=d)
+        self.pointnet4 = PointNetModule(in_chs=d, out_chs=d)
+
+    def forward(self, x):
+        raise NotImplementedError("PointNetBlock is computed inside CGEncoder's fused path; call the encoder")
+
+
+class TemporalConvolutionBlock(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        f = constants.DTC_FILTERS
+        chans = [constants.POINTNET_OUT_DIM] + list(f)
+        for l, dil in enumerate(engine.DTC_DILATIONS, start=1):
+            setattr(self, f"dtc{l}", DilTempConv1d(in_chs=chans[l - 1], out_chs=chans[l], dilation=dil, kernel_size=3))
+
+    def forward(self, x):
+        raise NotImplementedError("TemporalConvolutionBlock is computed inside CGEncoder's fused path")
+
+
+# ------------------------------------------------------------------------------------------------ encoder
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, module, names, *params):
+        P = _named_tensors(module)
+        training = module.training
+        logits, fv, saved = engine.encoder_forward(x, P, training, module.use_projection_head)
+        if training:
+            for k, v in P.items():
+                if k.endswith("num_batches_tracked"):
+                    v.add_(1)
+        ctx.saved, ctx.module, ctx.names = saved, module, names
+        ctx.set_materialize_grads(False)
+        return logits, fv
+
+    @staticmethod
+    def backward(ctx, dlogits, dfv):
+        P = _named_tensors(ctx.module)
+        dlogits = None if dlogits is None else dlogits.contiguous()
+        dfv = None if dfv is None else dfv.contiguous()
+        G = engine.encoder_backward(dlogits, dfv, ctx.saved, P)
+        ctx.saved = None
+        return (None, None, None) + tuple(G[n] for n in ctx.names)
+
+
+class CGEncoder(torch.nn.Module):
+    def __init__(self, n_out_labels, nmax_points=constants.NMAX, use_projection_head=False):
+        super().__init__()
+        self.use_projection_head = use_projection_head
+        self.pc_block = PointNetBlock()
+        self.glob_avg_pool1 = torch.nn.AvgPool2d(kernel_size=(1, nmax_points))
+        self.tc_block = TemporalConvolutionBlock()
+        self.glob_avg_pool2 = torch.nn.AvgPool1d(kernel_size=constants.NSTEPS)
+        self.MLP_sup1 = torch.nn.Sequential(
+            torch.nn.Linear(in_features=constants.DTC_FILTERS[-1], out_features=constants.SUP_LATENT_DIM),
+            torch.nn.ELU(),
+        )
+        head_out = constants.SUP_LATENT_DIM if not use_projection_head else constants.SUP_LATENT_DIM // 2
+        if self.use_projection_head:
+            self.MLP_head = torch.nn.Sequential(
+                torch.nn.Linear(in_features=constants.SUP_LATENT_DIM, out_features=head_out), torch.nn.ELU())
+        self.MLP_sup2 = torch.nn.Sequential(
+            torch.nn.Linear(in_features=head_out, out_features=n_out_labels), torch.nn.ELU())
+        self.nmax_points = nmax_points
+
+    def forward(self, x):
+        _require_cuda(x, "CGEncoder")
+        if x.shape[-1] != self.nmax_points or x.shape[2] != constants.NSTEPS:
+            raise ValueError(f"CGEncoder expects (B,{constants.NFEATURES},{constants.NSTEPS},{self.nmax_points}), got {tuple(x.shape)}")
+        x = x.float().contiguous()
+        names = [k for k, _ in self.named_parameters()]
+        out_classes, sup_fv = _EncoderFn.apply(x, self, names, *[p for _, p in self.named_parameters()])
+        return out_classes, sup_fv
+
+
+# ------------------------------------------------------------------------------------------------ decoder
+class _DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, module, names, *params):
+        P = _named_tensors(module)
+        out, acts = engine.decoder_forward(x, P)
+        ctx.acts, ctx.module, ctx.names = acts, module, names
+        ctx.need_dx = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        P = _named_tensors(ctx.module)
+        dx, G = engine.decoder_backward(dout.contiguous(), ctx.acts, P, need_dx=ctx.need_dx)
+        ctx.acts = None
+        # bn1-4 are constructed but never applied (models.py:353-368 vs 373-385): their gradient stays None
+        return (dx, None, None) + tuple(G.get(n) for n in ctx.names)
+
+
+class CGDecoder(torch.nn.Module):
+    def __init__(self, input_dim=constants.SUP_LATENT_DIM, nmax_points=constants.NMAX):
+        super().__init__()
+        self.decoder_mlp_size = constants.NSTEPS * constants.NFEATURES * nmax_points
+        self.nmax_points = nmax_points
+        self.activation = torch.nn.ELU()
+        s = self.decoder_mlp_size
+        self.dense1 = torch.nn.Linear(in_features=input_dim, out_features=s // 16)
+        self.bn1 = torch.nn.BatchNorm1d(s // 16)
+        self.dense2 = torch.nn.Linear(in_features=s // 16, out_features=s // 8)
+        self.bn2 = torch.nn.BatchNorm1d(s // 8)
+        self.dense3 = torch.nn.Linear(in_features=s // 8, out_features=s // 4)
+        self.bn3 = torch.nn.BatchNorm1d(s // 4)
+        self.dense4 = torch.nn.Linear(in_features=s // 4, out_features=s // 2)
+        self.bn4 = torch.nn.BatchNorm1d(s // 2)
+        self.dense5 = torch.nn.Linear(in_features=s // 2, out_features=s)
+
+    def forward(self, x):
+        _require_cuda(x, "CGDecoder")
+        names = [k for k, _ in self.named_parameters()]
+        out = _DecoderFn.apply(x.float().contiguous(), self, names, *[p for _, p in self.named_parameters()])
+        return out.view(-1, constants.NFEATURES, constants.NSTEPS, self.nmax_points)
+
+
+# ------------------------------------------------------------------------------------------------ critic
+# The unmodified trainers call torch.autograd.grad(D(interp), interp, create_graph=True) and then backpropagate through
+# that gradient (PCAA_ablation.py:955-973), so every Function below has a backward that is itself built from these
+# Functions (closed under differentiation); each one is a single small CUDA kernel.  The fused trainer (train.py) uses
+# the analytic single-kernel pcaa_wgangp_dstep instead.
+class _MatMul(torch.autograd.Function):
+    """op(a) @ op(b) through the CUDA-core GEMM."""
+
+    @staticmethod
+    def forward(ctx, a, b, ta, tb):
+        ctx.save_for_backward(a, b)
+        ctx.ta, ctx.tb = ta, tb
+        return ops.gemm(a, b, trans_a=ta, trans_b=tb)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ta, tb = ctx.ta, ctx.tb
+        g = g.contiguous()
+        if not ta:
+            da = _MatMul.apply(g, b, False, not tb)
+        else:
+            da = _MatMul.apply(b, g, tb, True)
+        if not tb:
+            db = _MatMul.apply(a, g, not ta, False)
+        else:
+            db = _MatMul.apply(g, a, True, ta)
+        return da, db, None, None
+
+
+class _ColSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.rows = x.shape[0]
+        return ops.colsum(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return _BroadcastRows.apply(g, ctx.rows)
+
+
+class _BroadcastRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, rows):
+        return ops.ew(EW_ADD_ROWVEC, None, v.contiguous(), shape=(rows, v.numel()))
+
+    @staticmethod
+    def backward(ctx, g):
+        return _ColSum.apply(g), None
+
+
+class _AddRowVec(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, v):
+        return ops.ew(EW_ADD_ROWVEC, x.contiguous(), v.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, _ColSum.apply(g)
+
+
+class _Mul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return ops.ew(EW_MUL, a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return _Mul.apply(g, b), _Mul.apply(g, a)
+
+
+class _EluD(torch.autograd.Function):
+    """order-th derivative of ELU applied element-wise (order 0 = ELU itself)."""
+
+    @staticmethod
+    def forward(ctx, x, order):
+        ctx.save_for_backward(x)
+        ctx.order = order
+        return ops.ew((EW_ELU, EW_ELU_GRAD, EW_ELU_GRAD2)[min(order, 2)], x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return _Mul.apply(g, _EluD.apply(x, ctx.order + 1)), None
+
+
+class CGDiscriminator(torch.nn.Module):
+    def __init__(self, n_in_labels):
+        super().__init__()
+        self.model = torch.nn.Sequential(
+            torch.nn.Linear(constants.SUP_LATENT_DIM + n_in_labels, 64, bias=True),
+            torch.nn.ELU(),
+            torch.nn.Linear(64, 32, bias=True),
+            torch.nn.ELU(),
+            torch.nn.Linear(32, 1, bias=True),
+        )
+
+    def forward(self, x, label):
+        _require_cuda(x, "CGDiscriminator")
+        h = torch.cat([x, label], dim=-1).float()          # data movement only
+        for i in (0, 2, 4):
+            lin = self.model[i]
+            h = _AddRowVec.apply(_MatMul.apply(h, lin.weight, False, True), lin.bias)
+            if i < 4:
+                h = _EluD.apply(h, 0)
+        return h
+
+
+# ------------------------------------------------------------------------------------------------ variant-1 learner
+class GaussianMeanLearner(torch.nn.Module):
+    """Learned class centroids of ablation variant 1 (models.py:424-443): 3 x (Linear, BatchNorm1d, ELU) + Linear."""
+
+    def __init__(self, n_in_labels):
+        super().__init__()
+        self.model = torch.nn.Sequential(
+            torch.nn.Linear(n_in_labels, 16, bias=True), torch.nn.BatchNorm1d(16), torch.nn.ELU(),
+            torch.nn.Linear(16, 32, bias=True), torch.nn.BatchNorm1d(32), torch.nn.ELU(),
+            torch.nn.Linear(32, 64, bias=True), torch.nn.BatchNorm1d(64), torch.nn.ELU(),
+            torch.nn.Linear(64, constants.SUP_LATENT_DIM, bias=True),
+        )
+
+    def forward(self, x):
+        _require_cuda(x, "GaussianMeanLearner")
+        return _MeanLearnerFn.apply(x.float().contiguous(), self, *[p for _, p in self.named_parameters()])
+
+
+class _MeanLearnerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, module, *params):
+        m = module.model
+        training = module.training
+        sv = []
+        h = x
+        for i in (0, 3, 6):
+            lin, bn = m[i], m[i + 1]
+            y = ops.gemm(h, lin.weight, trans_b=True, bias=lin.bias)
+            if training:
+                coef = ops.bn_finalize(ops.colstats(y), y.shape[0], bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                       engine.BN_MOMENTUM, engine.BN_EPS)
+                bn.num_batches_tracked.add_(1)
+            else:
+                coef = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, engine.BN_EPS)
+            a = ops.bn_elu_apply(y, coef[0], coef[1])
+            sv.append((h, y, coef))
+            h = a
+        out = ops.gemm(h, m[9].weight, trans_b=True, bias=m[9].bias)
+        ctx.sv, ctx.h_last, ctx.module = sv, h, module
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        m = ctx.module.model
+        dout = dout.contiguous()
+        grads = {}
+        grads["9.weight"] = ops.gemm(dout, ctx.h_last, trans_a=True)
+        grads["9.bias"] = ops.colsum(dout)
+        d = ops.gemm(dout, m[9].weight)
+        for idx, i in reversed(list(enumerate((0, 3, 6)))):
+            h_in, y, coef = ctx.sv[idx]
+            dz, st2 = ops.elu_bwd_colstats(d, y, coef)
+            c, dgam, dbet = ops.bn_bwd_finalize(st2, y.shape[0], coef)
+            dy = ops.bn_bwd_apply(dz, y, c, out=dz)
+            grads[f"{i + 1}.weight"], grads[f"{i + 1}.bias"] = dgam, dbet
+            grads[f"{i}.weight"] = ops.gemm(dy, h_in, trans_a=True)
+            grads[f"{i}.bias"] = ops.colsum(dy)
+            d = ops.gemm(dy, m[i].weight)
+        names = [k[len("model."):] for k, _ in ctx.module.named_parameters()]
+        return (d, None) + tuple(grads[n] for n in names)
+
+
+# ------------------------------------------------------------------------------------------------ dead classes
+def _dead(name):
+    class _Dead(torch.nn.Module):
+        def __init__(self, *a, **k):
+            # the reference's un-prefixed Encoder / Decoder / Discriminator read constants.UNSUP_LATENT_DIM, which
+            # does not exist (models.py:202,301,393): constructing them raises AttributeError there too.
+            raise AttributeError("module 'constants' has no attribute 'UNSUP_LATENT_DIM'")
+    _Dead.__name__ = _Dead.__qualname__ = name
+    return _Dead
+
+
+Encoder = _dead("Encoder")
+Decoder = _dead("Decoder")
+Discriminator = _dead("Discriminator")

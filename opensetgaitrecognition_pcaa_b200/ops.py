@@ -276,6 +276,25 @@ def chamfer_bwd(preds, gts, i1, i2, gout, avg_out=True):
     return g
 
 
+def pairwise_dist(x, y):
+    _chk(x, torch.float32), _chk(y, torch.float32)
+    B, F, T, N = x.shape
+    P = torch.empty((B, T, N, N), device=x.device, dtype=torch.float32)
+    call("pcaa_pairwise_dist", _p(x), _p(y), B, F, T, N, _p(P), _s())
+    return P
+
+
+def ew(op: int, a: Optional[torch.Tensor], b: Optional[torch.Tensor] = None, shape=None):
+    """Element-wise kernel family (see pcaa_ew); a, b fp32 contiguous."""
+    ref = a if a is not None else b
+    if shape is None:
+        shape = ref.shape
+    out = torch.empty(shape, device=ref.device, dtype=torch.float32)
+    ncols = shape[-1] if len(shape) else 1
+    call("pcaa_ew", op, _p(a), _p(b), _p(out), out.numel(), ncols, _s())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ critic
 def wgangp_dstep(fv, z0, means, labels, alphas, W1, b1, W2, b2, W3, b3, gp_weight, grads):
     """grads = (gW1,gb1,gW2,gb2,gW3,gb3) pre-zeroed fp32 tensors (added to).  Returns losses[4] on device."""
@@ -287,12 +306,16 @@ def wgangp_dstep(fv, z0, means, labels, alphas, W1, b1, W2, b2, W3, b3, gp_weigh
     return losses
 
 
-def disc_fwd(x, labels, W1, b1, W2, b2, W3, b3, n_classes: int, want_out=True, want_dx=False):
+def disc_fwd(x, labels, W1, b1, W2, b2, W3, b3, n_classes: int, want_out=True, want_dx=False, dx_scale=1.0,
+             want_sum=False, out_scale=1.0):
     B = x.shape[0]
     out = torch.empty((B, 1), device=x.device, dtype=torch.float32) if want_out else None
     dx = torch.empty((B, 32), device=x.device, dtype=torch.float32) if want_dx else None
-    call("pcaa_disc_fwd", _p(x), _p(labels), _p(W1), _p(b1), _p(W2), _p(b2), _p(W3), _p(b3), _p(out), _p(dx), B,
-         n_classes, _s())
+    osum = torch.empty((), device=x.device, dtype=torch.float32) if want_sum else None
+    call("pcaa_disc_fwd", _p(x), _p(labels), _p(W1), _p(b1), _p(W2), _p(b2), _p(W3), _p(b3), _p(out), _p(dx),
+         float(dx_scale), _p(osum), float(out_scale), B, n_classes, _s())
+    if want_sum:
+        return out, dx, osum
     return out, dx
 
 

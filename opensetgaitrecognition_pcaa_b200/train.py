@@ -1,0 +1,186 @@
+"""Fused PCAA (ablation variant 4 = the paper's model) training step on one B200, optionally data-parallel.
+
+Mirrors one iteration of the reference loop ``PCAA_ablation.py:882-1021`` (encoder forward, WGAN-GP critic step,
+decoder + Chamfer + adversarial + cross-entropy generator step, two Adam updates) as a fixed sequence of C-ABI
+kernels with no host synchronisation: losses stay on the device until the caller reads them.
+
+All trainable tensors of the generator side (encoder, decoder projection head, decoder dense layers) are re-pointed
+into ONE flat fp32 buffer (plus flat gradient / Adam-moment buffers), so the optimizer is a single fused kernel and
+the data-parallel gradient exchange is a bucketed NCCL all-reduce over contiguous slices (decoder slice first, while
+the PointNet backward is still running).  ``state_dict()`` of the modules keeps the reference's keys.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import engine, ops
+from ._lib import ACT_ELU
+
+
+class _Flat:
+    """Flat fp32 storage for a list of (name, tensor): parameters become views; same layout for grad / m / v."""
+
+    def __init__(self, named: List, device):
+        self.names, self.slices = [], {}
+        off = 0
+        for name, t in named:
+            n = t.numel()
+            self.names.append(name)
+            self.slices[name] = (off, n, tuple(t.shape))
+            off += (n + 3) // 4 * 4                     # keep every tensor 16-byte aligned
+        self.size = off
+        self.p = torch.zeros(off, device=device, dtype=torch.float32)
+        self.g = torch.zeros(off, device=device, dtype=torch.float32)
+        self.m = torch.zeros(off, device=device, dtype=torch.float32)
+        self.v = torch.zeros(off, device=device, dtype=torch.float32)
+        for name, t in named:
+            o, n, shp = self.slices[name]
+            self.p[o:o + n].copy_(t.detach().reshape(-1))
+            t.data = self.p[o:o + n].view(shp)          # the module parameter now aliases the flat buffer
+        self.step = 0
+
+    def view(self, buf, name):
+        o, n, shp = self.slices[name]
+        return buf[o:o + n].view(shp)
+
+    def span(self, names):
+        """[start, end) of the flat range covered by `names` (must be contiguous in registration order)."""
+        o0 = min(self.slices[n][0] for n in names)
+        o1 = max(self.slices[n][0] + (self.slices[n][1] + 3) // 4 * 4 for n in names)
+        return o0, o1
+
+
+class PCAATrainer:
+    """encoder/decoder/discriminator: the drop-in modules of models.py (CUDA, fp32).
+
+    config keys (reference constants.CONFIG): LR, B1, B2, GP_WEIGHT, ADV_WEIGHT.
+    """
+
+    def __init__(self, encoder, decoder, discriminator, decoder_projection_head, means: torch.Tensor, config: dict,
+                 process_group=None):
+        self.enc, self.dec, self.dis, self.gph = encoder, decoder, discriminator, decoder_projection_head
+        dev = next(encoder.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("PCAATrainer needs CUDA modules (no CPU fallback)")
+        self.dev = dev
+        self.cfg = dict(config)
+        self.means = means.to(dev).float().contiguous()
+        self.C = self.means.shape[0]
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        # ---- flat generator-side parameters: optimizer_G chain order (PCAA_ablation.py:821-826); the decoder's bn1-4
+        # never receive a gradient (models.py:373-385), torch.optim.Adam skips them -> they stay outside the flat range
+        named = [("E." + k, p) for k, p in encoder.named_parameters()]
+        named += [("GPH." + k, p) for k, p in decoder_projection_head.named_parameters()]
+        named += [("G." + k, p) for k, p in decoder.named_parameters() if k.startswith("dense")]
+        self.G = _Flat(named, dev)
+        self.D = _Flat([("D." + k, p) for k, p in discriminator.named_parameters()], dev)
+        self._dec_span = self.G.span([n for n in self.G.names if n.startswith("G.") or n.startswith("GPH.")])
+        self._enc_span = self.G.span([n for n in self.G.names if n.startswith("E.")])
+        self._refresh_views()
+        self._comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self._one = torch.ones((), device=dev, dtype=torch.float32)
+
+    def _refresh_views(self):
+        enc_t = {k: v for k, v in self.enc.named_parameters()}
+        enc_t.update({k: v for k, v in self.enc.named_buffers()})
+        self.P_E = enc_t
+        self.P_G = {k: v for k, v in self.dec.named_parameters()}
+        self.P_GPH = {k: v for k, v in self.gph.named_parameters()}
+        self.gb_E = {k: self.G.view(self.G.g, "E." + k) for k, _ in self.enc.named_parameters()}
+        self.gb_G = {k: self.G.view(self.G.g, "G." + k) for k, _ in self.dec.named_parameters() if k.startswith("dense")}
+        self.gb_GPH = {k: self.G.view(self.G.g, "GPH." + k) for k, _ in self.gph.named_parameters()}
+        self.Dw = [self.D.view(self.D.p, f"D.model.{i}.{s}") for i in (0, 2, 4) for s in ("weight", "bias")]
+        self.Dg = [self.D.view(self.D.g, f"D.model.{i}.{s}") for i in (0, 2, 4) for s in ("weight", "bias")]
+        self._nbt = [v for k, v in self.enc.named_buffers() if k.endswith("num_batches_tracked")]
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _allreduce(self, buf, async_op=False):
+        return torch.distributed.all_reduce(buf, op=torch.distributed.ReduceOp.SUM, group=self.pg, async_op=async_op)
+
+    def step(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """One variant-4 iteration.  pcs (B,4,30,N) fp32, gt (B,) int64, z0 (B,32) ~ N(0,1) and alphas (B,1) ~ U(0,1)
+        are the host RNG draws of PCAA_ablation.py:915-931, 944-948 (already on the device).  Returns device scalars."""
+        cfg = self.cfg
+        B = pcs.shape[0]
+        S = pcs.shape[1] * pcs.shape[2] * pcs.shape[3]
+        gscale = 1.0 / self.world
+        self.enc.train(), self.dec.train(), self.dis.train()
+        # ---- encoder forward (train-mode BatchNorm; running statistics updated in place)
+        logits, fv, saved = engine.encoder_forward(pcs, self.P_E, True, self.enc.use_projection_head)
+        for t in self._nbt:
+            t.add_(1)
+        # ---- critic step (PCAA_ablation.py:900-980), one fused kernel + Adam
+        self.D.g.zero_()
+        d_losses = ops.wgangp_dstep(fv, z0, self.means, gt, alphas.reshape(-1), *self.Dw, cfg["GP_WEIGHT"], self.Dg)
+        if self.world > 1:
+            self._allreduce(self.D.g)
+        self.D.step += 1
+        ops.adam_flat(self.D.p, self.D.g, self.D.m, self.D.v, cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, self.D.step, gscale)
+        # ---- generator step (PCAA_ablation.py:985-1021)
+        h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
+        rec, acts = engine.decoder_forward(h0, self.P_G)
+        rec4 = rec.view(pcs.shape)
+        frame_loss, i1, i2 = ops.chamfer_fwd(rec4, pcs)
+        rec_loss = ops.chamfer_reduce(frame_loss, True)
+        drec = ops.chamfer_bwd(rec4, pcs, i1, i2, self._one, True)
+        adv = -float(cfg["ADV_WEIGHT"]) / B
+        _, dfv, loss_g = ops.disc_fwd(fv, gt, *self.Dw, self.C, want_out=False, want_dx=True, dx_scale=adv,
+                                      want_sum=True, out_scale=adv)           # critic already updated (:996)
+        sup_loss, dlogits, pred = ops.softmax_ce(logits, gt, want_grad=True)
+        # backward: Chamfer -> decoder -> projection head -> (+ adversarial) -> encoder
+        G_unused: Dict[str, torch.Tensor] = {}
+        dh0, _ = engine.decoder_backward(drec.view(B, S), acts, self.P_G, self.gb_G)
+        engine.linear_backward(dh0, fv, h0, self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused, self.gb_GPH,
+                               dx_out=dfv, dx_acc=True)
+        work = None
+        if self.world > 1:
+            # decoder-side gradients (99 % of the bytes) are final: reduce them while the encoder backward runs
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ev)
+                work = self._allreduce(self.G.g[self._dec_span[0]:self._dec_span[1]], async_op=True)
+        engine.encoder_backward(dlogits, dfv, saved, self.P_E, self.gb_E)
+        if self.world > 1:
+            self._allreduce(self.G.g[self._enc_span[0]:self._enc_span[1]])
+            work.wait()
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self.G.step += 1
+        ops.adam_flat(self.G.p, self.G.g, self.G.m, self.G.v, cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, self.G.step, gscale)
+        return {"rec_loss": rec_loss, "d_loss": d_losses[0], "gp": d_losses[1], "loss_g": loss_g, "sup_loss": sup_loss,
+                "pred": pred, "logits": logits, "fv": fv}
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def evaluate(self, pcs: torch.Tensor, gt: torch.Tensor):
+        """Validation pass of PCAA_ablation.py:1046-1064: eval-mode encoder, decoder, Chamfer, CE, argmax."""
+        self.enc.eval(), self.dec.eval()
+        logits, fv, _ = engine.encoder_forward(pcs, self.P_E, False, self.enc.use_projection_head)
+        h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
+        rec, _ = engine.decoder_forward(h0, self.P_G)
+        fl, _, _ = ops.chamfer_fwd(rec.view(pcs.shape), pcs, want_idx=False)
+        ce, _, pred = ops.softmax_ce(logits, gt, want_grad=False)
+        return ops.chamfer_reduce(fl, True), ce, pred
+
+
+def build_variant4(n_classes: int, nmax: int, config: Optional[dict] = None, device="cuda", seed: Optional[int] = None,
+                   process_group=None):
+    """Construct the variant-4 networks exactly as PCAA_ablation.py:764-786 does and wrap them in a PCAATrainer."""
+    from . import models, utils
+    if seed is not None:
+        torch.manual_seed(seed)
+    cfg = dict(LR=1e-4, B1=0.9, B2=0.99, GP_WEIGHT=15, ADV_WEIGHT=1, SUP_LATENT_DIM=32)
+    if config:
+        cfg.update(config)
+    enc = models.CGEncoder(n_out_labels=n_classes, use_projection_head=True, nmax_points=nmax).to(device).float()
+    dec = models.CGDecoder(input_dim=cfg["SUP_LATENT_DIM"] * 2, nmax_points=nmax).to(device).float()
+    dis = models.CGDiscriminator(n_classes).to(device).float()
+    gph = torch.nn.Sequential(torch.nn.Linear(cfg["SUP_LATENT_DIM"], cfg["SUP_LATENT_DIM"] * 2), torch.nn.ELU()).to(device).float()
+    means = utils.sample_distant_points(cfg["SUP_LATENT_DIM"], n_classes, 10, 10).float()
+    return PCAATrainer(enc, dec, dis, gph, means, cfg, process_group)

@@ -1,0 +1,218 @@
+"""Parity of the drop-in modules and of the fused variant-4 train step against the oracle and the golden
+vectors produced by the reference (B200 only).
+
+Stated tolerances.  The PointNet layers run bf16 x bf16 -> fp32 on the tensor cores with bf16 activations, the
+reference is fp32 throughout, so:
+  embeddings / logits      : 3e-2 of max |ref|
+  losses                   : 2e-2 relative
+  gradients (per tensor)   : ||g - g_ref|| / ||g_ref|| <= 6e-2  (encoder), 2e-2 (decoder, fed by bf16-path embeddings)
+  BatchNorm running stats  : 2e-2 of max |ref|
+  post-Adam weights        : every entry within 2*lr*steps (Adam's first steps are ~lr*sign(g); entries whose gradient
+                             is rounding noise may take the other sign), at most 5 % of the entries off by > 5e-6
+  class predictions        : exact, except samples whose top-2 logit gap is below the logit tolerance (listed)
+Conv biases that feed a train-mode BatchNorm have an identically-zero gradient; the reference computes fp32 noise
+there (~1e-9) -- excluded from gradient parity (oracle/gen_golden.py, bn_cancelled_bias).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pcaa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(LR=1e-4, B1=0.9, B2=0.99, GP_WEIGHT=15, ADV_WEIGHT=1)
+
+
+def bn_cancelled_bias(name):
+    return name.endswith("module.0.bias") or name.endswith("conv1d.bias")
+
+
+def relmax(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def relnorm(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def build(p, C, nmax):
+    from opensetgaitrecognition_pcaa_b200 import models
+    enc = models.CGEncoder(n_out_labels=C, use_projection_head=True, nmax_points=nmax)
+    dec = models.CGDecoder(input_dim=64, nmax_points=nmax)
+    dis = models.CGDiscriminator(C)
+    gph = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ELU())
+    for pre, m in (("E.", enc), ("G.", dec), ("D.", dis), ("GPH.", gph)):
+        m.load_state_dict({k[len(pre):]: v.clone() for k, v in p.items() if k.startswith(pre)})   # reference keys
+        m.cuda().float()
+    return enc, dec, dis, gph
+
+
+def test_state_dict_keys_match_reference_shapes():
+    p = O.det_params(4, 150, 0)
+    enc, dec, dis, gph = build(p, 4, 150)
+    for pre, m in (("E.", enc), ("G.", dec), ("D.", dis)):
+        sd = m.state_dict()
+        want = {k[len(pre):]: tuple(v.shape) for k, v in p.items() if k.startswith(pre)}
+        assert {k: tuple(v.shape) for k, v in sd.items()} == want
+
+
+@pytest.mark.parametrize("name", ["n50_c2_b4", "n70_c4_b3"])
+def test_modules_vs_reference_golden(golden_dir, name):
+    from opensetgaitrecognition_pcaa_b200 import utils
+    gd = np.load(os.path.join(golden_dir, f"modules_{name}.npz"))
+    B, nmax, C, seed = int(gd["B"]), int(gd["nmax"]), int(gd["C"]), int(gd["seed"])
+    p = O.det_params(C, nmax, seed)
+    pcs, gt = O.synth_batch(B, nmax, C, seed=1234 + seed)
+    enc, dec, dis, gph = build(p, C, nmax)
+    x = pcs.cuda()
+    # eval mode first (running stats untouched)
+    enc.eval()
+    with torch.no_grad():
+        lg, fv = enc(x)
+    assert relmax(lg, torch.from_numpy(gd["enc_eval_logits"])) < 3e-2
+    assert relmax(fv, torch.from_numpy(gd["enc_eval_fv"])) < 3e-2
+    # decoder + Chamfer on the reference's own embeddings (isolates the fp32 decoder path)
+    fv_ref = torch.from_numpy(gd["enc_eval_fv"]).cuda()
+    with torch.no_grad():
+        rec = dec(gph[1](torch.nn.functional.linear(fv_ref, gph[0].weight, gph[0].bias)))   # tiny host-side glue
+        loss = utils.SeqChamferLoss()(rec, x)
+        per = utils.SeqChamferLoss()(rec, x, avg_out=False)
+    assert rec.shape == (B, 4, 30, nmax)
+    assert relmax(rec[:, :, :2, :8], torch.from_numpy(gd["rec_head"])) < 1e-4
+    assert abs(float(loss) - float(gd["chamfer"])) / float(gd["chamfer"]) < 1e-4
+    assert relmax(per, torch.from_numpy(gd["chamfer_per_sample"])) < 1e-4
+    oh = torch.nn.functional.one_hot(gt, C).float().cuda()
+    with torch.no_grad():
+        d = dis(fv_ref, oh)
+    assert relmax(d, torch.from_numpy(gd["disc_out"])) < 1e-4
+    # train mode: batch statistics + running-stat update
+    enc.train()
+    lg, fv = enc(x)
+    assert relmax(lg, torch.from_numpy(gd["enc_train_logits"])) < 3e-2
+    assert relmax(fv, torch.from_numpy(gd["enc_train_fv"])) < 3e-2
+    sd = enc.state_dict()
+    for k in gd.files:
+        if k.startswith("run:E."):
+            assert relmax(sd[k[len("run:E."):]], torch.from_numpy(gd[k])) < 2e-2, k
+    assert int(sd["pc_block.pointnet1.module.1.num_batches_tracked"]) == 1
+    # pairwise distance matrix of the API surface
+    P = utils.SeqChamferLoss().batch_pairwise_dist(x, rec)
+    assert relmax(P, O.pairwise_dist(pcs, rec.cpu())) < 1e-5
+
+
+def _oracle_step(p, ost, pcs, gt, z0, alphas, means, nmax):
+    return O.train_step_variant4(p, ost, pcs, gt, z0, alphas, means, dict(CFG, NMAX=nmax))
+
+
+@pytest.mark.parametrize("name", ["n50_c2_b4", "n150_c4_b2"])
+def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
+    from opensetgaitrecognition_pcaa_b200.train import PCAATrainer
+    gd = np.load(os.path.join(golden_dir, f"step_{name}.npz"))
+    B, nmax, C, seed, nsteps = (int(gd[k]) for k in ("B", "nmax", "C", "seed", "nsteps"))
+    p = O.det_params(C, nmax, seed)
+    po = {k: v.clone() for k, v in p.items()}
+    enc, dec, dis, gph = build(p, C, nmax)
+    means = torch.from_numpy(gd["means"])
+    tr = PCAATrainer(enc, dec, dis, gph, means, CFG)
+    ost = {}
+    rng = np.random.default_rng(999 + seed)
+    for s in range(nsteps):
+        pcs, gt = O.synth_batch(B, nmax, C, seed=4321 + 10 * seed + s)
+        z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float()
+        alphas = torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32))
+        ref = _oracle_step(po, ost, pcs, gt, z0, alphas, means, nmax)
+        out = tr.step(pcs.cuda(), gt.cuda(), z0.cuda(), alphas.cuda())
+        torch.cuda.synchronize()
+        # losses: oracle and the reference's golden values
+        for k in ("rec_loss", "d_loss", "sup_loss", "loss_g"):
+            assert abs(float(out[k]) - float(ref[k])) <= 2e-2 * max(1.0, abs(float(ref[k]))), (s, k)
+            assert abs(float(out[k]) - float(gd[f"s{s}:{k}"])) <= 2e-2 * max(1.0, abs(float(gd[f"s{s}:{k}"]))), (s, k)
+        assert relmax(out["fv"], torch.from_numpy(gd[f"s{s}:fv"])) < 3e-2
+        assert relmax(out["logits"], torch.from_numpy(gd[f"s{s}:logits"])) < 3e-2
+        # class predictions: exact unless the reference's top-2 logit gap is inside the logit tolerance
+        lg = ref["logits"]
+        top2 = lg.topk(2, dim=1).values
+        decided = (top2[:, 0] - top2[:, 1]) > 6e-2 * float(lg.abs().max())
+        assert torch.equal(out["pred"].cpu().long()[decided], ref["pred"][decided])
+        # gradients (still in the flat gradient buffers).  Only the first iteration is comparable tensor-by-tensor:
+        # Adam's first update is ~lr*sign(g), so entries whose gradient sign differs between the bf16 path and the
+        # fp32 oracle move 2*lr apart and later iterations are evaluated at (slightly) different weights.
+        for kind, flat in (("g_grads", tr.G), ("d_grads", tr.D)) if s == 0 else ():
+            for n, g_ref in ref[kind].items():
+                if g_ref is None or n not in flat.slices or bn_cancelled_bias(n):
+                    continue
+                g = flat.view(flat.g, n)
+                tol = 6e-2 if n.startswith("E.") or n.startswith("D.") else 2e-2
+                assert relnorm(g, g_ref) < tol, (s, n, relnorm(g, g_ref))
+    # weights after the Adam updates
+    lr = CFG["LR"]
+    nbad = ntot = 0
+    for pre, m in (("E.", enc), ("G.", dec), ("D.", dis), ("GPH.", gph)):
+        for k, v in m.state_dict().items():
+            if not v.dtype.is_floating_point:
+                assert int(v) == int(po[pre + k]), k
+                continue
+            d = (v.detach().cpu().double() - po[pre + k].double()).abs()
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                assert float(d.max()) <= 2e-2 * float(po[pre + k].abs().max()), k
+                continue
+            assert float(d.max()) <= 2 * lr * nsteps * 1.01, (k, float(d.max()))
+            if not bn_cancelled_bias(k):
+                nbad += int((d > 5e-6).sum())
+                ntot += d.numel()
+    assert nbad / ntot < 0.05, nbad / ntot
+
+
+def test_module_autograd_path_matches_oracle():
+    """The nn.Module surface driven the way the reference trainer drives it (stock autograd, torch.optim.Adam,
+    autograd.grad(create_graph=True) through the critic)."""
+    from opensetgaitrecognition_pcaa_b200 import utils
+    B, nmax, C, seed = 4, 50, 2, 0
+    p = O.det_params(C, nmax, seed)
+    enc, dec, dis, gph = build(p, C, nmax)
+    pcs, gt = O.synth_batch(B, nmax, C, seed=4321)
+    rng = np.random.default_rng(999)
+    z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float()
+    alphas = torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32))
+    means = O.sample_distant_points(32, C, 10, 10).float()
+    po = {k: v.clone() for k, v in p.items()}
+    ref = _oracle_step(po, {}, pcs, gt, z0, alphas, means, nmax)
+    x, g = pcs.cuda(), gt.cuda()
+    enc.train(), dec.train(), dis.train()
+    logits, fv = enc(x)
+    oh = torch.nn.functional.one_hot(g, C).float()
+    z = (z0.cuda() + oh @ means.cuda()).requires_grad_(True)
+    real, fake = dis(z, oh), dis(fv.detach(), oh)
+    interp = z + alphas.cuda().repeat(1, 32) * (fv.detach() - z)
+    di = dis(interp, oh)
+    grads = torch.autograd.grad(di, interp, torch.ones_like(di), create_graph=True, retain_graph=True, only_inputs=True)[0]
+    slopes = torch.sqrt(torch.sum(grads ** 2, dim=1) + 1e-12)
+    d_loss = fake.mean() - real.mean() + CFG["GP_WEIGHT"] * ((slopes - 1) ** 2).mean()
+    d_loss.backward()
+    assert abs(float(d_loss) - float(ref["d_loss"])) <= 2e-2 * max(1.0, abs(float(ref["d_loss"])))
+    for n, prm in dis.named_parameters():
+        assert relnorm(prm.grad, ref["d_grads"]["D." + n]) < 6e-2, n
+    optD = torch.optim.Adam(dis.parameters(), lr=CFG["LR"], betas=(CFG["B1"], CFG["B2"]))
+    optD.step()
+    dis.zero_grad()
+    rec = dec(gph(fv))
+    rec_loss = utils.SeqChamferLoss()(rec, x)
+    loss_g = -torch.mean(dis(fv, oh))
+    sup = torch.nn.CrossEntropyLoss()(logits, g)
+    (rec_loss + loss_g + sup).backward()
+    for k, want in (("rec_loss", rec_loss), ("loss_g", loss_g), ("sup_loss", sup)):
+        assert abs(float(want) - float(ref[k])) <= 2e-2 * max(1.0, abs(float(ref[k]))), k
+    for pre, m in (("E.", enc), ("G.", dec), ("GPH.", gph)):
+        for n, prm in m.named_parameters():
+            g_ref = ref["g_grads"][pre + n]
+            if g_ref is None:
+                assert prm.grad is None, n            # decoder bn1-4: never used, grad stays None
+                continue
+            if bn_cancelled_bias(n):
+                continue
+            assert relnorm(prm.grad, g_ref) < (6e-2 if pre == "E." else 2e-2), (pre + n, relnorm(prm.grad, g_ref))
