@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""PCAA hot-path benchmark (BASELINE.json metric: PCAA train samples/s on B200; inference seq/s; % of roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm (oracle port) on the host
+
+One "step" = one full variant-4 AAE iteration (encoder fwd, WGAN-GP critic step, decoder + Chamfer + adversarial +
+CE generator step, both Adam updates; reference PCAA_ablation.py:882-1021) on one batch of synthetic
+mmGait10-shaped crops.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NMAX, NCLS = 150, 4
+METRIC, UNIT = "pcaa_train_samples_per_sec", "samples/s"
+# algorithmic tensor-core work of one train step, per sample (SURVEY.md 8d / DESIGN.md): PointNet layers 2-4,
+# forward + data gradient + weight gradient = 3 x 2 x (512*512 + 512*1024 + 1024*1024) MAC-FLOPs per point,
+# minus the layer-2 data gradient... (layer 2 HAS a data gradient towards layer 1's BatchNorm) -> 3 GEMMs per layer.
+FLOP_PER_POINT_TC = 3 * 2 * (512 * 512 + 512 * 1024 + 1024 * 1024)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])), mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        os.unlink(self.f.name)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------- reference / CPU arm
+def cpu_step_rate(batch: int, steps: int, warmup: int, threads: int):
+    """The reference's algorithm on the host cores (oracle port of PCAA_ablation.py:882-1021), fp32, `threads` threads."""
+    from oracle import pcaa_oracle as O
+    torch.set_num_threads(threads)
+    p = O.det_params(NCLS, NMAX, seed=0)
+    means = O.sample_distant_points(32, NCLS, 10, 10).float()
+    cfg = dict(LR=1e-4, B1=0.9, B2=0.99, GP_WEIGHT=15, ADV_WEIGHT=1, NMAX=NMAX)
+    pcs, gt = O.synth_batch(batch, NMAX, NCLS, seed=1234)
+    rng = np.random.default_rng(0)
+    ost = {}
+    times = []
+    for i in range(warmup + steps):
+        z0 = torch.from_numpy(rng.normal(0, 1, (batch, 32))).float()
+        al = torch.from_numpy(rng.uniform(0, 1, (batch, 1)).astype(np.float32))
+        t0 = time.perf_counter()
+        O.train_step_variant4(p, ost, pcs, gt, z0, al, means, cfg, clone_leaves=False)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return batch / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    b = 32
+    rate, dt = cpu_step_rate(b, max(1, min(args.steps, 3)), 1, threads)
+    sample = f"variant-4 train step, batch {b}, N={NMAX}, C={NCLS}, fp32, 1 warm-up + {max(1, min(args.steps, 3))} timed steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"pcaa_variant4_train_step_N{NMAX}_C{NCLS}", "batch_per_step": b,
+                   "note": "reference algorithm (oracle port of PCAA_ablation.py:882-1021) on the host CPU cores"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- sm_100a arm
+def run_b200(args):
+    from opensetgaitrecognition_pcaa_b200 import _lib, ops, synth
+    from opensetgaitrecognition_pcaa_b200.train import build_variant4
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    trainer = build_variant4(NCLS, NMAX, seed=0, device=dev)
+    if world > 1:
+        # identical replicas: broadcast rank 0's initial weights (flat buffers)
+        torch.distributed.broadcast(trainer.G.p, 0)
+        torch.distributed.broadcast(trainer.D.p, 0)
+        for b in list(trainer.enc.buffers()):
+            torch.distributed.broadcast(b, 0)
+    # distinct synthetic batches (host, pinned), rotated so consecutive steps never see the same input
+    nb = 3
+    host = []
+    rng = np.random.default_rng(100 + rank)
+    for i in range(nb):
+        pcs, gt = synth.synth_batch(B, NMAX, NCLS, seed=1234 + 17 * rank + i)
+        z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float()
+        al = torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32))
+        host.append(tuple(t.pin_memory() for t in (pcs, gt, z0, al)))
+    devb = [tuple(t.to(dev) for t in h) for h in host]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput, with CUDA events around every tensor-core GEMM launch
+    tc_events = []
+    orig_tn, orig_wg = ops.gemm_tc_tn, ops.gemm_tc_nt_wgrad
+    record = {"on": False}
+
+    def timed(fn, flops_of):
+        def w(*a, **k):
+            if not record["on"]:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            tc_events.append((e0, e1, flops_of(*a, **k)))
+            return r
+        return w
+
+    ops.gemm_tc_tn = timed(orig_tn, lambda a, w, *r, **k: 2.0 * a.shape[0] * a.shape[1] * w.shape[0])
+    ops.gemm_tc_nt_wgrad = timed(orig_wg, lambda a, b, dW: 2.0 * a.shape[0] * a.shape[1] * b.shape[1])
+    from opensetgaitrecognition_pcaa_b200 import engine
+    engine.ops = ops
+
+    for i in range(args.warmup):
+        trainer.step(*devb[i % nb])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    calls0 = _lib.CALLS
+    record["on"] = True
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        out = trainer.step(*devb[i % nb])
+    t1.record()
+    barrier()
+    record["on"] = False
+    launches = _lib.CALLS - calls0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = t0.elapsed_time(t1)
+    tc_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in tc_events)
+    tc_flops = sum(f for _, _, f in tc_events)
+
+    # ---- end-to-end through the public API with HOST buffers: H2D of the step inputs + D2H of the losses inside
+    res_host = torch.empty(5, dtype=torch.float32).pin_memory()
+    pred_host = torch.empty(B, dtype=torch.int32).pin_memory()
+    e2e_steps = args.steps
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        h = host[i % nb]
+        d = tuple(t.to(dev, non_blocking=True) for t in h)
+        out = trainer.step(*d)
+        res_host.copy_(torch.stack([out["rec_loss"], out["d_loss"], out["gp"], out["loss_g"], out["sup_loss"]]), non_blocking=True)
+        pred_host.copy_(out["pred"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the reference reads .item() every step (PCAA_ablation.py:1023-1030)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = res_host.numel() * 4 + pred_host.numel() * 4
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * e2e_steps / (ms_e2e * 1e-3)
+    peak_tf, peak_hbm, peak_src = peaks()
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"pcaa_variant4_train_step_N{NMAX}_C{NCLS}", "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}", "l2": "per-step activations (>10 GB) and 3 rotating input batches exceed the 126 MB L2",
+                   "losses_last_step": {k: float(out[k]) for k in ("rec_loss", "d_loss", "sup_loss", "loss_g")}},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                     "kernel": "gemm_tc_kernel (tcgen05 PointNet fwd/dgrad/wgrad GEMMs)",
+                     "launches_timed": len(tc_events), "share_of_step": tc_ms / ms if ms else None, "peak_source": peak_src,
+                     "whole_step_tensor_frac": (world * B * args.steps * 30 * NMAX * FLOP_PER_POINT_TC) / (ms * 1e-3) / 1e12 / (peak_tf * world)},
+    }
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        bc = 32
+        rate, dt = cpu_step_rate(bc, 2, 1, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"oracle port of the variant-4 step, batch {bc}, N={NMAX}, C={NCLS}, fp32, 1 warm-up + 2 timed steps ({dt:.2f} s/step)"}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

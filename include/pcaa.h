@@ -55,7 +55,20 @@ int pcaa_gemm_simt(const void* A, int a_dtype, int64_t sam, int64_t sak,
  * mode PCAA_TC_DGRAD_ELUBN: dZ = (A W^T) * ELU'(scale*Yprev + shift) (bf16 out) and sum dZ, sum dZ*xhat added to
  *                           stats[2N]  (backward of models.py:33-34 fused in the data-gradient GEMM's epilogue)
  * A [M,K] (lda), W [N,K] (ldw), out [M,N] (ldo); all bf16, leading dims multiples of 8 elements. */
-typedef enum { PCAA_TC_BIAS_STATS = 0, PCAA_TC_BIAS_ELU = 1, PCAA_TC_PLAIN = 2, PCAA_TC_DGRAD_ELUBN = 3 } pcaa_tc_mode;
+typedef enum { PCAA_TC_BIAS_STATS = 0, PCAA_TC_BIAS_ELU = 1, PCAA_TC_PLAIN = 2, PCAA_TC_DGRAD_ELUBN = 3,
+               PCAA_TC_WGRAD_ACC = 4, PCAA_TC_DGRAD_ELUOUT = 5, PCAA_TC_WGRAD_STORE = 6 } pcaa_tc_mode;
+/* General form.  out[m,n] = epilogue( sum_k A(m,k) B(n,k) ), bf16 operands, fp32 accumulation in TMEM.
+ * A(m,k) is stored [M,K] (a_mn = 0, "K-major") or [K,M] (a_mn = 1, "MN-major"); B(n,k) is stored [N,K] (b_mn = 0) or
+ * [K,N] (b_mn = 1); leading dimensions in elements, multiples of 8.  out_dtype: PCAA_BF16 or PCAA_F32 (modes 1, 2).
+ * Extra modes: PCAA_TC_WGRAD_ACC   out (fp32) += A B^T, split over k across the SMs (weight gradient, k = rows);
+ *              PCAA_TC_WGRAD_STORE out (fp32)  = A B^T (no split, plain stores: decoder weight gradient, k = batch);
+ *              PCAA_TC_DGRAD_ELUOUT out = (A B^T) * (a > 0 ? 1 : a + 1) with a = yprev [M, ldy] the saved bf16 OUTPUT
+ *                                  of the previous layer's ELU (decoder data gradient, models.py:373-382).
+ * Instantiated layouts: (a_mn,b_mn) = (0,0) modes 0-3; (0,1) modes 2, 5; (1,1) modes 4, 6. */
+int pcaa_gemm_tc(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo,
+                 int out_dtype, int64_t M, int64_t N, int64_t K, int mode, const float* bias, double* stats,
+                 const void* yprev, int64_t ldy, const float* scale, const float* shift, const float* mean,
+                 const float* invstd, pcaa_stream stream);
 int pcaa_gemm_tc_tn(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                     int64_t M, int64_t N, int64_t K, int mode,
                     const float* bias, double* stats,
@@ -107,6 +120,8 @@ int pcaa_bn_bwd_apply(const void* dz, int dz_dtype, const void* y, int y_dtype, 
 /* dz = dout * (out > 0 ? 1 : out + 1): ELU backward from the saved OUTPUT (Linear+ELU heads, decoder) */
 int pcaa_elu_bwd_from_out(const float* dout, const float* out, float* dz, int64_t n, pcaa_stream stream);
 int pcaa_colsum(const float* x, int64_t R, int C, float* out, pcaa_stream stream);
+/* same for a fp32 / bf16 matrix with leading dimension ld (bias gradients of the tensor-core decoder path) */
+int pcaa_colsum_ld(const void* x, int dtype, int64_t R, int C, int64_t ld, float* out, pcaa_stream stream);
 int pcaa_convert(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, pcaa_stream stream);
 /* out[r, c] (ld_out, bf16) = in[r, c] (ld_in, fp32), or the transpose when transpose != 0; pad columns zeroed */
 int pcaa_pack_bf16(const float* in, int64_t R, int64_t C, int64_t ld_in, void* out, int64_t ld_out, int transpose,

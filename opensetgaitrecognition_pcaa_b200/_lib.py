@@ -13,13 +13,14 @@ LIB_PATH = os.path.join(_PKG, "libpcaa_sm100.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_ELU = 0, 1
 EW_MUL, EW_ADD, EW_ELU, EW_ELU_GRAD, EW_ELU_GRAD2, EW_ADD_ROWVEC = range(6)
-TC_BIAS_STATS, TC_BIAS_ELU, TC_PLAIN, TC_DGRAD_ELUBN = 0, 1, 2, 3
+TC_BIAS_STATS, TC_BIAS_ELU, TC_PLAIN, TC_DGRAD_ELUBN, TC_WGRAD_ACC, TC_DGRAD_ELUOUT, TC_WGRAD_STORE = range(7)
 
 _p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 # name -> argument ctypes (return type is always int except the two string getters / sm_count)
 SIGNATURES = {
     "pcaa_gemm_simt": [_p, _i, _l, _l, _p, _i, _l, _l, _p, _i, _l, _l, _l, _l, _l, _p, _i, _i, _p],
+    "pcaa_gemm_tc": [_p, _l, _i, _p, _l, _i, _p, _l, _i, _l, _l, _l, _i, _p, _p, _p, _l, _p, _p, _p, _p, _p],
     "pcaa_gemm_tc_tn": [_p, _l, _p, _l, _p, _l, _l, _l, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "pcaa_gemm_tc_nt_wgrad": [_p, _l, _p, _l, _p, _l, _l, _l, _l, _p],
     "pcaa_pointnet_l1_fwd": [_p, _p, _p, _p, _p, _l, _l, _i, _p],
@@ -34,6 +35,7 @@ SIGNATURES = {
     "pcaa_bn_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _l, _i, _p],
     "pcaa_elu_bwd_from_out": [_p, _p, _p, _l, _p],
     "pcaa_colsum": [_p, _l, _i, _p, _p],
+    "pcaa_colsum_ld": [_p, _i, _l, _i, _l, _p, _p],
     "pcaa_convert": [_p, _i, _p, _i, _l, _p],
     "pcaa_pack_bf16": [_p, _l, _l, _l, _p, _l, _i, _p],
     "pcaa_tcn_im2col": [_p, _p, _l, _i, _i, _i, _p],
@@ -76,8 +78,13 @@ def load() -> C.CDLL:
     return _lib
 
 
+CALLS = 0          # number of C-ABI launches issued by this process (bench.py reports it as gpu_launches)
+
+
 def call(name: str, *args) -> None:
+    global CALLS
     lib = load()
+    CALLS += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (status {rc}): {lib.pcaa_last_error().decode()}")

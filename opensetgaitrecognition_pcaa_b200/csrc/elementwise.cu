@@ -319,12 +319,13 @@ __global__ void elu_bwd_from_out_kernel(const float* __restrict__ dout, const fl
 }
 
 // out[c] = sum_r x[r,c]; one block per 32 columns, 8 row lanes
-__global__ void colsum_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ out) {
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t R, int C, int64_t ld, float* __restrict__ out) {
     __shared__ float sm[8][33];
     int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
     if (c < C)
-        for (int64_t r = threadIdx.y; r < R; r += 8) s += x[r * C + c];
+        for (int64_t r = threadIdx.y; r < R; r += 8) s += ld_as_float<T>(x + r * ld + c);
     sm[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
@@ -756,8 +757,16 @@ int pcaa_elu_bwd_from_out(const float* dout, const float* out, float* dz, int64_
 }
 
 int pcaa_colsum(const float* x, int64_t R, int C, float* out, pcaa_stream stream) {
-    colsum_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, ST(stream)>>>(x, R, C, out);
+    colsum_kernel<float><<<ceil_div(C, 32), dim3(32, 8), 0, ST(stream)>>>(x, R, C, C, out);
     return check_launch("colsum");
+}
+
+int pcaa_colsum_ld(const void* x, int dtype, int64_t R, int C, int64_t ld, float* out, pcaa_stream stream) {
+    if (dtype == PCAA_BF16)
+        colsum_kernel<__nv_bfloat16><<<ceil_div(C, 32), dim3(32, 8), 0, ST(stream)>>>((const __nv_bfloat16*)x, R, C, ld, out);
+    else
+        colsum_kernel<float><<<ceil_div(C, 32), dim3(32, 8), 0, ST(stream)>>>((const float*)x, R, C, ld, out);
+    return check_launch("colsum_ld");
 }
 
 int pcaa_convert(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, pcaa_stream stream) {

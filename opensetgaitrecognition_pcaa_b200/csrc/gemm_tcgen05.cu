@@ -3,7 +3,8 @@
 //
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
-//   warps 2..5  : epilogue (TMEM -> registers -> fused epilogue -> global), one TMEM lane quarter each
+//   warps 2..9  : epilogue (TMEM -> registers -> fused epilogue -> global): two warps per TMEM lane quarter, each
+//                 owning half of the tile's columns
 //
 // Two 128 x BN fp32 accumulators live in TMEM (2*BN <= 512 columns) so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Work items are (m-tile, n-tile, k-split) triples strided over the persistent grid.
@@ -19,17 +20,20 @@ namespace pcaa {
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_THREADS = 256;
 
-enum { MODE_BIAS_STATS = 0, MODE_BIAS_ELU = 1, MODE_PLAIN = 2, MODE_DGRAD_ELUBN = 3, MODE_WGRAD = 4 };
+enum { MODE_BIAS_STATS = 0, MODE_BIAS_ELU = 1, MODE_PLAIN = 2, MODE_DGRAD_ELUBN = 3, MODE_WGRAD = 4, MODE_DGRAD_ELUOUT = 5 };
 
 struct GemmParams {
     int64_t M, N;                 // output extent (rows, cols)
     int m_tiles, n_tiles, k_splits;
     int kb_total, kb_per_split;   // K blocks of BK
-    void* out;                    // bf16 [M, ldo]  or fp32 (MODE_WGRAD)
+    void* out;                    // bf16 [M, ldo]  or fp32 (MODE_WGRAD, or out_f32)
     int64_t ldo;
+    int out_f32;                  // store fp32 instead of bf16 (modes 1, 2)
+    int wgrad_store;              // MODE_WGRAD: overwrite instead of atomicAdd (requires k_splits == 1)
+    int out_scalar;               // fp32 rows are not 16-byte aligned (ldo % 4 != 0): scalar stores
     const float* bias;
     double* stats;                // [2*N]
     const __nv_bfloat16* yprev;   // [M, ldy] (MODE_DGRAD_ELUBN)
@@ -274,8 +278,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ===================================================================== epilogue warps
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const int et = threadIdx.x - 64;                // 0..127
-        float* my_s1 = wstat + (warp - 2) * 2 * BN;
+        const int half = (warp - 2) >> 2;               // which half of the tile's columns this warp owns
+        const int et = threadIdx.x - 64;                // 0..255
+        constexpr int CHUNKS = BN / 32;
+        const int c_begin = half * (CHUNKS / 2), c_end = c_begin + CHUNKS / 2;
+        float* my_s1 = wstat + q * 2 * BN;
         float* my_s2 = my_s1 + BN;
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -298,76 +305,102 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     colp[4 * BN + c] = ok ? p.invstd[n0 + c] : 0.f;
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
+                const int64_t col0 = n0 + c * 32;
+                // previous-layer activation tile (needed by the data-gradient epilogues): issue the loads before
+                // the TMEM read so their latency overlaps it
+                uint4 yraw[4];
+                if constexpr (MODE == MODE_DGRAD_ELUBN || MODE == MODE_DGRAD_ELUOUT) {
+                    const bool ok = row_ok && col0 < p.N;
+                    const uint4* yp = reinterpret_cast<const uint4*>(p.yprev + (ok ? row * p.ldy + col0 : 0));
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) yraw[g] = (ok && col0 + g * 8 < p.N) ? __ldg(yp + g) : make_uint4(0, 0, 0, 0);
+                }
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                const int64_t col0 = n0 + c * 32;
                 if constexpr (MODE == MODE_WGRAD) {
                     if (row_ok) {
                         float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+                        if (p.out_scalar) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (col0 + j < p.N) atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.N) {
+                                    if (p.wgrad_store) o[j] = v[j];
+                                    else atomicAdd(o + j, v[j]);
+                                }
+                        } else if (p.wgrad_store) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (col0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (col0 + j < p.N) atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                        }
                     }
                 } else {
                     float s2v[32];
                     if constexpr (MODE == MODE_BIAS_STATS || MODE == MODE_PLAIN) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            v[j] += colp[c * 32 + j];
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] += colp[c * 32 + j];
                     } else if constexpr (MODE == MODE_BIAS_ELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = elu_f(v[j] + colp[c * 32 + j]);
-                    } else if constexpr (MODE == MODE_DGRAD_ELUBN) {
+                    } else if constexpr (MODE == MODE_DGRAD_ELUBN || MODE == MODE_DGRAD_ELUOUT) {
                         float yv[32];
-                        if (row_ok) {
-                            const uint4* yp = reinterpret_cast<const uint4*>(p.yprev + row * p.ldy + col0);
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                uint4 u = __ldg(yp + g);
-                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float2 f = __bfloat1622float2(h[e]);
-                                    yv[g * 8 + 2 * e] = f.x;
-                                    yv[g * 8 + 2 * e + 1] = f.y;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) yv[j] = 0.f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int cc = c * 32 + j;
-                            float z = fmaf(yv[j], colp[BN + cc], colp[2 * BN + cc]);
-                            float g = v[j] * elu_grad_f(z);
-                            float xh = (yv[j] - colp[3 * BN + cc]) * colp[4 * BN + cc];
-                            v[j] = g;
-                            s2v[j] = g * xh;
-                        }
-                    }
-                    // bf16 store of this thread's 32 consecutive columns (64 B)
-                    if (row_ok) {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            if (col0 + g * 8 < p.N) {
-                                uint4 u;
-                                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yraw[g]);
 #pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-                                *reinterpret_cast<uint4*>(o + g * 8) = u;
+                            for (int e = 0; e < 4; ++e) {
+                                float2 f = __bfloat1622float2(h[e]);
+                                yv[g * 8 + 2 * e] = f.x;
+                                yv[g * 8 + 2 * e + 1] = f.y;
+                            }
+                        }
+                        if constexpr (MODE == MODE_DGRAD_ELUBN) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int cc = c * 32 + j;
+                                float z = fmaf(yv[j], colp[BN + cc], colp[2 * BN + cc]);
+                                float g = v[j] * elu_grad_f(z);
+                                float xh = (yv[j] - colp[3 * BN + cc]) * colp[4 * BN + cc];
+                                v[j] = g;
+                                s2v[j] = g * xh;
+                            }
+                        } else {
+                            // ELU backward from the saved OUTPUT a = ELU(z): ELU'(z) = a > 0 ? 1 : a + 1
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= (yv[j] > 0.f ? 1.f : yv[j] + 1.f);
+                        }
+                    }
+                    if (row_ok) {
+                        if (p.out_f32) {
+                            float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (col0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+                            // bf16 store of this thread's 32 consecutive columns (64 B)
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (col0 + g * 8 < p.N) {
+                                    uint4 u;
+                                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                                    *reinterpret_cast<uint4*>(o + g * 8) = u;
+                                }
                             }
                         }
                     }
@@ -397,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
             // every epilogue warp is done with colp / has published its partial statistics
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if constexpr (MODE == MODE_BIAS_STATS || MODE == MODE_DGRAD_ELUBN) {
                 for (int c = et; c < 2 * BN; c += EPI_THREADS) {
                     const int which = c / BN, cc = c % BN;
@@ -491,77 +524,104 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
 
 using namespace pcaa;
 
-extern "C" int pcaa_gemm_tc_tn(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int64_t M,
-                               int64_t N, int64_t K, int mode, const float* bias, double* stats, const void* yprev,
-                               const float* scale, const float* shift, const float* mean, const float* invstd,
-                               pcaa_stream stream) {
+// A(m,k): a_mn == 0 -> stored [M, K] (lda), else stored [K, M] (lda).  B(n,k): b_mn == 0 -> [N, K], else [K, N].
+static int gemm_tc_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out,
+                            int64_t ldo, int out_dtype, int64_t M, int64_t N, int64_t K, int mode, const float* bias,
+                            double* stats, const void* yprev, int64_t ldy, const float* scale, const float* shift,
+                            const float* mean, const float* invstd, cudaStream_t st) {
     if (M == 0 || N == 0) return PCAA_OK;
-    PCAA_REQUIRE(M > 0 && N > 0 && K > 0, PCAA_ERR_SHAPE, "gemm_tc_tn: bad shape");
-    PCAA_REQUIRE(N % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)out & 15) == 0, PCAA_ERR_ALIGN,
-                 "gemm_tc_tn: N and ldo must be multiples of 8 and out 16-byte aligned");
-    PCAA_REQUIRE(mode >= 0 && mode <= 3, PCAA_ERR_UNSUPPORTED, "gemm_tc_tn: unknown mode %d", mode);
+    PCAA_REQUIRE(M > 0 && N > 0 && K > 0, PCAA_ERR_SHAPE, "gemm_tc: bad shape");
+    PCAA_REQUIRE(mode >= 0 && mode <= PCAA_TC_WGRAD_STORE, PCAA_ERR_UNSUPPORTED, "gemm_tc: unknown mode %d", mode);
+    const bool wgrad = (mode == PCAA_TC_WGRAD_ACC || mode == PCAA_TC_WGRAD_STORE);
+    const bool f32out = wgrad || out_dtype == PCAA_F32;
+    // bf16 rows are written in 16-byte groups: the buffer must have ldo >= round_up(N, 8) (pad columns receive the
+    // epilogue of zero accumulators); fp32 rows use 16-byte stores when aligned, scalar stores otherwise (wgrad only)
+    const bool scalar_out = f32out && (((uintptr_t)out & 15) != 0 || ldo % 4 != 0 || N % 4 != 0);
+    PCAA_REQUIRE(!scalar_out || wgrad, PCAA_ERR_ALIGN, "gemm_tc: fp32 output needs 16-byte aligned rows (ldo %% 4 == 0, N %% 4 == 0)");
+    PCAA_REQUIRE(f32out || (((uintptr_t)out & 15) == 0 && ldo % 8 == 0 && ldo >= (N + 7) / 8 * 8), PCAA_ERR_ALIGN,
+                 "gemm_tc: bf16 output needs 16-byte aligned rows with ldo >= round_up(N, 8)");
     if (mode == PCAA_TC_BIAS_STATS || mode == PCAA_TC_DGRAD_ELUBN)
-        PCAA_REQUIRE(stats != nullptr, PCAA_ERR_SHAPE, "gemm_tc_tn: stats buffer required for mode %d", mode);
+        PCAA_REQUIRE(stats != nullptr, PCAA_ERR_SHAPE, "gemm_tc: stats buffer required for mode %d", mode);
     if (mode == PCAA_TC_DGRAD_ELUBN)
-        PCAA_REQUIRE(yprev && scale && shift && mean && invstd, PCAA_ERR_SHAPE, "gemm_tc_tn: dgrad mode needs yprev/coefficients");
+        PCAA_REQUIRE(yprev && scale && shift && mean && invstd, PCAA_ERR_SHAPE, "gemm_tc: mode 3 needs yprev/coefficients");
+    if (mode == PCAA_TC_DGRAD_ELUOUT) PCAA_REQUIRE(yprev != nullptr, PCAA_ERR_SHAPE, "gemm_tc: mode 5 needs the saved activation");
+    if (yprev) PCAA_REQUIRE(((uintptr_t)yprev & 15) == 0 && ldy % 8 == 0, PCAA_ERR_ALIGN, "gemm_tc: yprev alignment");
     constexpr int BN = 256;
     CUtensorMap ta, tb;
-    int rc = make_map(&ta, A, K, M, lda, BK, BM);
+    int rc = a_mn ? make_map(&ta, A, M, K, lda, 64, BK) : make_map(&ta, A, K, M, lda, BK, BM);
     if (rc) return rc;
-    rc = make_map(&tb, W, K, N, ldw, BK, BN);
+    rc = b_mn ? make_map(&tb, B, N, K, ldb, 64, BK) : make_map(&tb, B, K, N, ldb, BK, BN);
     if (rc) return rc;
     GemmParams p{};
     p.M = M;
     p.N = N;
     p.m_tiles = ceil_div(M, BM);
     p.n_tiles = ceil_div(N, BN);
-    p.k_splits = 1;
     p.kb_total = ceil_div(K, BK);
+    p.k_splits = 1;
     p.kb_per_split = p.kb_total;
+    if (mode == PCAA_TC_WGRAD_ACC) {
+        int tiles = p.m_tiles * p.n_tiles;
+        int splits = num_sms() / tiles;
+        if (splits < 1) splits = 1;
+        if (splits > p.kb_total) splits = p.kb_total;
+        p.kb_per_split = ceil_div(p.kb_total, splits);
+        p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
+    }
     p.out = out;
     p.ldo = ldo;
+    p.out_f32 = f32out ? 1 : 0;
+    p.wgrad_store = mode == PCAA_TC_WGRAD_STORE;
+    p.out_scalar = scalar_out ? 1 : 0;
     p.bias = bias;
     p.stats = stats;
     p.yprev = (const __nv_bfloat16*)yprev;
-    p.ldy = N;
+    p.ldy = ldy;
     p.scale = scale;
     p.shift = shift;
     p.mean = mean;
     p.invstd = invstd;
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (mode) {
-        case PCAA_TC_BIAS_STATS: return launch_tc<BN, false, false, MODE_BIAS_STATS>(ta, tb, p, st);
-        case PCAA_TC_BIAS_ELU: return launch_tc<BN, false, false, MODE_BIAS_ELU>(ta, tb, p, st);
-        case PCAA_TC_PLAIN: return launch_tc<BN, false, false, MODE_PLAIN>(ta, tb, p, st);
-        default: return launch_tc<BN, false, false, MODE_DGRAD_ELUBN>(ta, tb, p, st);
+    const int key = (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
+    if (key == 0) {
+        switch (mode) {
+            case PCAA_TC_BIAS_STATS: return launch_tc<BN, false, false, MODE_BIAS_STATS>(ta, tb, p, st);
+            case PCAA_TC_BIAS_ELU: return launch_tc<BN, false, false, MODE_BIAS_ELU>(ta, tb, p, st);
+            case PCAA_TC_PLAIN: return launch_tc<BN, false, false, MODE_PLAIN>(ta, tb, p, st);
+            case PCAA_TC_DGRAD_ELUBN: return launch_tc<BN, false, false, MODE_DGRAD_ELUBN>(ta, tb, p, st);
+            default: break;
+        }
+    } else if (key == 1) {
+        switch (mode) {
+            case PCAA_TC_PLAIN: return launch_tc<BN, false, true, MODE_PLAIN>(ta, tb, p, st);
+            case PCAA_TC_DGRAD_ELUOUT: return launch_tc<BN, false, true, MODE_DGRAD_ELUOUT>(ta, tb, p, st);
+            default: break;
+        }
+    } else if (key == 3) {
+        if (wgrad) return launch_tc<BN, true, true, MODE_WGRAD>(ta, tb, p, st);
     }
+    set_error("gemm_tc: operand layout (a_mn=%d, b_mn=%d) is not instantiated for mode %d", a_mn, b_mn, mode);
+    return PCAA_ERR_UNSUPPORTED;
+}
+
+extern "C" int pcaa_gemm_tc(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out,
+                            int64_t ldo, int out_dtype, int64_t M, int64_t N, int64_t K, int mode, const float* bias,
+                            double* stats, const void* yprev, int64_t ldy, const float* scale, const float* shift,
+                            const float* mean, const float* invstd, pcaa_stream stream) {
+    return gemm_tc_dispatch(A, lda, a_mn, B, ldb, b_mn, out, ldo, out_dtype, M, N, K, mode, bias, stats, yprev, ldy, scale,
+                            shift, mean, invstd, (cudaStream_t)stream);
+}
+
+extern "C" int pcaa_gemm_tc_tn(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int64_t M,
+                               int64_t N, int64_t K, int mode, const float* bias, double* stats, const void* yprev,
+                               const float* scale, const float* shift, const float* mean, const float* invstd,
+                               pcaa_stream stream) {
+    PCAA_REQUIRE(mode >= 0 && mode <= 3, PCAA_ERR_UNSUPPORTED, "gemm_tc_tn: unknown mode %d", mode);
+    return gemm_tc_dispatch(A, lda, 0, W, ldw, 0, out, ldo, PCAA_BF16, M, N, K, mode, bias, stats, yprev, N, scale, shift,
+                            mean, invstd, (cudaStream_t)stream);
 }
 
 extern "C" int pcaa_gemm_tc_nt_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw,
                                      int64_t N1, int64_t N2, int64_t K, pcaa_stream stream) {
-    if (N1 == 0 || N2 == 0 || K == 0) return PCAA_OK;
-    PCAA_REQUIRE(N1 > 0 && N2 > 0 && K > 0, PCAA_ERR_SHAPE, "gemm_tc_nt_wgrad: bad shape");
-    PCAA_REQUIRE(N2 % 4 == 0 && ldw % 4 == 0 && ((uintptr_t)dW & 15) == 0, PCAA_ERR_ALIGN,
-                 "gemm_tc_nt_wgrad: N2 and ldw must be multiples of 4 and dW 16-byte aligned");
-    constexpr int BN = 256;
-    CUtensorMap ta, tb;
-    int rc = make_map(&ta, A, N1, K, lda, 64, BK);
-    if (rc) return rc;
-    rc = make_map(&tb, B, N2, K, ldb, 64, BK);
-    if (rc) return rc;
-    GemmParams p{};
-    p.M = N1;
-    p.N = N2;
-    p.m_tiles = ceil_div(N1, BM);
-    p.n_tiles = ceil_div(N2, BN);
-    p.kb_total = ceil_div(K, BK);
-    int tiles = p.m_tiles * p.n_tiles;
-    int splits = num_sms() / tiles;
-    if (splits < 1) splits = 1;
-    if (splits > p.kb_total) splits = p.kb_total;
-    p.kb_per_split = ceil_div(p.kb_total, splits);
-    p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
-    p.out = dW;
-    p.ldo = ldw;
-    return launch_tc<BN, true, true, MODE_WGRAD>(ta, tb, p, (cudaStream_t)stream);
+    return gemm_tc_dispatch(A, lda, 1, B, ldb, 1, dW, ldw, PCAA_F32, N1, N2, K, PCAA_TC_WGRAD_ACC, nullptr, nullptr, nullptr,
+                            0, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }

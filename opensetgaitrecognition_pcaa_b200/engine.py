@@ -14,7 +14,8 @@ from typing import Dict, Optional
 import torch
 
 from . import ops
-from ._lib import ACT_ELU, ACT_NONE, TC_BIAS_STATS, TC_DGRAD_ELUBN, TC_PLAIN
+from ._lib import (ACT_ELU, ACT_NONE, TC_BIAS_ELU, TC_BIAS_STATS, TC_DGRAD_ELUBN, TC_DGRAD_ELUOUT, TC_PLAIN,
+                   TC_WGRAD_STORE)
 
 T_STEPS = 30
 DTC_DILATIONS = (1, 2, 4, 1, 2, 4)
@@ -245,3 +246,64 @@ def decoder_backward(dout: torch.Tensor, acts, P: Params, gradbuf: Optional[Grad
         d = linear_backward(d, acts[l - 1], acts[l] if l < 5 else None, P[f"{pre}dense{l}.weight"],
                             f"{pre}dense{l}.weight", f"{pre}dense{l}.bias", G, gradbuf, need_dx=(l > 1 or need_dx))
     return d, G
+
+
+# ------------------------------------------------------------------------------------------------ decoder, tensor cores
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def decoder_pack_weights(P: Params, pre: str = "", cache: Optional[dict] = None):
+    """bf16 operand copies of the five decoder weight matrices ([out, pad8(in)], zero padded).  With `cache`, a copy
+    is only refreshed when the fp32 parameter changed (data_ptr / in-place version counter)."""
+    wb = {}
+    for l in range(1, 6):
+        W = P[f"{pre}dense{l}.weight"]
+        key = (W.data_ptr(), W._version)
+        if cache is not None and cache.get(l, (None, None))[0] == key:
+            wb[l] = cache[l][1]
+            continue
+        wb[l] = ops.pack_bf16(W, ld_out=pad8(W.shape[1]))
+        if cache is not None:
+            cache[l] = (key, wb[l])
+    return wb
+
+
+def decoder_forward_tc(h: torch.Tensor, P: Params, wb, pre: str = ""):
+    """Tensor-core decoder: h [B, input_dim] fp32 -> rec [B, S] fp32.  Activations are bf16 [B, pad8(dim)];
+    weights wb[l] bf16 [out, pad8(in)] (tcgen05 GEMM with fused bias + ELU, fp32 accumulation)."""
+    B = h.shape[0]
+    a = ops.convert(h, torch.bfloat16)
+    acts = [a]
+    for l in range(1, 6):
+        W = P[f"{pre}dense{l}.weight"]
+        Nout, K = W.shape
+        if l < 5:
+            a = ops.gemm_tc(a, wb[l], TC_BIAS_ELU, B, Nout, K, bias=P[f"{pre}dense{l}.bias"])
+        else:
+            a = ops.gemm_tc(a, wb[l], TC_PLAIN, B, Nout, K, bias=P[f"{pre}dense{l}.bias"], out_dtype=torch.float32)
+        acts.append(a)
+    return a, acts
+
+
+def decoder_backward_tc(dout: torch.Tensor, acts, P: Params, wb, gradbuf: Optional[Grads] = None, pre: str = ""):
+    """dout [B, S] fp32 -> (d h [B, input_dim] fp32, grads).  Data gradients: dz_{l-1} = (dz_l W_l) * ELU'(.) with the
+    weight read MN-major straight from the forward's bf16 copy; weight gradients dW_l = dz_l^T a_{l-1} stored fp32."""
+    G: Grads = {}
+    B = dout.shape[0]
+    dz = ops.convert(dout, torch.bfloat16)
+    for l in range(5, 0, -1):
+        W = P[f"{pre}dense{l}.weight"]
+        Nout, K = W.shape
+        wname, bname = f"{pre}dense{l}.weight", f"{pre}dense{l}.bias"
+        dW = _out(gradbuf, wname)
+        if dW is None:
+            dW = torch.empty_like(W)
+        ops.gemm_tc(dz, acts[l - 1], TC_WGRAD_STORE, Nout, K, B, a_mn=True, b_mn=True, out=dW)
+        G[wname] = dW
+        G[bname] = ops.colsum_ld(dz, Nout, _out(gradbuf, bname))
+        if l > 1:
+            dz = ops.gemm_tc(dz, wb[l], TC_DGRAD_ELUOUT, B, K, Nout, b_mn=True, yprev=acts[l - 1])
+        else:
+            dz = ops.gemm_tc(dz, wb[l], TC_PLAIN, B, K, Nout, b_mn=True, out_dtype=torch.float32)
+    return dz, G

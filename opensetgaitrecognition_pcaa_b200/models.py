@@ -146,16 +146,16 @@ class _DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, module, names, *params):
         P = _named_tensors(module)
-        out, acts = engine.decoder_forward(x, P)
-        ctx.acts, ctx.module, ctx.names = acts, module, names
-        ctx.need_dx = x.requires_grad
+        wb = engine.decoder_pack_weights(P, cache=module.__dict__.setdefault("_pcaa_wcache", {}))
+        out, acts = engine.decoder_forward_tc(x, P, wb)
+        ctx.acts, ctx.module, ctx.names, ctx.wb = acts, module, names, wb
         return out
 
     @staticmethod
     def backward(ctx, dout):
         P = _named_tensors(ctx.module)
-        dx, G = engine.decoder_backward(dout.contiguous(), ctx.acts, P, need_dx=ctx.need_dx)
-        ctx.acts = None
+        dx, G = engine.decoder_backward_tc(dout.contiguous(), ctx.acts, P, ctx.wb)
+        ctx.acts = ctx.wb = None
         # bn1-4 are constructed but never applied (models.py:353-368 vs 373-385): their gradient stays None
         return (dx, None, None) + tuple(G.get(n) for n in ctx.names)
 

@@ -242,6 +242,37 @@ def gemm_tc_tn(a, w, mode: int, *, bias=None, stats=None, yprev=None, coef=None,
     return out
 
 
+def gemm_tc(a, b, mode: int, M: int, N: int, K: int, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16,
+            bias=None, stats=None, yprev=None, coef=None):
+    """General tcgen05 GEMM: out[M,N] = epilogue(sum_k A(m,k) B(n,k)).  `a` is stored [M,K] (or [K,M] when a_mn),
+    `b` is stored [N,K] (or [K,N] when b_mn); both bf16 2-D with unit inner stride; M, N, K are the TRUE extents
+    (buffers may be wider: leading dimensions come from the strides)."""
+    _chk(a, torch.bfloat16, contiguous=False), _chk(b, torch.bfloat16, contiguous=False)
+    if a.stride(1) != 1 or b.stride(1) != 1:
+        raise ValueError("gemm_tc: operands need unit inner stride")
+    if out is None:
+        if out_dtype == torch.bfloat16:
+            out = torch.empty((M, (N + 7) // 8 * 8), device=a.device, dtype=torch.bfloat16)
+        else:
+            out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    sc = sh = mu = inv = None
+    if coef is not None:
+        sc, sh, mu, inv = coef[0], coef[1], coef[2], coef[3]
+    call("pcaa_gemm_tc", _p(a), a.stride(0), 1 if a_mn else 0, _p(b), b.stride(0), 1 if b_mn else 0, _p(out),
+         out.stride(0), _DT[out.dtype], M, N, K, mode, _p(bias), _p(stats), _p(yprev),
+         0 if yprev is None else yprev.stride(0), _p(sc), _p(sh), _p(mu), _p(inv), _s())
+    return out
+
+
+def colsum_ld(x, C: int, out: Optional[torch.Tensor] = None):
+    """Column sums of the first C columns of a 2-D fp32 / bf16 matrix with arbitrary leading dimension."""
+    R = x.shape[0]
+    if out is None:
+        out = torch.empty(C, device=x.device, dtype=torch.float32)
+    call("pcaa_colsum_ld", _p(x), _DT[x.dtype], R, C, x.stride(0), _p(out), _s())
+    return out
+
+
 def gemm_tc_nt_wgrad(a, b, dW):
     """dW[N1,N2] (fp32) += a[K,N1]^T @ b[K,N2]  (bf16 operands, K = number of rows)."""
     _chk(a, torch.bfloat16), _chk(b, torch.bfloat16), _chk(dW, torch.float32)

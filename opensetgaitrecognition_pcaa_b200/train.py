@@ -30,7 +30,7 @@ class _Flat:
             n = t.numel()
             self.names.append(name)
             self.slices[name] = (off, n, tuple(t.shape))
-            off += (n + 3) // 4 * 4                     # keep every tensor 16-byte aligned
+            off += (n + 7) // 8 * 8                     # 16-byte alignment of every tensor, also in the bf16 shadow
         self.size = off
         self.p = torch.zeros(off, device=device, dtype=torch.float32)
         self.g = torch.zeros(off, device=device, dtype=torch.float32)
@@ -41,6 +41,12 @@ class _Flat:
             self.p[o:o + n].copy_(t.detach().reshape(-1))
             t.data = self.p[o:o + n].view(shp)          # the module parameter now aliases the flat buffer
         self.step = 0
+        self.shadow = None
+
+    def make_shadow(self):
+        """bf16 copy of the whole flat parameter buffer (same indexing); kept current by the fused Adam kernel."""
+        self.shadow = ops.convert(self.p, torch.bfloat16)
+        return self.shadow
 
     def view(self, buf, name):
         o, n, shp = self.slices[name]
@@ -49,7 +55,7 @@ class _Flat:
     def span(self, names):
         """[start, end) of the flat range covered by `names` (must be contiguous in registration order)."""
         o0 = min(self.slices[n][0] for n in names)
-        o1 = max(self.slices[n][0] + (self.slices[n][1] + 3) // 4 * 4 for n in names)
+        o1 = max(self.slices[n][0] + (self.slices[n][1] + 7) // 8 * 8 for n in names)
         return o0, o1
 
 
@@ -82,6 +88,7 @@ class PCAATrainer:
         self.D = _Flat([("D." + k, p) for k, p in discriminator.named_parameters()], dev)
         self._dec_span = self.G.span([n for n in self.G.names if n.startswith("G.") or n.startswith("GPH.")])
         self._enc_span = self.G.span([n for n in self.G.names if n.startswith("E.")])
+        self.G.make_shadow()
         self._refresh_views()
         self._comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._one = torch.ones((), device=dev, dtype=torch.float32)
@@ -98,6 +105,21 @@ class PCAATrainer:
         self.Dw = [self.D.view(self.D.p, f"D.model.{i}.{s}") for i in (0, 2, 4) for s in ("weight", "bias")]
         self.Dg = [self.D.view(self.D.g, f"D.model.{i}.{s}") for i in (0, 2, 4) for s in ("weight", "bias")]
         self._nbt = [v for k, v in self.enc.named_buffers() if k.endswith("num_batches_tracked")]
+        # tensor-core operand copies of the decoder weights: a view of the Adam-maintained bf16 shadow when the row
+        # length is a multiple of 8 elements (TMA needs 16-byte row strides), else re-packed (padded) every step
+        self._dec_shadow = {}
+        for l in range(1, 6):
+            W = self.P_G[f"dense{l}.weight"]
+            if W.shape[1] % 8 == 0:
+                self._dec_shadow[l] = self.G.view(self.G.shadow, f"G.dense{l}.weight")
+
+    def _decoder_weights_bf16(self):
+        wb = dict(self._dec_shadow)
+        for l in range(1, 6):
+            if l not in wb:
+                W = self.P_G[f"dense{l}.weight"]
+                wb[l] = ops.pack_bf16(W, ld_out=engine.pad8(W.shape[1]))
+        return wb
 
     # ------------------------------------------------------------------------------------------------------------
     def _allreduce(self, buf, async_op=False):
@@ -124,7 +146,8 @@ class PCAATrainer:
         ops.adam_flat(self.D.p, self.D.g, self.D.m, self.D.v, cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, self.D.step, gscale)
         # ---- generator step (PCAA_ablation.py:985-1021)
         h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
-        rec, acts = engine.decoder_forward(h0, self.P_G)
+        wb = self._decoder_weights_bf16()
+        rec, acts = engine.decoder_forward_tc(h0, self.P_G, wb)
         rec4 = rec.view(pcs.shape)
         frame_loss, i1, i2 = ops.chamfer_fwd(rec4, pcs)
         rec_loss = ops.chamfer_reduce(frame_loss, True)
@@ -135,7 +158,7 @@ class PCAATrainer:
         sup_loss, dlogits, pred = ops.softmax_ce(logits, gt, want_grad=True)
         # backward: Chamfer -> decoder -> projection head -> (+ adversarial) -> encoder
         G_unused: Dict[str, torch.Tensor] = {}
-        dh0, _ = engine.decoder_backward(drec.view(B, S), acts, self.P_G, self.gb_G)
+        dh0, _ = engine.decoder_backward_tc(drec.view(B, S), acts, self.P_G, wb, self.gb_G)
         engine.linear_backward(dh0, fv, h0, self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused, self.gb_GPH,
                                dx_out=dfv, dx_acc=True)
         work = None
@@ -152,7 +175,8 @@ class PCAATrainer:
             work.wait()
             torch.cuda.current_stream().wait_stream(self._comm_stream)
         self.G.step += 1
-        ops.adam_flat(self.G.p, self.G.g, self.G.m, self.G.v, cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, self.G.step, gscale)
+        ops.adam_flat(self.G.p, self.G.g, self.G.m, self.G.v, cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, self.G.step, gscale,
+                      self.G.shadow)
         return {"rec_loss": rec_loss, "d_loss": d_losses[0], "gp": d_losses[1], "loss_g": loss_g, "sup_loss": sup_loss,
                 "pred": pred, "logits": logits, "fv": fv}
 
@@ -163,7 +187,7 @@ class PCAATrainer:
         self.enc.eval(), self.dec.eval()
         logits, fv, _ = engine.encoder_forward(pcs, self.P_E, False, self.enc.use_projection_head)
         h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
-        rec, _ = engine.decoder_forward(h0, self.P_G)
+        rec, _ = engine.decoder_forward_tc(h0, self.P_G, self._decoder_weights_bf16())
         fl, _, _ = ops.chamfer_fwd(rec.view(pcs.shape), pcs, want_idx=False)
         ce, _, pred = ops.softmax_ce(logits, gt, want_grad=False)
         return ops.chamfer_reduce(fl, True), ce, pred

@@ -281,7 +281,8 @@ def trainable_names(p: Params, prefixes) -> List[str]:
     return [k for pre in prefixes for k in p if k.startswith(pre) and not is_buffer(k)]
 
 
-def train_step_variant4(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict) -> dict:
+def train_step_variant4(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict,
+                        clone_leaves: bool = True) -> dict:
     """One iteration of the paper-PCAA loop, PCAA_ablation.py:882-1021 (in place on ``p``).
 
     cfg: LR, B1, B2, GP_WEIGHT, ADV_WEIGHT, NMAX.  ``z0`` (B,32) and ``alphas`` (B,1) are the
@@ -291,8 +292,12 @@ def train_step_variant4(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, 
     C = means.shape[0]
     nmax = cfg["NMAX"]
     out: dict = {}
-    # leaf copies that require grad
-    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items() if not is_buffer(k)}
+    # leaf copies that require grad (clone_leaves=False: differentiate the stored tensors in place -- what the
+    # reference's own modules do; used by the timed CPU baseline to avoid an 861 MB copy per step)
+    if clone_leaves:
+        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items() if not is_buffer(k)}
+    else:
+        leaves = {k: v.requires_grad_(True) for k, v in p.items() if not is_buffer(k)}
     q = dict(p)
     q.update(leaves)
     upd: dict = {}
@@ -313,8 +318,9 @@ def train_step_variant4(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, 
         adam_update([p[n] for n in d_names], list(d_grads), opt_state.setdefault("D", [dict() for _ in d_names]),
                     cfg["LR"], cfg["B1"], cfg["B2"])
     # generator step sees the *updated* critic (PCAA_ablation.py:996)
-    for n in d_names:
-        q[n] = p[n].detach().clone().requires_grad_(True)
+    if clone_leaves:
+        for n in d_names:
+            q[n] = p[n].detach().clone().requires_grad_(True)
 
     # ---- generator step
     rec = decoder_forward(q, proj_head_forward(q, fv), nmax)

@@ -354,3 +354,40 @@ def test_openset_scoring(ops, golden_dir):
         n = (len(lik) // k) * k
         votes = ops.openset_vote(cuda(torch.from_numpy(ll[:n])), cuda(preds[:n]), k, math.log(thr), C).cpu().numpy()
         assert np.array_equal(votes, gd[f"votes_k{k}"])          # bit-exact integer labels vs the reference
+
+
+# ------------------------------------------------------------------------------------------------ decoder tensor-core path
+@pytest.mark.parametrize("B,K,Nout", [(4, 64, 375), (32, 1125, 2250), (256, 375, 752), (130, 4500, 1000)])
+def test_gemm_tc_decoder_modes(ops, B, K, Nout):
+    from opensetgaitrecognition_pcaa_b200 import engine
+    L = ops._lib
+    g = torch.Generator().manual_seed(B + K + Nout)
+    a = bf16_round(torch.randn(B, K, generator=g))
+    W = torch.randn(Nout, K, generator=g) / math.sqrt(K)
+    bias = torch.randn(Nout, generator=g)
+    wb = ops.pack_bf16(cuda(W), ld_out=engine.pad8(K))
+    Wr = bf16_round(W)
+    ad = torch.zeros(B, engine.pad8(K), dtype=torch.bfloat16, device="cuda")
+    ad[:, :K] = cuda(a).bfloat16()
+    # forward: bias + ELU, bf16 out with padded leading dimension; and fp32 out
+    out = ops.gemm_tc(ad, wb, L.TC_BIAS_ELU, B, Nout, K, bias=cuda(bias))
+    ref = O.elu(a @ Wr.t() + bias)
+    assert out.shape == (B, engine.pad8(Nout)) and rel_err(out[:, :Nout].float(), ref) < 1e-2
+    if Nout % 4 == 0:
+        o32 = ops.gemm_tc(ad, wb, L.TC_PLAIN, B, Nout, K, bias=cuda(bias), out_dtype=torch.float32)
+        assert rel_err(o32, a @ Wr.t() + bias) < 1e-4
+    # data gradient through the MN-major weight + ELU'(saved output)
+    dz = bf16_round(torch.randn(B, Nout, generator=g))
+    dzd = torch.zeros(B, engine.pad8(Nout), dtype=torch.bfloat16, device="cuda")
+    dzd[:, :Nout] = cuda(dz).bfloat16()
+    act_prev = bf16_round(O.elu(torch.randn(B, K, generator=g)))
+    apd = torch.zeros(B, engine.pad8(K), dtype=torch.bfloat16, device="cuda")
+    apd[:, :K] = cuda(act_prev).bfloat16()
+    da = ops.gemm_tc(dzd, wb, L.TC_DGRAD_ELUOUT, B, K, Nout, b_mn=True, yprev=apd)
+    ref = (dz @ Wr) * torch.where(act_prev > 0, torch.ones_like(act_prev), act_prev + 1)
+    assert rel_err(da[:, :K].float(), ref) < 1e-2
+    # weight gradient, plain stores, rows not 16-byte aligned when K % 4 != 0
+    dW = torch.full((Nout, K), 7.0, device="cuda")
+    ops.gemm_tc(dzd, apd, L.TC_WGRAD_STORE, Nout, K, B, a_mn=True, b_mn=True, out=dW)
+    assert rel_err(dW, dz.double().t() @ act_prev.double()) < 1e-4
+    assert rel_err(ops.colsum_ld(dzd, Nout), dz.sum(0)) < 1e-4
