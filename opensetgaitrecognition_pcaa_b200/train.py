@@ -16,7 +16,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import engine, ops
+from . import dp, engine, ops
 from ._lib import ACT_ELU
 
 
@@ -76,9 +76,7 @@ class PCAATrainer:
         self.means = means.to(dev).float().contiguous()
         self.C = self.means.shape[0]
         self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
+        self.rank, self.world = dp.world_info(process_group)
         # ---- flat generator-side parameters: optimizer_G chain order (PCAA_ablation.py:821-826); the decoder's bn1-4
         # never receive a gradient (models.py:373-385), torch.optim.Adam skips them -> they stay outside the flat range
         named = [("E." + k, p) for k, p in encoder.named_parameters()]
@@ -90,7 +88,9 @@ class PCAATrainer:
         self._enc_span = self.G.span([n for n in self.G.names if n.startswith("E.")])
         self.G.make_shadow()
         self._refresh_views()
-        self._comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        # gradient exchange (dp.py): decoder-side span first (overlaps the encoder backward), then the encoder span
+        self.xG = dp.GradExchange(self.G.g, process_group)
+        self.xD = dp.GradExchange(self.D.g, process_group)
         self._one = torch.ones((), device=dev, dtype=torch.float32)
 
     def _refresh_views(self):
@@ -122,9 +122,6 @@ class PCAATrainer:
         return wb
 
     # ------------------------------------------------------------------------------------------------------------
-    def _allreduce(self, buf, async_op=False):
-        return torch.distributed.all_reduce(buf, op=torch.distributed.ReduceOp.SUM, group=self.pg, async_op=async_op)
-
     def step(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor) -> Dict[str, torch.Tensor]:
         """One variant-4 iteration.  pcs (B,4,30,N) fp32, gt (B,) int64, z0 (B,32) ~ N(0,1) and alphas (B,1) ~ U(0,1)
         are the host RNG draws of PCAA_ablation.py:915-931, 944-948 (already on the device).  Returns device scalars."""
@@ -140,8 +137,8 @@ class PCAATrainer:
         # ---- critic step (PCAA_ablation.py:900-980), one fused kernel + Adam
         self.D.g.zero_()
         d_losses = ops.wgangp_dstep(fv, z0, self.means, gt, alphas.reshape(-1), *self.Dw, cfg["GP_WEIGHT"], self.Dg)
-        if self.world > 1:
-            self._allreduce(self.D.g)
+        self.xD.start(0, self.D.size)
+        self.xD.finish()
         self.D.step += 1
         ops.adam_flat(self.D.p, self.D.g, self.D.m, self.D.v, cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, self.D.step, gscale)
         # ---- generator step (PCAA_ablation.py:985-1021)
@@ -161,19 +158,11 @@ class PCAATrainer:
         dh0, _ = engine.decoder_backward_tc(drec.view(B, S), acts, self.P_G, wb, self.gb_G)
         engine.linear_backward(dh0, fv, h0, self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused, self.gb_GPH,
                                dx_out=dfv, dx_acc=True)
-        work = None
-        if self.world > 1:
-            # decoder-side gradients (99 % of the bytes) are final: reduce them while the encoder backward runs
-            ev = torch.cuda.Event()
-            ev.record()
-            with torch.cuda.stream(self._comm_stream):
-                self._comm_stream.wait_event(ev)
-                work = self._allreduce(self.G.g[self._dec_span[0]:self._dec_span[1]], async_op=True)
+        # decoder-side gradients (99 % of the bytes) are final: reduce them while the encoder backward runs
+        self.xG.start(*self._dec_span)
         engine.encoder_backward(dlogits, dfv, saved, self.P_E, self.gb_E)
-        if self.world > 1:
-            self._allreduce(self.G.g[self._enc_span[0]:self._enc_span[1]])
-            work.wait()
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self.xG.start(*self._enc_span)
+        self.xG.finish()
         self.G.step += 1
         ops.adam_flat(self.G.p, self.G.g, self.G.m, self.G.v, cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, self.G.step, gscale,
                       self.G.shadow)
