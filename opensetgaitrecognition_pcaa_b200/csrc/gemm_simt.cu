@@ -11,7 +11,7 @@ template <typename TA, typename TB, typename TC>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TA* __restrict__ A, int64_t sam, int64_t sak, const TB* __restrict__ B, int64_t sbk, int64_t sbn,
                  TC* __restrict__ C, int64_t scm, int64_t scn, int64_t M, int64_t N, int64_t K,
-                 const float* __restrict__ bias, int act, int accumulate) {
+                 const float* __restrict__ bias, int act, int accumulate, int64_t k_per_split) {
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN_ + 4];
     int tid = threadIdx.x;
@@ -24,7 +24,11 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sam, int64_t sak, const TB* _
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const bool a_kfast = (sak == 1);
     const bool b_nfast = (sbn == 1);
-    for (int64_t k0 = 0; k0 < K; k0 += TK) {
+    // split-K (gridDim.z > 1): this block reduces k in [kbeg, kend) and atomically adds into a zeroed fp32 C
+    const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
+    const int64_t kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+    const bool split = gridDim.z > 1;
+    for (int64_t k0 = kbeg; k0 < kend; k0 += TK) {
         // A tile: 64 x 16 = 1024 elements, 4 per thread
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -32,7 +36,7 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sam, int64_t sak, const TB* _
             if (a_kfast) { k = tid % TK; m = tid / TK + 16 * i; }
             else { m = tid % TM; k = tid / TM + 4 * i; }
             int64_t gm = m0 + m, gk = k0 + k;
-            As[k][m] = (gm < M && gk < K) ? ld_as_float<TA>(A + gm * sam + gk * sak) : 0.f;
+            As[k][m] = (gm < M && gk < kend) ? ld_as_float<TA>(A + gm * sam + gk * sak) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -40,7 +44,7 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sam, int64_t sak, const TB* _
             if (b_nfast) { n = tid % TN_; k = tid / TN_ + 4 * i; }
             else { k = tid % TK; n = tid / TK + 16 * i; }
             int64_t gn = n0 + n, gk = k0 + k;
-            Bs[k][n] = (gn < N && gk < K) ? ld_as_float<TB>(B + gk * sbk + gn * sbn) : 0.f;
+            Bs[k][n] = (gn < N && gk < kend) ? ld_as_float<TB>(B + gk * sbk + gn * sbn) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -64,9 +68,14 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sam, int64_t sak, const TB* _
             int64_t gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
             float v = acc[i][j];
+            TC* c = C + gm * scm + gn * scn;
+            if (split) {
+                if (bias && blockIdx.z == 0) v += bias[gn];
+                if constexpr (sizeof(TC) == 4) atomicAdd(reinterpret_cast<float*>(c), v);
+                continue;
+            }
             if (bias) v += bias[gn];
             if (act == PCAA_ACT_ELU) v = elu_f(v);
-            TC* c = C + gm * scm + gn * scn;
             if (accumulate) v += ld_as_float<TC>(c);
             st_from_float<TC>(c, v);
         }
@@ -78,8 +87,22 @@ static int launch(const void* A, int64_t sam, int64_t sak, const void* B, int64_
                   int64_t scn, int64_t M, int64_t N, int64_t K, const float* bias, int act, int accumulate,
                   cudaStream_t st) {
     dim3 grid(ceil_div(M, TM), ceil_div(N, TN_));
+    int64_t k_per_split = K > 0 ? K : 1;
+    // tall-K products with few output tiles (weight gradients of the TCN / heads: K = rows) would leave most SMs idle:
+    // split K over grid.z and reduce with fp32 atomics into a zeroed, contiguous fp32 C
+    const int64_t tiles = (int64_t)grid.x * grid.y;
+    if (sizeof(TC) == 4 && act == PCAA_ACT_NONE && !accumulate && scn == 1 && scm == N && K >= 2048 && tiles <= 74) {
+        int splits = (int)((2 * 148 + tiles - 1) / tiles);
+        int max_splits = (int)(K / 256);
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 1) {
+            k_per_split = ((K + splits - 1) / splits + TK - 1) / TK * TK;
+            grid.z = (unsigned)ceil_div(K, k_per_split);
+            if (cudaMemsetAsync(C, 0, sizeof(float) * M * N, st) != cudaSuccess) return check_launch("gemm_simt memset");
+        }
+    }
     gemm_simt_kernel<TA, TB, TC><<<grid, 256, 0, st>>>((const TA*)A, sam, sak, (const TB*)B, sbk, sbn, (TC*)C, scm, scn, M,
-                                                      N, K, bias, act, accumulate);
+                                                      N, K, bias, act, accumulate, k_per_split);
     return check_launch("gemm_simt");
 }
 

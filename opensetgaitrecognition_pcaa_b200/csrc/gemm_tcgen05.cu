@@ -23,7 +23,12 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;
 constexpr int EPI_THREADS = 256;
 
-enum { MODE_BIAS_STATS = 0, MODE_BIAS_ELU = 1, MODE_PLAIN = 2, MODE_DGRAD_ELUBN = 3, MODE_WGRAD = 4, MODE_DGRAD_ELUOUT = 5 };
+enum { MODE_BIAS_STATS = 0, MODE_BIAS_ELU = 1, MODE_PLAIN = 2, MODE_DGRAD_ELUBN = 3, MODE_WGRAD = 4, MODE_DGRAD_ELUOUT = 5,
+       // "channel-major" modes: the output ROW (TMEM lane) is the channel, the columns are points; per-channel
+       // parameters are per-thread scalars and BatchNorm statistics are plain in-thread sums (no cross-lane reduction)
+       MODE_T_BIAS_STATS = 7, MODE_T_AFFINE_ELU = 8, MODE_T_DGRAD_ELUBN = 9 };
+
+template <int MODE> constexpr bool is_t_mode() { return MODE == MODE_T_BIAS_STATS || MODE == MODE_T_AFFINE_ELU || MODE == MODE_T_DGRAD_ELUBN; }
 
 struct GemmParams {
     int64_t M, N;                 // output extent (rows, cols)
@@ -39,7 +44,28 @@ struct GemmParams {
     const __nv_bfloat16* yprev;   // [M, ldy] (MODE_DGRAD_ELUBN)
     int64_t ldy;
     const float *scale, *shift, *mean, *invstd;
+    int sched_mfixed;             // tile order: 0 = items strided over the grid; 1 = CTA keeps one m block (T modes)
 };
+
+// tile `it` of this CTA -> (m block, n block, k split); false when the CTA has no more work
+__device__ __forceinline__ bool tile_at(const GemmParams& p, int it, int& m_blk, int& n_blk, int& ks) {
+    if (p.sched_mfixed) {
+        // gridDim.x is a multiple of m_tiles: CTAs b, b+1, .. b+m_tiles-1 work on the same n block at the same time
+        // (the activation tile is fetched from DRAM once and hit in L2 by the others) and a CTA never changes m block
+        const int per = gridDim.x / p.m_tiles;
+        m_blk = blockIdx.x % p.m_tiles;
+        n_blk = blockIdx.x / p.m_tiles + it * per;
+        ks = 0;
+        return n_blk < p.n_tiles;
+    }
+    const int item = blockIdx.x + it * gridDim.x;
+    if (item >= p.m_tiles * p.n_tiles * p.k_splits) return false;
+    ks = item % p.k_splits;
+    const int tile = item / p.k_splits;
+    n_blk = tile % p.n_tiles;
+    m_blk = tile / p.n_tiles;
+    return true;
+}
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,6 +121,28 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// registers of an issued load are only valid after wait::ld: tie them to the wait so no consumer is scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -200,17 +248,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_items = p.m_tiles * p.n_tiles * p.k_splits;
-
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int ks = item % p.k_splits;
-                const int tile = item / p.k_splits;
-                const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+            int m_blk, n_blk, ks;
+            for (int it = 0; tile_at(p, it, m_blk, n_blk, ks); ++it) {
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -249,9 +293,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr uint32_t B_KSTEP = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int ks = item % p.k_splits;
+            int m_blk, n_blk, ks;
+            for (int it = 0; tile_at(p, it, m_blk, n_blk, ks); ++it) {
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 const int buf = it & 1;
@@ -275,6 +318,128 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_commit(&tfull[buf]);                // accumulator ready for the epilogue
             }
         }
+    } else if constexpr (is_t_mode<MODE>()) {
+        // ===================================================================== epilogue warps, channel-major modes
+        // thread = one output row (channel): its bias / BatchNorm coefficients are scalars, its statistics are plain
+        // running sums kept in registers over all tiles of the CTA (the scheduler keeps the m block fixed) and
+        // flushed with ONE double atomic per row at the end.  TMEM loads are software-pipelined: the load of chunk
+        // c+1 is in flight while chunk c is processed.
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int CPW = BN / 64;                    // 32-column chunks per warp per tile
+        int cur_m = -1;
+        int64_t row = 0;
+        bool row_ok = false;
+        float r_bias = 0.f, r_scale = 0.f, r_shift = 0.f, r_mean = 0.f, r_invstd = 0.f;
+        double d1 = 0.0, d2 = 0.0;
+        int m_blk, n_blk, ks;
+        for (int it = 0; tile_at(p, it, m_blk, n_blk, ks); ++it) {
+            if (m_blk != cur_m) {
+                if (cur_m >= 0 && row_ok && MODE != MODE_T_AFFINE_ELU) {
+                    atomicAdd(&p.stats[row], d1);
+                    atomicAdd(&p.stats[p.M + row], d2);
+                }
+                d1 = d2 = 0.0;
+                cur_m = m_blk;
+                row = (int64_t)m_blk * BM + q * 32 + lane;
+                row_ok = row < p.M;
+                if (row_ok) {
+                    if constexpr (MODE == MODE_T_BIAS_STATS) r_bias = p.bias ? p.bias[row] : 0.f;
+                    if constexpr (MODE == MODE_T_AFFINE_ELU) {
+                        r_scale = p.scale[row];
+                        r_shift = p.bias ? fmaf(p.bias[row], r_scale, p.shift[row]) : p.shift[row];
+                    }
+                    if constexpr (MODE == MODE_T_DGRAD_ELUBN) {
+                        r_scale = p.scale[row]; r_shift = p.shift[row]; r_mean = p.mean[row]; r_invstd = p.invstd[row];
+                    }
+                }
+            }
+            const int buf = it & 1;
+            const int64_t n0 = (int64_t)n_blk * BN + half * (BN / 2);
+            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * (BN / 2);
+            uint32_t ra[32], rb[32];
+            float t1 = 0.f, t2 = 0.f;
+            tmem_ld32_issue(taddr, ra);
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+                uint32_t (&r)[32] = (c & 1) ? rb : ra;
+                uint32_t (&rn)[32] = (c & 1) ? ra : rb;
+                const int64_t col0 = n0 + c * 32;
+                const bool any = row_ok && col0 < p.N;
+                uint4 yraw[4];
+                if constexpr (MODE == MODE_T_DGRAD_ELUBN) {
+                    const uint4* yp = reinterpret_cast<const uint4*>(p.yprev + (any ? row * p.ldy + col0 : 0));
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) yraw[g] = (any && col0 + g * 8 < p.N) ? __ldg(yp + g) : make_uint4(0, 0, 0, 0);
+                }
+                tmem_ld_wait(r);
+                if (c + 1 < CPW) tmem_ld32_issue(taddr + (c + 1) * 32, rn);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                const bool full_chunk = col0 + 32 <= p.N;
+                if constexpr (MODE == MODE_T_BIAS_STATS) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] += r_bias;
+                        const float m = (full_chunk || col0 + j < p.N) ? v[j] : 0.f;
+                        t1 += m;
+                        t2 = fmaf(m, m, t2);
+                    }
+                } else if constexpr (MODE == MODE_T_AFFINE_ELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float z = fmaf(v[j], r_scale, r_shift);
+                        v[j] = z > 0.f ? z : __expf(z) - 1.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yraw[g]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __bfloat1622float2(h[e]);
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int j = g * 8 + 2 * e + u;
+                                const float yv = u ? f.y : f.x;
+                                const float z = fmaf(yv, r_scale, r_shift);
+                                float gq = v[j] * (z > 0.f ? 1.f : __expf(z));
+                                gq = (full_chunk || col0 + j < p.N) ? gq : 0.f;
+                                v[j] = gq;
+                                t1 += gq;
+                                t2 = fmaf(gq, (yv - r_mean) * r_invstd, t2);
+                            }
+                        }
+                    }
+                }
+                if (any) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (col0 + g * 8 < p.N) {
+                            uint4 u;
+                            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                            *reinterpret_cast<uint4*>(o + g * 8) = u;
+                        }
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator are complete -> hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+            d1 += (double)t1;
+            d2 += (double)t2;
+        }
+        if (cur_m >= 0 && row_ok && MODE != MODE_T_AFFINE_ELU) {
+            atomicAdd(&p.stats[row], d1);
+            atomicAdd(&p.stats[p.M + row], d2);
+        }
     } else {
         // ===================================================================== epilogue warps
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
@@ -284,10 +449,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c_begin = half * (CHUNKS / 2), c_end = c_begin + CHUNKS / 2;
         float* my_s1 = wstat + q * 2 * BN;
         float* my_s2 = my_s1 + BN;
-        int it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            const int tile = item / p.k_splits;
-            const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+        int m_blk, n_blk, ks;
+        for (int it = 0; tile_at(p, it, m_blk, n_blk, ks); ++it) {
             const int64_t n0 = (int64_t)n_blk * BN;
             const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
             const bool row_ok = row < p.M;
@@ -516,6 +679,16 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     }
     int items = p.m_tiles * p.n_tiles * p.k_splits;
     int grid = items < num_sms() ? items : num_sms();
+    if (p.sched_mfixed) {
+        // a multiple of m_tiles CTAs, at most one per SM and no more column groups than there are n tiles
+        int per = num_sms() / p.m_tiles;
+        if (per > p.n_tiles) per = p.n_tiles;
+        if (per < 1) {
+            set_error("gemm_tc: %d row blocks exceed the SM count (channel-major modes)", p.m_tiles);
+            return PCAA_ERR_UNSUPPORTED;
+        }
+        grid = per * p.m_tiles;
+    }
     kern<<<grid, NUM_THREADS, SmemLayout<BN>::TOTAL, st>>>(ta, tb, p);
     return check_launch("gemm_tc");
 }
@@ -531,7 +704,8 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_mn, const void* B,
                             const float* mean, const float* invstd, cudaStream_t st) {
     if (M == 0 || N == 0) return PCAA_OK;
     PCAA_REQUIRE(M > 0 && N > 0 && K > 0, PCAA_ERR_SHAPE, "gemm_tc: bad shape");
-    PCAA_REQUIRE(mode >= 0 && mode <= PCAA_TC_WGRAD_STORE, PCAA_ERR_UNSUPPORTED, "gemm_tc: unknown mode %d", mode);
+    PCAA_REQUIRE(mode >= 0 && mode <= PCAA_TC_T_DGRAD_ELUBN, PCAA_ERR_UNSUPPORTED, "gemm_tc: unknown mode %d", mode);
+    const bool tmode = mode >= PCAA_TC_T_BIAS_STATS;
     const bool wgrad = (mode == PCAA_TC_WGRAD_ACC || mode == PCAA_TC_WGRAD_STORE);
     const bool f32out = wgrad || out_dtype == PCAA_F32;
     // bf16 rows are written in 16-byte groups: the buffer must have ldo >= round_up(N, 8) (pad columns receive the
@@ -540,10 +714,12 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_mn, const void* B,
     PCAA_REQUIRE(!scalar_out || wgrad, PCAA_ERR_ALIGN, "gemm_tc: fp32 output needs 16-byte aligned rows (ldo %% 4 == 0, N %% 4 == 0)");
     PCAA_REQUIRE(f32out || (((uintptr_t)out & 15) == 0 && ldo % 8 == 0 && ldo >= (N + 7) / 8 * 8), PCAA_ERR_ALIGN,
                  "gemm_tc: bf16 output needs 16-byte aligned rows with ldo >= round_up(N, 8)");
-    if (mode == PCAA_TC_BIAS_STATS || mode == PCAA_TC_DGRAD_ELUBN)
+    if (mode == PCAA_TC_BIAS_STATS || mode == PCAA_TC_DGRAD_ELUBN || mode == PCAA_TC_T_BIAS_STATS || mode == PCAA_TC_T_DGRAD_ELUBN)
         PCAA_REQUIRE(stats != nullptr, PCAA_ERR_SHAPE, "gemm_tc: stats buffer required for mode %d", mode);
-    if (mode == PCAA_TC_DGRAD_ELUBN)
-        PCAA_REQUIRE(yprev && scale && shift && mean && invstd, PCAA_ERR_SHAPE, "gemm_tc: mode 3 needs yprev/coefficients");
+    if (mode == PCAA_TC_DGRAD_ELUBN || mode == PCAA_TC_T_DGRAD_ELUBN)
+        PCAA_REQUIRE(yprev && scale && shift && mean && invstd, PCAA_ERR_SHAPE, "gemm_tc: mode %d needs yprev/coefficients", mode);
+    if (mode == PCAA_TC_T_AFFINE_ELU) PCAA_REQUIRE(scale && shift, PCAA_ERR_SHAPE, "gemm_tc: mode 8 needs scale/shift");
+    if (tmode) PCAA_REQUIRE(out_dtype == PCAA_BF16, PCAA_ERR_UNSUPPORTED, "gemm_tc: channel-major modes store bf16");
     if (mode == PCAA_TC_DGRAD_ELUOUT) PCAA_REQUIRE(yprev != nullptr, PCAA_ERR_SHAPE, "gemm_tc: mode 5 needs the saved activation");
     if (yprev) PCAA_REQUIRE(((uintptr_t)yprev & 15) == 0 && ldy % 8 == 0, PCAA_ERR_ALIGN, "gemm_tc: yprev alignment");
     constexpr int BN = 256;
@@ -581,8 +757,10 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_mn, const void* B,
     p.shift = shift;
     p.mean = mean;
     p.invstd = invstd;
+    p.sched_mfixed = tmode ? 1 : 0;
     const int key = (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
     if (key == 0) {
+        if (wgrad) return launch_tc<BN, false, false, MODE_WGRAD>(ta, tb, p, st);
         switch (mode) {
             case PCAA_TC_BIAS_STATS: return launch_tc<BN, false, false, MODE_BIAS_STATS>(ta, tb, p, st);
             case PCAA_TC_BIAS_ELU: return launch_tc<BN, false, false, MODE_BIAS_ELU>(ta, tb, p, st);
@@ -594,10 +772,13 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_mn, const void* B,
         switch (mode) {
             case PCAA_TC_PLAIN: return launch_tc<BN, false, true, MODE_PLAIN>(ta, tb, p, st);
             case PCAA_TC_DGRAD_ELUOUT: return launch_tc<BN, false, true, MODE_DGRAD_ELUOUT>(ta, tb, p, st);
+            case PCAA_TC_T_BIAS_STATS: return launch_tc<BN, false, true, MODE_T_BIAS_STATS>(ta, tb, p, st);
+            case PCAA_TC_T_AFFINE_ELU: return launch_tc<BN, false, true, MODE_T_AFFINE_ELU>(ta, tb, p, st);
             default: break;
         }
     } else if (key == 3) {
         if (wgrad) return launch_tc<BN, true, true, MODE_WGRAD>(ta, tb, p, st);
+        if (mode == PCAA_TC_T_DGRAD_ELUBN) return launch_tc<BN, true, true, MODE_T_DGRAD_ELUBN>(ta, tb, p, st);
     }
     set_error("gemm_tc: operand layout (a_mn=%d, b_mn=%d) is not instantiated for mode %d", a_mn, b_mn, mode);
     return PCAA_ERR_UNSUPPORTED;

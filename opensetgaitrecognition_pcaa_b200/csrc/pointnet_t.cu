@@ -1,0 +1,456 @@
+// Channel-major ("T") PointNet kernels: activations are stored channels-first, yT[C][ld] bf16, with the
+// P = B*T*N points of the batch contiguous (rows ordered (b, t, n); ld = P rounded up to 8 elements so every row is
+// 16-byte aligned for TMA and vector access).  In this layout a BatchNorm channel is a ROW: its coefficients are
+// per-row scalars, its statistics are row sums, and the tcgen05 GEMMs (gemm_tcgen05.cu, MODE_T_*) produce them in
+// their epilogues without any cross-lane reduction.
+//
+// Replaces, for the per-point shared MLP of the reference: Conv2d(4->512, 1x1) (models.py:21-28, 86-88),
+// BatchNorm2d + ELU application (models.py:29, 33-34), AvgPool2d((1, nmax)) (models.py:242-243, 282) and their
+// autograd backward.  All kernels are HBM-bound streaming passes with 16-byte accesses.
+#include "common.cuh"
+
+namespace pcaa {
+
+__device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    return u;
+}
+
+// 8 consecutive points p0 .. p0+7 of feature plane f of x (B, 4, TN) fp32; out-of-range points read as 0
+__device__ __forceinline__ void load_x8(const float* __restrict__ x, int64_t p0, int64_t P, int64_t TN, int f,
+                                        float (&v)[8]) {
+    const int64_t b = p0 / TN, tn = p0 - b * TN;
+    const int64_t off = (b * 4 + f) * TN + tn;
+    if (p0 + 8 <= P && tn + 8 <= TN && (off & 3) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + off));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(x + off) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t p = p0 + j;
+            if (p < P) {
+                const int64_t bb = p / TN, t2 = p - bb * TN;
+                v[j] = __ldg(x + (bb * 4 + f) * TN + t2);
+            } else {
+                v[j] = 0.f;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layer 1 forward
+// grid (point tiles, Cout / 64); 8 warps x 8 channels; a warp sweeps its tile 256 points at a time (8 per lane).
+constexpr int L1_CH_PER_WARP = 8;
+constexpr int L1_TILE_POINTS = 2048;
+
+__global__ void __launch_bounds__(256)
+pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         __nv_bfloat16* __restrict__ yT, int64_t ld, double* __restrict__ stats, int64_t P, int64_t TN,
+                         int Cout) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = (blockIdx.y * 8 + warp) * L1_CH_PER_WARP;
+    if (c0 >= Cout) return;
+    float wr[L1_CH_PER_WARP][4], br[L1_CH_PER_WARP], sc[L1_CH_PER_WARP], sh[L1_CH_PER_WARP];
+#pragma unroll
+    for (int k = 0; k < L1_CH_PER_WARP; ++k) {
+        const int c = min(c0 + k, Cout - 1);
+        const float4 t = __ldg(reinterpret_cast<const float4*>(w) + c);
+        wr[k][0] = t.x; wr[k][1] = t.y; wr[k][2] = t.z; wr[k][3] = t.w;
+        br[k] = bias ? __ldg(bias + c) : 0.f;
+        sc[k] = scale ? __ldg(scale + c) : 1.f;
+        sh[k] = shift ? __ldg(shift + c) : 0.f;
+    }
+    float s1[L1_CH_PER_WARP], s2[L1_CH_PER_WARP];
+#pragma unroll
+    for (int k = 0; k < L1_CH_PER_WARP; ++k) s1[k] = s2[k] = 0.f;
+    const int64_t tile0 = (int64_t)blockIdx.x * L1_TILE_POINTS;
+    for (int ch = 0; ch < L1_TILE_POINTS / 256; ++ch) {
+        const int64_t p0 = tile0 + ch * 256 + lane * 8;
+        if (p0 >= P) break;
+        float xv[4][8];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);
+        const bool full = p0 + 8 <= P;
+#pragma unroll
+        for (int k = 0; k < L1_CH_PER_WARP; ++k) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = fmaf(wr[k][3], xv[3][j], br[k]);
+                v = fmaf(wr[k][2], xv[2][j], v);
+                v = fmaf(wr[k][1], xv[1][j], v);
+                v = fmaf(wr[k][0], xv[0][j], v);
+                const float m = (full || p0 + j < P) ? v : 0.f;
+                s1[k] += m;
+                s2[k] = fmaf(m, m, s2[k]);
+                y[j] = scale ? elu_fast(fmaf(v, sc[k], sh[k])) : v;
+            }
+            if (c0 + k < Cout) *reinterpret_cast<uint4*>(yT + (int64_t)(c0 + k) * ld + p0) = pack8(y);
+        }
+    }
+    if (stats) {
+#pragma unroll
+        for (int k = 0; k < L1_CH_PER_WARP; ++k) {
+            const float a = warp_sum(s1[k]), b = warp_sum(s2[k]);
+            if (lane == 0 && c0 + k < Cout) {
+                atomicAdd(&stats[c0 + k], (double)a);
+                atomicAdd(&stats[Cout + c0 + k], (double)b);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layer 1 weight gradient
+// dW1[c][f] = sum_p dy[c][p] * x[f][p] with dy = c1[c]*dz + c2[c]*y + c3[c] formed on the fly (BatchNorm backward of
+// layer 1 fused in: its dy is never written) or dy = dz when y is null.
+__global__ void __launch_bounds__(256)
+pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dzT,
+                           const __nv_bfloat16* __restrict__ yT, int64_t ld, const float* __restrict__ c1,
+                           const float* __restrict__ c2, const float* __restrict__ c3, float* __restrict__ dW,
+                           int64_t P, int64_t TN, int Cout) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = (blockIdx.y * 8 + warp) * L1_CH_PER_WARP;
+    if (c0 >= Cout) return;
+    float a1[L1_CH_PER_WARP], a2[L1_CH_PER_WARP], a3[L1_CH_PER_WARP];
+#pragma unroll
+    for (int k = 0; k < L1_CH_PER_WARP; ++k) {
+        const int c = min(c0 + k, Cout - 1);
+        a1[k] = yT ? __ldg(c1 + c) : 1.f;
+        a2[k] = yT ? __ldg(c2 + c) : 0.f;
+        a3[k] = yT ? __ldg(c3 + c) : 0.f;
+    }
+    float acc[L1_CH_PER_WARP][4];
+#pragma unroll
+    for (int k = 0; k < L1_CH_PER_WARP; ++k)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[k][f] = 0.f;
+    const int64_t tile0 = (int64_t)blockIdx.x * L1_TILE_POINTS;
+    for (int ch = 0; ch < L1_TILE_POINTS / 256; ++ch) {
+        const int64_t p0 = tile0 + ch * 256 + lane * 8;
+        if (p0 >= P) break;
+        float xv[4][8];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);
+        const bool full = p0 + 8 <= P;
+#pragma unroll
+        for (int k = 0; k < L1_CH_PER_WARP; ++k) {
+            const int64_t off = (int64_t)min(c0 + k, Cout - 1) * ld + p0;
+            float dz[8], yv[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dzT + off)), dz);
+            if (yT) unpack8(__ldg(reinterpret_cast<const uint4*>(yT + off)), yv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float d = yT ? fmaf(a1[k], dz[j], fmaf(a2[k], yv[j], a3[k])) : dz[j];
+                d = (full || p0 + j < P) ? d : 0.f;          // pad columns hold unspecified bits (maybe NaN)
+#pragma unroll
+                for (int f = 0; f < 4; ++f) acc[k][f] = fmaf(d, xv[f][j], acc[k][f]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < L1_CH_PER_WARP; ++k)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const float t = warp_sum(acc[k][f]);
+            if (lane == 0 && c0 + k < Cout) atomicAdd(dW + (c0 + k) * 4 + f, t);
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ BN + ELU apply
+// grid (x blocks, C); every thread streams UNROLL chunks of 8 points of its channel row
+constexpr int EW_UNROLL = 4;
+
+__global__ void __launch_bounds__(256)
+bn_elu_apply_t_kernel(const __nv_bfloat16* __restrict__ yT, const float* __restrict__ scale,
+                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ outT, int64_t ld, int64_t P) {
+    const int c = blockIdx.y;
+    const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+    const __nv_bfloat16* src = yT + (int64_t)c * ld;
+    __nv_bfloat16* dst = outT + (int64_t)c * ld;
+    const int64_t base = ((int64_t)blockIdx.x * EW_UNROLL * 256 + threadIdx.x) * 8;
+    uint4 raw[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int64_t p0 = base + (int64_t)u * 256 * 8;
+        if (p0 < P) raw[u] = __ldg(reinterpret_cast<const uint4*>(src + p0));
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int64_t p0 = base + (int64_t)u * 256 * 8;
+        if (p0 < P) {
+            float v[8];
+            unpack8(raw[u], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = elu_fast(fmaf(v[j], sc, sh));
+            *reinterpret_cast<uint4*>(dst + p0) = pack8(v);
+        }
+    }
+}
+
+// dy = c1[c]*dz + c2[c]*y + c3[c]  (BatchNorm backward), may run in place on dz
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_t_kernel(const __nv_bfloat16* __restrict__ dzT, const __nv_bfloat16* __restrict__ yT,
+                      const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ c3,
+                      __nv_bfloat16* __restrict__ dyT, int64_t ld, int64_t P) {
+    const int c = blockIdx.y;
+    const float a1 = __ldg(c1 + c), a2 = __ldg(c2 + c), a3 = __ldg(c3 + c);
+    const int64_t row = (int64_t)c * ld;
+    const int64_t base = ((int64_t)blockIdx.x * EW_UNROLL * 256 + threadIdx.x) * 8;
+    uint4 rz[EW_UNROLL], ry[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int64_t p0 = base + (int64_t)u * 256 * 8;
+        if (p0 < P) {
+            rz[u] = __ldg(reinterpret_cast<const uint4*>(dzT + row + p0));
+            ry[u] = __ldg(reinterpret_cast<const uint4*>(yT + row + p0));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int64_t p0 = base + (int64_t)u * 256 * 8;
+        if (p0 < P) {
+            float z[8], y[8];
+            unpack8(rz[u], z);
+            unpack8(ry[u], y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z[j] = fmaf(a1, z[j], fmaf(a2, y[j], a3));
+            *reinterpret_cast<uint4*>(dyT + row + p0) = pack8(z);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ mean pool over points
+// pooled[g][c] = mean_{i<n} ELU(scale[c]*yT[c][g*n+i] + shift[c]); when e1/e2 are given (training) also
+// e1[g][c] = sum_i ELU'(z), e2[g][c] = sum_i ELU'(z)*xhat -- the group sums from which the backward's BatchNorm
+// statistics follow without another pass over the activations (d pooled / d z is constant over a group).
+// grid (ceil(G / 8), C / 32): warp w owns group g0 + w and walks the 32 channel rows of the block.
+__global__ void __launch_bounds__(256)
+bn_elu_meanpool_t_kernel(const __nv_bfloat16* __restrict__ yT, int64_t ld, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, float* __restrict__ pooled, float* __restrict__ e1,
+                         float* __restrict__ e2, int64_t G, int n, int C, int apply) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * 8 + warp;
+    if (g >= G) return;
+    const int cb = blockIdx.y * 32;
+    const bool pairs = ((n & 1) == 0) && ((ld & 1) == 0);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+        const int c = cb + i;
+        if (c >= C) break;
+        const float sc = apply ? __ldg(scale + c) : 1.f, sh = apply ? __ldg(shift + c) : 0.f;
+        const float mu = e1 ? __ldg(mean + c) : 0.f, is = e1 ? __ldg(invstd + c) : 0.f;
+        const __nv_bfloat16* src = yT + (int64_t)c * ld + g * n;
+        float s = 0.f, t1 = 0.f, t2 = 0.f;
+        if (pairs) {
+            for (int k = lane; k < n / 2; k += 32) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + 2 * k));
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float y = u ? f.y : f.x;
+                    const float z = fmaf(y, sc, sh);
+                    const float a = apply ? elu_fast(z) : z;
+                    s += a;
+                    if (e1) {
+                        const float d = z > 0.f ? 1.f : a + 1.f;
+                        t1 += d;
+                        t2 = fmaf(d, (y - mu) * is, t2);
+                    }
+                }
+            }
+        } else {
+            for (int k = lane; k < n; k += 32) {
+                const float y = __bfloat162float(src[k]);
+                const float z = fmaf(y, sc, sh);
+                const float a = apply ? elu_fast(z) : z;
+                s += a;
+                if (e1) {
+                    const float d = z > 0.f ? 1.f : a + 1.f;
+                    t1 += d;
+                    t2 = fmaf(d, (y - mu) * is, t2);
+                }
+            }
+        }
+        s = warp_sum(s);
+        if (e1) { t1 = warp_sum(t1); t2 = warp_sum(t2); }
+        if (lane == i) { r0 = s; r1 = t1; r2 = t2; }
+    }
+    if (cb + lane < C) {
+        const int64_t o = g * C + cb + lane;
+        pooled[o] = r0 / (float)n;
+        if (e1) { e1[o] = r1; e2[o] = r2; }
+    }
+}
+
+// stats2[c] += sum_g dpool[g][c]/n * e1[g][c]; stats2[C+c] += sum_g dpool[g][c]/n * e2[g][c]
+// grid (C / 32, row splits), block (32, 8)
+__global__ void __launch_bounds__(256)
+pool_bwd_stats_kernel(const float* __restrict__ dpool, const float* __restrict__ e1, const float* __restrict__ e2,
+                      double* __restrict__ stats2, int64_t G, int C, float inv_n) {
+    __shared__ float sm[2][8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float t1 = 0.f, t2 = 0.f;
+    if (c < C) {
+        for (int64_t g = (int64_t)blockIdx.y * 8 + threadIdx.y; g < G; g += (int64_t)gridDim.y * 8) {
+            const float d = __ldg(dpool + g * C + c) * inv_n;
+            t1 = fmaf(d, __ldg(e1 + g * C + c), t1);
+            t2 = fmaf(d, __ldg(e2 + g * C + c), t2);
+        }
+    }
+    sm[0][threadIdx.y][threadIdx.x] = t1;
+    sm[1][threadIdx.y][threadIdx.x] = t2;
+    __syncthreads();
+    if (threadIdx.y < 2 && c < C) {
+        double a = 0.0;
+        for (int l = 0; l < 8; ++l) a += (double)sm[threadIdx.y][l][threadIdx.x];
+        atomicAdd(&stats2[(int64_t)threadIdx.y * C + c], a);
+    }
+}
+
+// dyT[c][p] = c1[c] * (dpool[g(p)][c]/n) * ELU'(scale*y+shift) + c2[c]*y + c3[c]   (mean-pool backward, ELU backward
+// and BatchNorm backward of layer 4 in ONE pass over y4)
+__global__ void __launch_bounds__(256)
+pool_bwd_apply_t_kernel(const float* __restrict__ dpool, const __nv_bfloat16* __restrict__ yT,
+                        const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ c1,
+                        const float* __restrict__ c2, const float* __restrict__ c3, __nv_bfloat16* __restrict__ dyT,
+                        int64_t ld, int64_t P, int n, int C, float inv_n) {
+    const int c = blockIdx.y;
+    const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+    const float a1 = __ldg(c1 + c) * inv_n, a2 = __ldg(c2 + c), a3 = __ldg(c3 + c);
+    const int64_t row = (int64_t)c * ld;
+    const int64_t base = ((int64_t)blockIdx.x * EW_UNROLL * 256 + threadIdx.x) * 8;
+    uint4 ry[EW_UNROLL];
+    float g0v[EW_UNROLL], g1v[EW_UNROLL];
+    int split[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int64_t p0 = base + (int64_t)u * 256 * 8;
+        if (p0 < P) {
+            ry[u] = __ldg(reinterpret_cast<const uint4*>(yT + row + p0));
+            const int64_t g0 = p0 / n;
+            const int64_t nxt = (g0 + 1) * n - p0;             // first index (0..8+) that belongs to the next group
+            split[u] = nxt < 8 ? (int)nxt : 8;
+            g0v[u] = __ldg(dpool + g0 * C + c);
+            g1v[u] = (nxt < 8 && (g0 + 1) * n < P) ? __ldg(dpool + (g0 + 1) * C + c) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int64_t p0 = base + (int64_t)u * 256 * 8;
+        if (p0 < P) {
+            float y[8];
+            unpack8(ry[u], y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float z = fmaf(y[j], sc, sh);
+                float gv = j < split[u] ? g0v[u] : g1v[u];
+                if (n < 8) gv = (p0 + j < P) ? __ldg(dpool + ((p0 + j) / n) * C + c) : 0.f;   // tiny clouds: > 2 groups per chunk
+                const float d = gv * (z > 0.f ? 1.f : __expf(z));
+                y[j] = fmaf(a1, d, fmaf(a2, y[j], a3));
+            }
+            *reinterpret_cast<uint4*>(dyT + row + p0) = pack8(y);
+        }
+    }
+}
+
+}  // namespace pcaa
+
+using namespace pcaa;
+#define ST(s) ((cudaStream_t)(s))
+
+static inline unsigned ew_blocks(int64_t P) { return (unsigned)ceil_div(ceil_div(P, 8), 256 * EW_UNROLL); }
+
+extern "C" {
+
+int pcaa_pointnet_l1_fwd_t(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
+                           void* yT, int64_t ld, double* stats, int64_t B, int64_t TN, int Cout, pcaa_stream stream) {
+    if (B == 0) return PCAA_OK;
+    const int64_t P = B * TN;
+    PCAA_REQUIRE(ld % 8 == 0 && ld >= P && ((uintptr_t)yT & 15) == 0, PCAA_ERR_ALIGN, "pointnet_l1_fwd_t: ld must be a multiple of 8 and >= B*TN");
+    PCAA_REQUIRE(Cout > 0 && ((uintptr_t)w & 15) == 0, PCAA_ERR_SHAPE, "pointnet_l1_fwd_t: bad Cout / weight alignment");
+    PCAA_REQUIRE((scale == nullptr) == (shift == nullptr), PCAA_ERR_SHAPE, "pointnet_l1_fwd_t: scale and shift go together");
+    dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
+    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, ld, stats, P, TN, Cout);
+    return check_launch("pointnet_l1_fwd_t");
+}
+
+int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, int64_t ld, const float* c1,
+                             const float* c2, const float* c3, float* dW, int64_t B, int64_t TN, int Cout,
+                             pcaa_stream stream) {
+    if (cudaMemsetAsync(dW, 0, sizeof(float) * 4 * Cout, ST(stream)) != cudaSuccess) return check_launch("pointnet_l1_wgrad_t memset");
+    if (B == 0) return PCAA_OK;
+    const int64_t P = B * TN;
+    PCAA_REQUIRE(ld % 8 == 0 && ld >= P, PCAA_ERR_ALIGN, "pointnet_l1_wgrad_t: ld must be a multiple of 8 and >= B*TN");
+    PCAA_REQUIRE(yT == nullptr || (c1 && c2 && c3), PCAA_ERR_SHAPE, "pointnet_l1_wgrad_t: y needs the BatchNorm-backward coefficients");
+    dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
+    pointnet_l1_wgrad_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, (const __nv_bfloat16*)dzT, (const __nv_bfloat16*)yT, ld, c1, c2, c3, dW, P, TN, Cout);
+    return check_launch("pointnet_l1_wgrad_t");
+}
+
+int pcaa_bn_elu_apply_t(const void* yT, const float* scale, const float* shift, void* outT, int64_t ld, int64_t P, int C,
+                        pcaa_stream stream) {
+    if (P == 0 || C == 0) return PCAA_OK;
+    PCAA_REQUIRE(ld % 8 == 0 && ld >= P && C <= 65535, PCAA_ERR_ALIGN, "bn_elu_apply_t: ld must be a multiple of 8 and >= P");
+    bn_elu_apply_t_kernel<<<dim3(ew_blocks(P), C), 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, (__nv_bfloat16*)outT, ld, P);
+    return check_launch("bn_elu_apply_t");
+}
+
+int pcaa_bn_bwd_apply_t(const void* dzT, const void* yT, const float* c1, const float* c2, const float* c3, void* dyT,
+                        int64_t ld, int64_t P, int C, pcaa_stream stream) {
+    if (P == 0 || C == 0) return PCAA_OK;
+    PCAA_REQUIRE(ld % 8 == 0 && ld >= P && C <= 65535, PCAA_ERR_ALIGN, "bn_bwd_apply_t: ld must be a multiple of 8 and >= P");
+    bn_bwd_apply_t_kernel<<<dim3(ew_blocks(P), C), 256, 0, ST(stream)>>>((const __nv_bfloat16*)dzT, (const __nv_bfloat16*)yT, c1, c2, c3, (__nv_bfloat16*)dyT, ld, P);
+    return check_launch("bn_bwd_apply_t");
+}
+
+int pcaa_bn_elu_meanpool_t(const void* yT, int64_t ld, const float* scale, const float* shift, const float* mean,
+                           const float* invstd, float* pooled, float* e1, float* e2, int64_t G, int n, int C,
+                           pcaa_stream stream) {
+    if (G == 0 || C == 0) return PCAA_OK;
+    PCAA_REQUIRE(n > 0 && ld >= G * n, PCAA_ERR_SHAPE, "bn_elu_meanpool_t: bad group size / leading dimension");
+    PCAA_REQUIRE((e1 == nullptr) == (e2 == nullptr) && (e1 == nullptr || (mean && invstd && scale)), PCAA_ERR_SHAPE,
+                 "bn_elu_meanpool_t: e1/e2 need mean/invstd/scale");
+    const int apply = scale != nullptr;
+    dim3 grid((unsigned)ceil_div(G, 8), (unsigned)ceil_div(C, 32));
+    bn_elu_meanpool_t_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, ld, scale, shift, mean, invstd, pooled, e1, e2, G, n, C, apply);
+    return check_launch("bn_elu_meanpool_t");
+}
+
+int pcaa_pool_bwd_stats(const float* dpool, const float* e1, const float* e2, double* stats2, int64_t G, int n, int C,
+                        pcaa_stream stream) {
+    if (G == 0 || C == 0) return PCAA_OK;
+    int splits = (int)(G / 64);
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+    pool_bwd_stats_kernel<<<dim3((unsigned)ceil_div(C, 32), splits), dim3(32, 8), 0, ST(stream)>>>(dpool, e1, e2, stats2, G, C, 1.f / (float)n);
+    return check_launch("pool_bwd_stats");
+}
+
+int pcaa_pool_bwd_apply_t(const float* dpool, const void* yT, const float* scale, const float* shift, const float* c1,
+                          const float* c2, const float* c3, void* dyT, int64_t ld, int64_t G, int n, int C,
+                          pcaa_stream stream) {
+    if (G == 0 || C == 0) return PCAA_OK;
+    const int64_t P = G * n;
+    PCAA_REQUIRE(ld % 8 == 0 && ld >= P && C <= 65535 && n >= 1, PCAA_ERR_ALIGN, "pool_bwd_apply_t: ld must be a multiple of 8 and >= G*n");
+    pool_bwd_apply_t_kernel<<<dim3(ew_blocks(P), C), 256, 0, ST(stream)>>>(dpool, (const __nv_bfloat16*)yT, scale, shift, c1, c2, c3, (__nv_bfloat16*)dyT, ld, P, n, C, 1.f / (float)n);
+    return check_launch("pool_bwd_apply_t");
+}
+
+}  // extern "C"

@@ -4,8 +4,8 @@ Everything here is orchestration: which kernel runs on which buffer.  Parameters
 reference's ``state_dict`` names (relative to the module: e.g. ``pc_block.pointnet2.module.0.weight``), so the same
 functions serve the drop-in ``nn.Module``s (models.py) and the fused trainer (train.py).
 
-Layouts: point activations are channels-last bf16 ``[B*T*N, C]`` (rows ordered (b, t, n)); TCN / head / decoder
-activations are fp32 ``[rows, C]``.  Reference: models.py:82-160, 232-292, 340-385.
+Layouts: point activations are channel-major bf16 ``[C, pad8(B*T*N)]`` (points contiguous, ordered (b, t, n)); TCN /
+head / decoder activations are fp32 ``[rows, C]``.  Reference: models.py:82-160, 232-292, 340-385.
 """
 from __future__ import annotations
 
@@ -15,7 +15,7 @@ import torch
 
 from . import ops
 from ._lib import (ACT_ELU, ACT_NONE, TC_BIAS_ELU, TC_BIAS_STATS, TC_DGRAD_ELUBN, TC_DGRAD_ELUOUT, TC_PLAIN,
-                   TC_WGRAD_STORE)
+                   TC_T_AFFINE_ELU, TC_T_BIAS_STATS, TC_T_DGRAD_ELUBN, TC_WGRAD_ACC, TC_WGRAD_STORE)
 
 T_STEPS = 30
 DTC_DILATIONS = (1, 2, 4, 1, 2, 4)
@@ -39,11 +39,21 @@ def _zeros_like_param(gradbuf, name, ref):
 
 
 # ====================================================================================================== PointNet
-def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_block."):
-    """x (B,4,T,N) fp32 -> pooled [B*T, 1024] fp32 (mean over the N points of ELU(BN(conv))), saved state."""
+def _conv_w(P: Params, pre: str, l: int):
+    W = P[f"{pre}pointnet{l}.module.0.weight"]
+    return W.view(W.shape[0], W.shape[1])
+
+
+def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_block.", wb16: Optional[dict] = None):
+    """x (B,4,T,N) fp32 -> pooled [B*T, 1024] fp32 (mean over the N points of ELU(BN(conv))), saved state.
+
+    Activations are channel-major bf16 ``yT [C, pad8(B*T*N)]`` (points contiguous): the tcgen05 GEMM of layer l
+    computes ``y_l^T = W_l a_{l-1}^T`` with the channel as the accumulator row, so bias / BatchNorm coefficients are
+    per-thread scalars and the batch statistics are in-thread sums of its epilogue.  ``wb16`` optionally maps the
+    layer number to a ready bf16 copy of the [Cout, Cin] weight (the trainer's Adam-maintained shadow)."""
     B, F, T, N = x.shape
     R = B * T * N
-    sv = {"x": x, "N": N, "R": R, "y": [None] * 5, "a": [None] * 5, "coef": [None] * 5}
+    sv = {"x": x, "N": N, "R": R, "G": B * T, "y": [None] * 5, "a": [None] * 5, "coef": [None] * 5, "wb": [None] * 5}
 
     def bn_coef(l, stats):
         k = f"{pre}pointnet{l}.module.1."
@@ -52,29 +62,36 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
                                    BN_MOMENTUM, BN_EPS)
         return ops.bn_eval_coeffs(P[k + "weight"], P[k + "bias"], P[k + "running_mean"], P[k + "running_var"], BN_EPS)
 
-    k1 = f"{pre}pointnet1.module.0."
-    w1 = P[k1 + "weight"].view(P[k1 + "weight"].shape[0], 4)
-    y, st = ops.pointnet_l1_fwd(x, w1, P[k1 + "bias"], want_stats=training)
-    coef = bn_coef(1, st)
-    sv["y"][1], sv["coef"][1] = y, coef
-    a = ops.bn_elu_apply(y, coef[0], coef[1])
-    sv["a"][1] = a
+    b1 = P[f"{pre}pointnet1.module.0.bias"]
+    if training:
+        y, st = ops.pointnet_l1_fwd_t(x, _conv_w(P, pre, 1), b1)
+        coef = bn_coef(1, st)
+        a = ops.bn_elu_apply_t(y, coef, R)
+        sv["y"][1], sv["coef"][1], sv["a"][1] = y, coef, a
+    else:
+        a, _ = ops.pointnet_l1_fwd_t(x, _conv_w(P, pre, 1), b1, coef=bn_coef(1, None))
+    ld = a.shape[1]
     for l in (2, 3, 4):
-        k = f"{pre}pointnet{l}.module.0."
-        W = P[k + "weight"]
-        wb = ops.pack_bf16(W.view(W.shape[0], W.shape[1]))
+        W = _conv_w(P, pre, l)
+        Cout, Cin = W.shape
+        wb = wb16[l] if wb16 is not None else ops.pack_bf16(W)
+        bias = P[f"{pre}pointnet{l}.module.0.bias"]
+        out = torch.empty((Cout, ld), device=x.device, dtype=torch.bfloat16)
         if training:
-            st = torch.zeros(2 * W.shape[0], device=x.device, dtype=torch.float64)
-            y = ops.gemm_tc_tn(a, wb, TC_BIAS_STATS, bias=P[k + "bias"], stats=st)
+            st = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64)
+            y = ops.gemm_tc(wb, a, TC_T_BIAS_STATS, Cout, R, Cin, b_mn=True, out=out, bias=bias, stats=st)
+            coef = bn_coef(l, st)
+            sv["y"][l], sv["coef"][l], sv["wb"][l] = y, coef, wb
+            if l < 4:
+                a = ops.bn_elu_apply_t(y, coef, R)
+                sv["a"][l] = a
         else:
-            st = None
-            y = ops.gemm_tc_tn(a, wb, TC_PLAIN, bias=P[k + "bias"])
-        coef = bn_coef(l, st)
-        sv["y"][l], sv["coef"][l] = y, coef
-        if l < 4:
-            a = ops.bn_elu_apply(y, coef[0], coef[1])
-            sv["a"][l] = a
-    pooled = ops.bn_elu_meanpool(y, coef[0], coef[1], N)
+            a = ops.gemm_tc(wb, a, TC_T_AFFINE_ELU, Cout, R, Cin, b_mn=True, out=out, bias=bias, coef=bn_coef(l, None))
+    if training:
+        pooled, e1, e2 = ops.bn_elu_meanpool_t(y, coef, B * T, N, want_e=True)
+        sv["e1"], sv["e2"] = e1, e2
+    else:
+        pooled, _, _ = ops.bn_elu_meanpool_t(a, None, B * T, N)
     return pooled, sv
 
 
@@ -83,29 +100,39 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
     """gpool [B*T, 1024] fp32 = d loss / d pooled.  Returns parameter gradients (written into gradbuf when given)."""
     G: Grads = {}
     R, N = sv["R"], sv["N"]
-    dz, st2 = ops.elu_bwd_colstats(gpool, sv["y"][4], sv["coef"][4], pooled_n=N)
+    gpool = gpool.contiguous()
+    # layer 4: the BatchNorm-backward statistics follow from the forward's group sums (no pass over y4), then ONE pass
+    # forms dy4 = BN'(ELU'(pool'(gpool)))
+    st2 = ops.pool_bwd_stats(gpool, sv["e1"], sv["e2"], N)
+    kb = f"{pre}pointnet4.module.1."
+    c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][4], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
+    G[kb + "weight"], G[kb + "bias"] = dgam, dbet
+    dy = ops.pool_bwd_apply_t(gpool, sv["y"][4], sv["coef"][4], c, N)
     for l in (4, 3, 2):
-        kb = f"{pre}pointnet{l}.module.1."
         kc = f"{pre}pointnet{l}.module.0."
-        c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][l], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
-        G[kb + "weight"], G[kb + "bias"] = dgam, dbet
-        dy = ops.bn_bwd_apply(dz, sv["y"][l], c, out=dz)
         W = P[kc + "weight"]
+        Cout, Cin = W.shape[0], W.shape[1]
         dW = _zeros_like_param(gradbuf, kc + "weight", W)
-        ops.gemm_tc_nt_wgrad(dy, sv["a"][l - 1], dW.view(W.shape[0], W.shape[1]))
+        # dW[Cout, Cin] += dyT [Cout, P] . a_{l-1}T [Cin, P]^T   (both operands K-major, K = points, split over the SMs)
+        ops.gemm_tc(dy, sv["a"][l - 1], TC_WGRAD_ACC, Cout, Cin, R, out=dW.view(Cout, Cin))
         G[kc + "weight"] = dW
         # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero
         G[kc + "bias"] = _zeros_like_param(gradbuf, kc + "bias", P[kc + "bias"])
-        wT = ops.pack_bf16(W.view(W.shape[0], W.shape[1]), transpose=True)          # [Cin, Cout]
-        st2 = torch.zeros(2 * W.shape[1], device=gpool.device, dtype=torch.float64)
-        dz = ops.gemm_tc_tn(dy, wT, TC_DGRAD_ELUBN, stats=st2, yprev=sv["y"][l - 1], coef=sv["coef"][l - 1])
-    kb, kc = f"{pre}pointnet1.module.1.", f"{pre}pointnet1.module.0."
-    c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][1], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
-    G[kb + "weight"], G[kb + "bias"] = dgam, dbet
-    dy = ops.bn_bwd_apply(dz, sv["y"][1], c, out=dz)
+        # dz_{l-1}T [Cin, P] = (W^T dyT) * ELU'(BN(y_{l-1})) with the statistics of BatchNorm l-1's backward
+        st2 = torch.zeros(2 * Cin, device=gpool.device, dtype=torch.float64)
+        dz = torch.empty((Cin, dy.shape[1]), device=gpool.device, dtype=torch.bfloat16)
+        ops.gemm_tc(sv["wb"][l], dy, TC_T_DGRAD_ELUBN, Cin, R, Cout, a_mn=True, b_mn=True, out=dz, stats=st2,
+                    yprev=sv["y"][l - 1], coef=sv["coef"][l - 1])
+        kb = f"{pre}pointnet{l - 1}.module.1."
+        c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][l - 1], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
+        G[kb + "weight"], G[kb + "bias"] = dgam, dbet
+        if l > 2:
+            dy = ops.bn_bwd_apply_t(dz, sv["y"][l - 1], c, R, out=dz)
+    kc = f"{pre}pointnet1.module.0."
     W1 = P[kc + "weight"]
     o = _out(gradbuf, kc + "weight")
-    dW1 = ops.pointnet_l1_wgrad(sv["x"], dy, None if o is None else o.view(W1.shape[0], 4))
+    # layer 1: BatchNorm backward fused into the K = 4 weight gradient (dy1 is never materialised)
+    dW1 = ops.pointnet_l1_wgrad_t(sv["x"], dz, sv["y"][1], c, None if o is None else o.view(W1.shape[0], 4))
     G[kc + "weight"] = dW1.view(W1.shape) if o is None else o
     G[kc + "bias"] = _zeros_like_param(gradbuf, kc + "bias", P[kc + "bias"])
     return G
@@ -210,9 +237,9 @@ def heads_backward(dlogits: Optional[torch.Tensor], dfv_ext: Optional[torch.Tens
 
 
 # ====================================================================================================== encoder
-def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_head: bool):
+def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_head: bool, wb16: Optional[dict] = None):
     B, F, T, N = x.shape
-    pooled, sv_p = pointnet_forward(x, P, training)
+    pooled, sv_p = pointnet_forward(x, P, training, wb16=wb16)
     h6, sv_t = tcn_forward(pooled.view(B, T, -1), P, training)
     logits, fv, sv_h = heads_forward(h6, P, use_projection_head)
     return logits, fv, (sv_p, sv_t, sv_h)

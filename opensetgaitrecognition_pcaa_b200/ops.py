@@ -226,6 +226,84 @@ def pointnet_l1_wgrad(x, dy, out: Optional[torch.Tensor] = None):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ channel-major PointNet
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def pointnet_l1_fwd_t(x, w, bias, coef=None, want_stats=True):
+    """x (B,4,T,N) fp32 -> yT [Cout, pad8(B*T*N)] bf16 (+ row statistics); with coef = (scale, shift) the stored value is
+    ELU(scale*y + shift) (eval mode) and no statistics are produced."""
+    _chk(x, torch.float32), _chk(w, torch.float32)
+    B, F, T, N = x.shape
+    Cout = w.shape[0]
+    ld = pad8(B * T * N)
+    yT = torch.empty((Cout, ld), device=x.device, dtype=torch.bfloat16)
+    stats = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64) if (want_stats and coef is None) else None
+    sc, sh = (None, None) if coef is None else (coef[0], coef[1])
+    call("pcaa_pointnet_l1_fwd_t", _p(x), _p(w), _p(bias), _p(sc), _p(sh), _p(yT), ld, _p(stats), B, T * N, Cout, _s())
+    return yT, stats
+
+
+def pointnet_l1_wgrad_t(x, dzT, yT=None, c=None, out: Optional[torch.Tensor] = None):
+    """dW1 [Cout,4] = sum_p (c1*dzT + c2*yT + c3)[c,p] * x[f,p]  (yT / c None: dy = dzT)."""
+    B, F, T, N = x.shape
+    Cout = dzT.shape[0]
+    if out is None:
+        out = torch.empty((Cout, 4), device=x.device, dtype=torch.float32)
+    c1, c2, c3 = (None, None, None) if c is None else (c[0], c[1], c[2])
+    call("pcaa_pointnet_l1_wgrad_t", _p(x), _p(dzT), _p(yT), dzT.stride(0), _p(c1), _p(c2), _p(c3), _p(out), B, T * N,
+         Cout, _s())
+    return out
+
+
+def bn_elu_apply_t(yT, coef, P: int):
+    out = torch.empty_like(yT)
+    call("pcaa_bn_elu_apply_t", _p(yT), _p(coef[0]), _p(coef[1]), _p(out), yT.stride(0), P, yT.shape[0], _s())
+    return out
+
+
+def bn_bwd_apply_t(dzT, yT, c, P: int, out: Optional[torch.Tensor] = None):
+    if out is None:
+        out = torch.empty_like(dzT)
+    call("pcaa_bn_bwd_apply_t", _p(dzT), _p(yT), _p(c[0]), _p(c[1]), _p(c[2]), _p(out), yT.stride(0), P, yT.shape[0], _s())
+    return out
+
+
+def bn_elu_meanpool_t(yT, coef, G: int, n: int, want_e=False):
+    """pooled [G, C] fp32 = mean over each group of n points of ELU(scale*yT+shift) (coef None: plain mean); with
+    want_e also the group sums e1 = sum ELU'(z), e2 = sum ELU'(z)*xhat used by the backward statistics."""
+    Cc = yT.shape[0]
+    pooled = torch.empty((G, Cc), device=yT.device, dtype=torch.float32)
+    e1 = torch.empty_like(pooled) if want_e else None
+    e2 = torch.empty_like(pooled) if want_e else None
+    sc = sh = mu = inv = None
+    if coef is not None:
+        sc, sh = coef[0], coef[1]
+        if want_e:
+            mu, inv = coef[2], coef[3]
+    call("pcaa_bn_elu_meanpool_t", _p(yT), yT.stride(0), _p(sc), _p(sh), _p(mu), _p(inv), _p(pooled), _p(e1), _p(e2), G,
+         n, Cc, _s())
+    return pooled, e1, e2
+
+
+def pool_bwd_stats(dpool, e1, e2, n: int):
+    _chk(dpool, torch.float32)
+    G, Cc = dpool.shape
+    stats2 = torch.zeros(2 * Cc, device=dpool.device, dtype=torch.float64)
+    call("pcaa_pool_bwd_stats", _p(dpool), _p(e1), _p(e2), _p(stats2), G, n, Cc, _s())
+    return stats2
+
+
+def pool_bwd_apply_t(dpool, yT, coef, c, n: int):
+    _chk(dpool, torch.float32)
+    G, Cc = dpool.shape
+    out = torch.empty_like(yT)
+    call("pcaa_pool_bwd_apply_t", _p(dpool), _p(yT), _p(coef[0]), _p(coef[1]), _p(c[0]), _p(c[1]), _p(c[2]), _p(out),
+         yT.stride(0), G, n, Cc, _s())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core GEMMs
 def gemm_tc_tn(a, w, mode: int, *, bias=None, stats=None, yprev=None, coef=None, out=None):
     """out[M,N] (bf16) = epilogue(a[M,K] @ w[N,K]^T); tcgen05 kernel (see include/pcaa.h for the modes)."""
@@ -257,7 +335,9 @@ def gemm_tc(a, b, mode: int, M: int, N: int, K: int, *, a_mn=False, b_mn=False, 
             out = torch.empty((M, N), device=a.device, dtype=torch.float32)
     sc = sh = mu = inv = None
     if coef is not None:
-        sc, sh, mu, inv = coef[0], coef[1], coef[2], coef[3]
+        sc, sh = coef[0], coef[1]
+        if len(coef) >= 4:
+            mu, inv = coef[2], coef[3]
     call("pcaa_gemm_tc", _p(a), a.stride(0), 1 if a_mn else 0, _p(b), b.stride(0), 1 if b_mn else 0, _p(out),
          out.stride(0), _DT[out.dtype], M, N, K, mode, _p(bias), _p(stats), _p(yprev),
          0 if yprev is None else yprev.stride(0), _p(sc), _p(sh), _p(mu), _p(inv), _s())
