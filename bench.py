@@ -171,25 +171,22 @@ def run_b200(args):
 
     # ---- device-resident throughput, with CUDA events around every tensor-core GEMM launch
     tc_events = []
-    orig_tn, orig_wg = ops.gemm_tc_tn, ops.gemm_tc_nt_wgrad
+    orig_tc = ops.gemm_tc
     record = {"on": False}
+    POINTNET_MODES = (_lib.TC_T_BIAS_STATS, _lib.TC_T_DGRAD_ELUBN, _lib.TC_WGRAD_ACC)
 
-    def timed(fn, flops_of):
-        def w(*a, **k):
-            if not record["on"]:
-                return fn(*a, **k)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn(*a, **k)
-            e1.record()
-            tc_events.append((e0, e1, flops_of(*a, **k)))
-            return r
-        return w
+    def timed_gemm_tc(a, b, mode, M, N, K, **k):
+        # CUDA events (torch's current stream = the launch stream) around every PointNet tcgen05 GEMM launch
+        if not record["on"] or mode not in POINTNET_MODES:
+            return orig_tc(a, b, mode, M, N, K, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_tc(a, b, mode, M, N, K, **k)
+        e1.record()
+        tc_events.append((e0, e1, 2.0 * M * N * K))
+        return r
 
-    ops.gemm_tc_tn = timed(orig_tn, lambda a, w, *r, **k: 2.0 * a.shape[0] * a.shape[1] * w.shape[0])
-    ops.gemm_tc_nt_wgrad = timed(orig_wg, lambda a, b, dW: 2.0 * a.shape[0] * a.shape[1] * b.shape[1])
-    from opensetgaitrecognition_pcaa_b200 import engine
-    engine.ops = ops
+    ops.gemm_tc = timed_gemm_tc
 
     for i in range(args.warmup):
         trainer.step(*devb[i % nb])

@@ -58,23 +58,30 @@ int pcaa_gemm_simt(const void* A, int a_dtype, int64_t sam, int64_t sak,
 typedef enum { PCAA_TC_BIAS_STATS = 0, PCAA_TC_BIAS_ELU = 1, PCAA_TC_PLAIN = 2, PCAA_TC_DGRAD_ELUBN = 3,
                PCAA_TC_WGRAD_ACC = 4, PCAA_TC_DGRAD_ELUOUT = 5, PCAA_TC_WGRAD_STORE = 6,
                PCAA_TC_T_BIAS_STATS = 7, PCAA_TC_T_AFFINE_ELU = 8, PCAA_TC_T_DGRAD_ELUBN = 9 } pcaa_tc_mode;
+/* operand storage: PCAA_OP_K     A(m,k) at A[m*lda + k]  (B(n,k) at B[n*ldb + k]),  "K-major"
+ *                  PCAA_OP_MN    A(m,k) at A[k*lda + m]  (B(n,k) at B[k*ldb + n]),  "MN-major"
+ *                  PCAA_OP_T256_* the channel-major activation format of the PointNet path: element (channel c, point p)
+ *                  at X[((p / 256) * C + c) * 256 + p % 256] -- 256-point tiles, each a contiguous [C, 256] block, the last
+ *                  tile zero-padded.  _K: the points are the k index (weight gradient); _MN: the points are the n index. */
+typedef enum { PCAA_OP_K = 0, PCAA_OP_MN = 1, PCAA_OP_T256_K = 2, PCAA_OP_T256_MN = 3 } pcaa_operand_layout;
 /* General form.  out[m,n] = epilogue( sum_k A(m,k) B(n,k) ), bf16 operands, fp32 accumulation in TMEM.
- * A(m,k) is stored [M,K] (a_mn = 0, "K-major") or [K,M] (a_mn = 1, "MN-major"); B(n,k) is stored [N,K] (b_mn = 0) or
- * [K,N] (b_mn = 1); leading dimensions in elements, multiples of 8.  out_dtype: PCAA_BF16 or PCAA_F32 (modes 1, 2).
+ * a_mn / b_mn are pcaa_operand_layout values; leading dimensions in elements, multiples of 8 (ignored for T256).  out_dtype: PCAA_BF16 or PCAA_F32 (modes 1, 2).
  * Extra modes: PCAA_TC_WGRAD_ACC   out (fp32) += A B^T, split over k across the SMs (weight gradient, k = rows);
  *              PCAA_TC_WGRAD_STORE out (fp32)  = A B^T (no split, plain stores: decoder weight gradient, k = batch);
  *              PCAA_TC_DGRAD_ELUOUT out = (A B^T) * (a > 0 ? 1 : a + 1) with a = yprev [M, ldy] the saved bf16 OUTPUT
  *                                  of the previous layer's ELU (decoder data gradient, models.py:373-382).
- * Channel-major ("T") modes -- the PointNet path keeps activations channels-first, yT [C, P] with the P = B*T*N points
- * contiguous, so the output ROW is the channel: per-channel parameters are per-row, BatchNorm statistics are per-row
- * sums over the columns n < N, kept in registers across all tiles of a CTA and added to stats[2M] once:
+ * Channel-major ("T") modes -- the PointNet path keeps activations channels-first in 256-point tiles (T256, above), so
+ * the output ROW is the channel: per-channel parameters are per-row, BatchNorm statistics are per-row sums over the
+ * points n < N, kept in registers across all tiles of a CTA and added to stats[2M] once.  B must be PCAA_OP_T256_MN,
+ * out (and yprev) are T256 with C = M; points >= N of the last tile are written as zeros:
  *   PCAA_TC_T_BIAS_STATS  out[m,n] = acc + bias[m] (bf16); stats[m] += sum_n out, stats[M+m] += sum_n out^2
  *                         (forward of models.py:21-29: A = W [Cout,Cin], B = aT [Cin,P] read MN-major)
  *   PCAA_TC_T_AFFINE_ELU  out[m,n] = ELU(scale[m]*(acc + bias[m]) + shift[m])  (eval mode: BatchNorm with running
  *                         statistics applied in the epilogue -> the next layer's activation in one pass)
  *   PCAA_TC_T_DGRAD_ELUBN out[m,n] = acc * ELU'(scale[m]*yprev[m,n] + shift[m]); stats += [sum dz, sum dz*xhat]
  *                         (A = W read MN-major = W^T, B = dyT [Cout,P] MN-major; yprev = yT of the previous layer)
- * Instantiated layouts: (a_mn,b_mn) = (0,0) modes 0-4, 6; (0,1) modes 2, 5, 7, 8; (1,1) modes 4, 6, 9. */
+ * Instantiated layouts (a,b): (K,K) modes 0-4, 6; (K,MN) 2, 5; (MN,MN) 4, 6; (K,T256_MN) 7, 8; (MN,T256_MN) 9;
+ * (T256_K,T256_K) 4 (PointNet weight gradient, k = points). */
 int pcaa_gemm_tc(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo,
                  int out_dtype, int64_t M, int64_t N, int64_t K, int mode, const float* bias, double* stats,
                  const void* yprev, int64_t ldy, const float* scale, const float* shift, const float* mean,
@@ -98,36 +105,34 @@ int pcaa_pointnet_l1_fwd(const float* x, const float* w, const float* bias, void
 int pcaa_pointnet_l1_wgrad(const float* x, const void* dy, float* dW, int64_t B, int64_t TN, int Cout,
                            pcaa_stream stream);
 
-/* ---- channel-major ("T") PointNet kernels: activations yT [C, ld] bf16, the P = B*TN points contiguous, ld = P rounded
- * up to a multiple of 8 (pad columns hold unspecified values and are never consumed) ------------------------------
- * layer 1, models.py:86-88: yT[c,p] = sum_f w[c,f] x[b,f,tn] + bias[c]; stats (nullable) += [sum_p y, sum_p y^2];
+/* ---- channel-major PointNet kernels on the T256 activation format (see pcaa_operand_layout): bf16, element (c, p) at
+ * X[((p / 256) * C + c) * 256 + p % 256], P = B*TN points ordered (b, t, n), pad points of the last tile stored as zeros.
+ * layer 1, models.py:86-88: y(c,p) = sum_f w[c,f] x[b,f,tn] + bias[c]; stats (nullable) += [sum_p y, sum_p y^2];
  * with scale/shift (eval mode, BatchNorm folded) the stored value is ELU(scale[c]*y + shift[c]) instead. */
 int pcaa_pointnet_l1_fwd_t(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
-                           void* yT, int64_t ld, double* stats, int64_t B, int64_t TN, int Cout, pcaa_stream stream);
-/* dW[Cout,4] (overwritten) = sum_p dy[c,p] x[f,p], dy = c1[c]*dzT + c2[c]*yT + c3[c] (BatchNorm backward fused; yT and
+                           void* yT, double* stats, int64_t B, int64_t TN, int Cout, pcaa_stream stream);
+/* dW[Cout,4] (overwritten) = sum_p dy(c,p) x[f,p], dy = c1[c]*dzT + c2[c]*yT + c3[c] (BatchNorm backward fused; yT and
  * the coefficients null: dy = dzT) */
-int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, int64_t ld, const float* c1,
-                             const float* c2, const float* c3, float* dW, int64_t B, int64_t TN, int Cout,
-                             pcaa_stream stream);
+int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, const float* c1, const float* c2,
+                             const float* c3, float* dW, int64_t B, int64_t TN, int Cout, pcaa_stream stream);
 /* outT = ELU(scale[c]*yT + shift[c])  (models.py:29, 33-34) */
-int pcaa_bn_elu_apply_t(const void* yT, const float* scale, const float* shift, void* outT, int64_t ld, int64_t P, int C,
+int pcaa_bn_elu_apply_t(const void* yT, const float* scale, const float* shift, void* outT, int64_t P, int C,
                         pcaa_stream stream);
 /* dyT = c1[c]*dzT + c2[c]*yT + c3[c]  (BatchNorm backward; may run in place on dzT) */
 int pcaa_bn_bwd_apply_t(const void* dzT, const void* yT, const float* c1, const float* c2, const float* c3, void* dyT,
-                        int64_t ld, int64_t P, int C, pcaa_stream stream);
-/* pooled[g,c] = mean_{i<n} ELU(scale[c]*yT[c, g*n+i] + shift[c])  (AvgPool2d((1,nmax)), models.py:242-243, 282; scale
+                        int64_t P, int C, pcaa_stream stream);
+/* pooled[g,c] = mean_{i<n} ELU(scale[c]*y(c, g*n+i) + shift[c])  (AvgPool2d((1,nmax)), models.py:242-243, 282; scale
  * null: plain mean of yT).  Training: e1[g,c] = sum_i ELU'(z), e2[g,c] = sum_i ELU'(z)*xhat (needs mean/invstd). */
-int pcaa_bn_elu_meanpool_t(const void* yT, int64_t ld, const float* scale, const float* shift, const float* mean,
+int pcaa_bn_elu_meanpool_t(const void* yT, const float* scale, const float* shift, const float* mean,
                            const float* invstd, float* pooled, float* e1, float* e2, int64_t G, int n, int C,
                            pcaa_stream stream);
 /* BatchNorm-backward statistics of the pooled layer from the group sums: stats2 += [sum_g dpool/n*e1, sum_g dpool/n*e2] */
 int pcaa_pool_bwd_stats(const float* dpool, const float* e1, const float* e2, double* stats2, int64_t G, int n, int C,
                         pcaa_stream stream);
-/* dyT[c,p] = c1[c]*(dpool[g(p),c]/n)*ELU'(scale[c]*yT+shift[c]) + c2[c]*yT + c3[c]: mean-pool, ELU and BatchNorm
- * backward of the last PointNet layer in one pass */
+/* dy(c,p) = c1[c]*(dpool[g(p),c]/n)*ELU'(scale[c]*y+shift[c]) + c2[c]*y + c3[c]: mean-pool, ELU and BatchNorm
+ * backward of the last PointNet layer in one pass (P = G*n) */
 int pcaa_pool_bwd_apply_t(const float* dpool, const void* yT, const float* scale, const float* shift, const float* c1,
-                          const float* c2, const float* c3, void* dyT, int64_t ld, int64_t G, int n, int C,
-                          pcaa_stream stream);
+                          const float* c2, const float* c3, void* dyT, int64_t G, int n, int C, pcaa_stream stream);
 
 /* ---- BatchNorm (train) + ELU on channels-last rows, models.py:29,33-34,72-78 ------------------------------ */
 int pcaa_colstats(const void* y, int dtype, int64_t R, int C, double* stats, pcaa_stream stream);

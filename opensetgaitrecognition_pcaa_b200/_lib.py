@@ -15,6 +15,7 @@ ACT_NONE, ACT_ELU = 0, 1
 EW_MUL, EW_ADD, EW_ELU, EW_ELU_GRAD, EW_ELU_GRAD2, EW_ADD_ROWVEC = range(6)
 TC_BIAS_STATS, TC_BIAS_ELU, TC_PLAIN, TC_DGRAD_ELUBN, TC_WGRAD_ACC, TC_DGRAD_ELUOUT, TC_WGRAD_STORE = range(7)
 TC_T_BIAS_STATS, TC_T_AFFINE_ELU, TC_T_DGRAD_ELUBN = 7, 8, 9
+OP_K, OP_MN, OP_T256_K, OP_T256_MN = range(4)          # pcaa_operand_layout
 
 _p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
@@ -26,13 +27,13 @@ SIGNATURES = {
     "pcaa_gemm_tc_nt_wgrad": [_p, _l, _p, _l, _p, _l, _l, _l, _l, _p],
     "pcaa_pointnet_l1_fwd": [_p, _p, _p, _p, _p, _l, _l, _i, _p],
     "pcaa_pointnet_l1_wgrad": [_p, _p, _p, _l, _l, _i, _p],
-    "pcaa_pointnet_l1_fwd_t": [_p, _p, _p, _p, _p, _p, _l, _p, _l, _l, _i, _p],
-    "pcaa_pointnet_l1_wgrad_t": [_p, _p, _p, _l, _p, _p, _p, _p, _l, _l, _i, _p],
-    "pcaa_bn_elu_apply_t": [_p, _p, _p, _p, _l, _l, _i, _p],
-    "pcaa_bn_bwd_apply_t": [_p, _p, _p, _p, _p, _p, _l, _l, _i, _p],
-    "pcaa_bn_elu_meanpool_t": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
+    "pcaa_pointnet_l1_fwd_t": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _p],
+    "pcaa_pointnet_l1_wgrad_t": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _p],
+    "pcaa_bn_elu_apply_t": [_p, _p, _p, _p, _l, _i, _p],
+    "pcaa_bn_bwd_apply_t": [_p, _p, _p, _p, _p, _p, _l, _i, _p],
+    "pcaa_bn_elu_meanpool_t": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
     "pcaa_pool_bwd_stats": [_p, _p, _p, _p, _l, _i, _i, _p],
-    "pcaa_pool_bwd_apply_t": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _i, _p],
+    "pcaa_pool_bwd_apply_t": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
     "pcaa_colstats": [_p, _i, _l, _i, _p, _p],
     "pcaa_bn_finalize": [_p, _l, _i, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p],
     "pcaa_bn_eval_coeffs": [_p, _p, _p, _p, _f, _p, _p, _i, _p],

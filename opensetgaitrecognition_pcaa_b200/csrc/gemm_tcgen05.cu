@@ -44,6 +44,7 @@ struct GemmParams {
     const __nv_bfloat16* yprev;   // [M, ldy] (MODE_DGRAD_ELUBN)
     int64_t ldy;
     const float *scale, *shift, *mean, *invstd;
+    int a_tiled, b_tiled;         // operand stored as 256-point tiles [n_tiles][C][256] (3-D tensor map), see pcaa.h
     int sched_mfixed;             // tile order: 0 = items strided over the grid; 1 = CTA keeps one m block (T modes)
 };
 
@@ -105,6 +106,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -263,14 +270,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* sb = sa + L::A_BYTES;
                     mbar_expect_tx(&full[stage], L::STAGE_BYTES);
                     if constexpr (!A_MN) {
-                        tma_load_2d(&tmA, &full[stage], sa, kb * BK, m_blk * BM);
+                        // tiled: k = points, 4 k blocks per 256-point tile, rows = channels
+                        if (p.a_tiled) tma_load_3d(&tmA, &full[stage], sa, (kb & 3) * BK, m_blk * BM, kb >> 2);
+                        else tma_load_2d(&tmA, &full[stage], sa, kb * BK, m_blk * BM);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BM / 64; ++i)
                             tma_load_2d(&tmA, &full[stage], sa + i * (BK * 128), m_blk * BM + i * 64, kb * BK);
                     }
                     if constexpr (!B_MN) {
-                        tma_load_2d(&tmB, &full[stage], sb, kb * BK, n_blk * BN);
+                        if (p.b_tiled) tma_load_3d(&tmB, &full[stage], sb, (kb & 3) * BK, n_blk * BN, kb >> 2);
+                        else tma_load_2d(&tmB, &full[stage], sb, kb * BK, n_blk * BN);
+                    } else if (p.b_tiled) {
+                        // n = points: the n block IS the 256-point tile (BN == 256), k rows = channels
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            tma_load_3d(&tmB, &full[stage], sb + i * (BK * 128), i * 64, kb * BK, n_blk);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BN / 64; ++i)
@@ -367,12 +382,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t (&r)[32] = (c & 1) ? rb : ra;
                 uint32_t (&rn)[32] = (c & 1) ? ra : rb;
                 const int64_t col0 = n0 + c * 32;
-                const bool any = row_ok && col0 < p.N;
+                // tiled addressing: element (row, point) lives at ((tile * M + row) * 256 + point % 256)
+                const int64_t toff = ((int64_t)n_blk * p.M + (row_ok ? row : 0)) * BN + half * (BN / 2) + c * 32;
                 uint4 yraw[4];
                 if constexpr (MODE == MODE_T_DGRAD_ELUBN) {
-                    const uint4* yp = reinterpret_cast<const uint4*>(p.yprev + (any ? row * p.ldy + col0 : 0));
+                    const uint4* yp = reinterpret_cast<const uint4*>(p.yprev + toff);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) yraw[g] = (any && col0 + g * 8 < p.N) ? __ldg(yp + g) : make_uint4(0, 0, 0, 0);
+                    for (int g = 0; g < 4; ++g) yraw[g] = row_ok ? __ldg(yp + g) : make_uint4(0, 0, 0, 0);
                 }
                 tmem_ld_wait(r);
                 if (c + 1 < CPW) tmem_ld32_issue(taddr + (c + 1) * 32, rn);
@@ -383,16 +399,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if constexpr (MODE == MODE_T_BIAS_STATS) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        v[j] += r_bias;
-                        const float m = (full_chunk || col0 + j < p.N) ? v[j] : 0.f;
-                        t1 += m;
-                        t2 = fmaf(m, m, t2);
+                        v[j] = (full_chunk || col0 + j < p.N) ? v[j] + r_bias : 0.f;     // pad points are stored as zeros
+                        t1 += v[j];
+                        t2 = fmaf(v[j], v[j], t2);
                     }
                 } else if constexpr (MODE == MODE_T_AFFINE_ELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float z = fmaf(v[j], r_scale, r_shift);
-                        v[j] = z > 0.f ? z : __expf(z) - 1.f;
+                        v[j] = (full_chunk || col0 + j < p.N) ? (z > 0.f ? z : __expf(z) - 1.f) : 0.f;
                     }
                 } else {
 #pragma unroll
@@ -406,26 +421,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const int j = g * 8 + 2 * e + u;
                                 const float yv = u ? f.y : f.x;
                                 const float z = fmaf(yv, r_scale, r_shift);
-                                float gq = v[j] * (z > 0.f ? 1.f : __expf(z));
-                                gq = (full_chunk || col0 + j < p.N) ? gq : 0.f;
+                                const bool in = full_chunk || col0 + j < p.N;   // pad columns may hold NaN bits
+                                const float gq = in ? v[j] * (z > 0.f ? 1.f : __expf(z)) : 0.f;
+                                const float xh = in ? (yv - r_mean) * r_invstd : 0.f;
                                 v[j] = gq;
                                 t1 += gq;
-                                t2 = fmaf(gq, (yv - r_mean) * r_invstd, t2);
+                                t2 = fmaf(gq, xh, t2);
                             }
                         }
                     }
                 }
-                if (any) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
+                if (row_ok) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + toff;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        if (col0 + g * 8 < p.N) {
-                            uint4 u;
-                            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-                            *reinterpret_cast<uint4*>(o + g * 8) = u;
-                        }
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                        *reinterpret_cast<uint4*>(o + g * 8) = u;
                     }
                 }
             }
@@ -653,6 +667,22 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t d0, int64_t d1, int
     return PCAA_OK;
 }
 
+// 3-D bf16 tensor map of a tiled operand [n_tiles][C][256]: box = b0 points x b1 channels x 1 tile
+static int make_map_tiled(CUtensorMap* m, const void* ptr, int64_t C, int64_t n_tiles, int b0, int b1) {
+    EncodeTiledFn enc = get_encode();
+    PCAA_REQUIRE(enc != nullptr, PCAA_ERR_DRIVER, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    PCAA_REQUIRE(((uintptr_t)ptr & 15) == 0, PCAA_ERR_ALIGN, "tiled tensor-core operand must be 16-byte aligned");
+    cuuint64_t dims[3] = {256, (cuuint64_t)C, (cuuint64_t)n_tiles};
+    cuuint64_t strides[2] = {256 * 2, (cuuint64_t)C * 256 * 2};
+    cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PCAA_REQUIRE(r == CUDA_SUCCESS, PCAA_ERR_DRIVER, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+    return PCAA_OK;
+}
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -698,11 +728,14 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
 using namespace pcaa;
 
 // A(m,k): a_mn == 0 -> stored [M, K] (lda), else stored [K, M] (lda).  B(n,k): b_mn == 0 -> [N, K], else [K, N].
-static int gemm_tc_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out,
+static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void* B, int64_t ldb, int b_layout, void* out,
                             int64_t ldo, int out_dtype, int64_t M, int64_t N, int64_t K, int mode, const float* bias,
                             double* stats, const void* yprev, int64_t ldy, const float* scale, const float* shift,
                             const float* mean, const float* invstd, cudaStream_t st) {
     if (M == 0 || N == 0) return PCAA_OK;
+    PCAA_REQUIRE(a_layout >= 0 && a_layout <= 3 && b_layout >= 0 && b_layout <= 3, PCAA_ERR_UNSUPPORTED, "gemm_tc: bad operand layout");
+    const int a_mn = a_layout & 1, b_mn = b_layout & 1;
+    const bool a_tiled = a_layout >= 2, b_tiled = b_layout >= 2;
     PCAA_REQUIRE(M > 0 && N > 0 && K > 0, PCAA_ERR_SHAPE, "gemm_tc: bad shape");
     PCAA_REQUIRE(mode >= 0 && mode <= PCAA_TC_T_DGRAD_ELUBN, PCAA_ERR_UNSUPPORTED, "gemm_tc: unknown mode %d", mode);
     const bool tmode = mode >= PCAA_TC_T_BIAS_STATS;
@@ -712,8 +745,12 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_mn, const void* B,
     // epilogue of zero accumulators); fp32 rows use 16-byte stores when aligned, scalar stores otherwise (wgrad only)
     const bool scalar_out = f32out && (((uintptr_t)out & 15) != 0 || ldo % 4 != 0 || N % 4 != 0);
     PCAA_REQUIRE(!scalar_out || wgrad, PCAA_ERR_ALIGN, "gemm_tc: fp32 output needs 16-byte aligned rows (ldo %% 4 == 0, N %% 4 == 0)");
-    PCAA_REQUIRE(f32out || (((uintptr_t)out & 15) == 0 && ldo % 8 == 0 && ldo >= (N + 7) / 8 * 8), PCAA_ERR_ALIGN,
+    PCAA_REQUIRE(f32out || tmode || (((uintptr_t)out & 15) == 0 && ldo % 8 == 0 && ldo >= (N + 7) / 8 * 8), PCAA_ERR_ALIGN,
                  "gemm_tc: bf16 output needs 16-byte aligned rows with ldo >= round_up(N, 8)");
+    if (tmode)
+        PCAA_REQUIRE(((uintptr_t)out & 15) == 0 && b_layout == PCAA_OP_T256_MN && !a_tiled, PCAA_ERR_UNSUPPORTED,
+                     "gemm_tc: channel-major modes take B as 256-point tiles (PCAA_OP_T256_MN) and write tiled output");
+    PCAA_REQUIRE(!a_tiled || a_layout == PCAA_OP_T256_K, PCAA_ERR_UNSUPPORTED, "gemm_tc: a tiled A operand must be PCAA_OP_T256_K");
     if (mode == PCAA_TC_BIAS_STATS || mode == PCAA_TC_DGRAD_ELUBN || mode == PCAA_TC_T_BIAS_STATS || mode == PCAA_TC_T_DGRAD_ELUBN)
         PCAA_REQUIRE(stats != nullptr, PCAA_ERR_SHAPE, "gemm_tc: stats buffer required for mode %d", mode);
     if (mode == PCAA_TC_DGRAD_ELUBN || mode == PCAA_TC_T_DGRAD_ELUBN)
@@ -721,19 +758,26 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_mn, const void* B,
     if (mode == PCAA_TC_T_AFFINE_ELU) PCAA_REQUIRE(scale && shift, PCAA_ERR_SHAPE, "gemm_tc: mode 8 needs scale/shift");
     if (tmode) PCAA_REQUIRE(out_dtype == PCAA_BF16, PCAA_ERR_UNSUPPORTED, "gemm_tc: channel-major modes store bf16");
     if (mode == PCAA_TC_DGRAD_ELUOUT) PCAA_REQUIRE(yprev != nullptr, PCAA_ERR_SHAPE, "gemm_tc: mode 5 needs the saved activation");
-    if (yprev) PCAA_REQUIRE(((uintptr_t)yprev & 15) == 0 && ldy % 8 == 0, PCAA_ERR_ALIGN, "gemm_tc: yprev alignment");
+    if (yprev) PCAA_REQUIRE(((uintptr_t)yprev & 15) == 0 && (tmode || ldy % 8 == 0), PCAA_ERR_ALIGN, "gemm_tc: yprev alignment");
     constexpr int BN = 256;
     CUtensorMap ta, tb;
-    int rc = a_mn ? make_map(&ta, A, M, K, lda, 64, BK) : make_map(&ta, A, K, M, lda, BK, BM);
+    int rc;
+    if (a_tiled) rc = make_map_tiled(&ta, A, M, ceil_div(K, 256), BK, BM);                 // [K/256 tiles][M][256], k = points
+    else rc = a_mn ? make_map(&ta, A, M, K, lda, 64, BK) : make_map(&ta, A, K, M, lda, BK, BM);
     if (rc) return rc;
-    rc = b_mn ? make_map(&tb, B, N, K, ldb, 64, BK) : make_map(&tb, B, K, N, ldb, BK, BN);
+    if (b_tiled && b_mn) rc = make_map_tiled(&tb, B, K, ceil_div(N, 256), 64, BK);         // [N/256 tiles][K][256], n = points
+    else if (b_tiled) rc = make_map_tiled(&tb, B, N, ceil_div(K, 256), BK, BN);            // [K/256 tiles][N][256], k = points
+    else rc = b_mn ? make_map(&tb, B, N, K, ldb, 64, BK) : make_map(&tb, B, K, N, ldb, BK, BN);
     if (rc) return rc;
+    PCAA_REQUIRE(a_tiled == (b_tiled && !b_mn), PCAA_ERR_UNSUPPORTED, "gemm_tc: k = points needs BOTH operands tiled (PCAA_OP_T256_K)");
     GemmParams p{};
     p.M = M;
     p.N = N;
     p.m_tiles = ceil_div(M, BM);
     p.n_tiles = ceil_div(N, BN);
-    p.kb_total = ceil_div(K, BK);
+    p.kb_total = a_tiled ? ceil_div(K, 256) * 4 : ceil_div(K, BK);     // tiled k: whole 256-point tiles (pad points are zeros)
+    p.a_tiled = a_tiled ? 1 : 0;
+    p.b_tiled = b_tiled ? 1 : 0;
     p.k_splits = 1;
     p.kb_per_split = p.kb_total;
     if (mode == PCAA_TC_WGRAD_ACC) {
@@ -780,7 +824,7 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_mn, const void* B,
         if (wgrad) return launch_tc<BN, true, true, MODE_WGRAD>(ta, tb, p, st);
         if (mode == PCAA_TC_T_DGRAD_ELUBN) return launch_tc<BN, true, true, MODE_T_DGRAD_ELUBN>(ta, tb, p, st);
     }
-    set_error("gemm_tc: operand layout (a_mn=%d, b_mn=%d) is not instantiated for mode %d", a_mn, b_mn, mode);
+    set_error("gemm_tc: operand layout (a=%d, b=%d) is not instantiated for mode %d", a_layout, b_layout, mode);
     return PCAA_ERR_UNSUPPORTED;
 }
 

@@ -1,8 +1,10 @@
-// Channel-major ("T") PointNet kernels: activations are stored channels-first, yT[C][ld] bf16, with the
-// P = B*T*N points of the batch contiguous (rows ordered (b, t, n); ld = P rounded up to 8 elements so every row is
-// 16-byte aligned for TMA and vector access).  In this layout a BatchNorm channel is a ROW: its coefficients are
-// per-row scalars, its statistics are row sums, and the tcgen05 GEMMs (gemm_tcgen05.cu, MODE_T_*) produce them in
-// their epilogues without any cross-lane reduction.
+// Channel-major ("T256") PointNet kernels.  Activations are stored channels-first in 256-point tiles:
+//     element (channel c, point p)  at  X[((p / 256) * C + c) * 256 + p % 256]          (bf16)
+// i.e. [n_tiles][C][256] with the P = B*T*N points of the batch ordered (b, t, n) and the last tile ZERO padded.
+// In this layout a BatchNorm channel is a row of every tile: its coefficients are per-row scalars, its statistics are
+// row sums, and the tcgen05 GEMMs (gemm_tcgen05.cu, MODE_T_*) produce them in their epilogues without any cross-lane
+// reduction; one GEMM tile reads / writes one contiguous [C, 256] block (DRAM-page friendly, unlike a [C, P] matrix
+// whose rows are megabytes apart).
 //
 // Replaces, for the per-point shared MLP of the reference: Conv2d(4->512, 1x1) (models.py:21-28, 86-88),
 // BatchNorm2d + ELU application (models.py:29, 33-34), AvgPool2d((1, nmax)) (models.py:242-243, 282) and their
@@ -12,6 +14,8 @@
 namespace pcaa {
 
 __device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+
+__device__ __forceinline__ int64_t t256(int64_t p, int c, int C) { return (((p >> 8) * C + c) << 8) + (p & 255); }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -54,15 +58,15 @@ __device__ __forceinline__ void load_x8(const float* __restrict__ x, int64_t p0,
 }
 
 // ------------------------------------------------------------------------------------------------ layer 1 forward
-// grid (point tiles, Cout / 64); 8 warps x 8 channels; a warp sweeps its tile 256 points at a time (8 per lane).
+// grid (point super-tiles of 2048, Cout / 64); 8 warps x 8 channels; a warp sweeps one 256-point tile at a time
+// (8 points per lane = one 512-byte tile row per channel).
 constexpr int L1_CH_PER_WARP = 8;
 constexpr int L1_TILE_POINTS = 2048;
 
 __global__ void __launch_bounds__(256)
 pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                          const float* __restrict__ scale, const float* __restrict__ shift,
-                         __nv_bfloat16* __restrict__ yT, int64_t ld, double* __restrict__ stats, int64_t P, int64_t TN,
-                         int Cout) {
+                         __nv_bfloat16* __restrict__ yT, double* __restrict__ stats, int64_t P, int64_t TN, int Cout) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c0 = (blockIdx.y * 8 + warp) * L1_CH_PER_WARP;
     if (c0 >= Cout) return;
@@ -79,10 +83,11 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
     float s1[L1_CH_PER_WARP], s2[L1_CH_PER_WARP];
 #pragma unroll
     for (int k = 0; k < L1_CH_PER_WARP; ++k) s1[k] = s2[k] = 0.f;
+    const int64_t Ppad = (P + 255) & ~(int64_t)255;
     const int64_t tile0 = (int64_t)blockIdx.x * L1_TILE_POINTS;
     for (int ch = 0; ch < L1_TILE_POINTS / 256; ++ch) {
         const int64_t p0 = tile0 + ch * 256 + lane * 8;
-        if (p0 >= P) break;
+        if (p0 >= Ppad) break;
         float xv[4][8];
 #pragma unroll
         for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);
@@ -96,12 +101,13 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
                 v = fmaf(wr[k][2], xv[2][j], v);
                 v = fmaf(wr[k][1], xv[1][j], v);
                 v = fmaf(wr[k][0], xv[0][j], v);
-                const float m = (full || p0 + j < P) ? v : 0.f;
+                const bool in = full || p0 + j < P;
+                const float m = in ? v : 0.f;
                 s1[k] += m;
                 s2[k] = fmaf(m, m, s2[k]);
-                y[j] = scale ? elu_fast(fmaf(v, sc[k], sh[k])) : v;
+                y[j] = in ? (scale ? elu_fast(fmaf(v, sc[k], sh[k])) : v) : 0.f;       // pad points are stored as zeros
             }
-            if (c0 + k < Cout) *reinterpret_cast<uint4*>(yT + (int64_t)(c0 + k) * ld + p0) = pack8(y);
+            if (c0 + k < Cout) *reinterpret_cast<uint4*>(yT + t256(p0, c0 + k, Cout)) = pack8(y);
         }
     }
     if (stats) {
@@ -121,7 +127,7 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
 // layer 1 fused in: its dy is never written) or dy = dz when y is null.
 __global__ void __launch_bounds__(256)
 pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dzT,
-                           const __nv_bfloat16* __restrict__ yT, int64_t ld, const float* __restrict__ c1,
+                           const __nv_bfloat16* __restrict__ yT, const float* __restrict__ c1,
                            const float* __restrict__ c2, const float* __restrict__ c3, float* __restrict__ dW,
                            int64_t P, int64_t TN, int Cout) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,14 +156,14 @@ pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __r
         const bool full = p0 + 8 <= P;
 #pragma unroll
         for (int k = 0; k < L1_CH_PER_WARP; ++k) {
-            const int64_t off = (int64_t)min(c0 + k, Cout - 1) * ld + p0;
+            const int64_t off = t256(p0, min(c0 + k, Cout - 1), Cout);
             float dz[8], yv[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(dzT + off)), dz);
             if (yT) unpack8(__ldg(reinterpret_cast<const uint4*>(yT + off)), yv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float d = yT ? fmaf(a1[k], dz[j], fmaf(a2[k], yv[j], a3[k])) : dz[j];
-                d = (full || p0 + j < P) ? d : 0.f;          // pad columns hold unspecified bits (maybe NaN)
+                d = (full || p0 + j < P) ? d : 0.f;
 #pragma unroll
                 for (int f = 0; f < 4; ++f) acc[k][f] = fmaf(d, xv[f][j], acc[k][f]);
             }
@@ -173,33 +179,48 @@ pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------------ BN + ELU apply
-// grid (x blocks, C); every thread streams UNROLL chunks of 8 points of its channel row
+// The tensor is a list of n_tiles * C rows of 256 points (32 chunks of 8); row r belongs to channel r % C.  Every thread
+// streams EW_UNROLL chunks (all loads issued before the first use).
 constexpr int EW_UNROLL = 4;
+
+struct ChunkPos {
+    int64_t off;      // element offset of the chunk
+    int64_t p0;       // first point of the chunk
+    int c;            // channel
+    bool ok;
+};
+__device__ __forceinline__ ChunkPos chunk_pos(int u, int64_t nchunks, int C) {
+    ChunkPos r;
+    const int64_t i = ((int64_t)blockIdx.x * EW_UNROLL + u) * 256 + threadIdx.x;
+    r.ok = i < nchunks;
+    const int64_t row = i >> 5;
+    r.c = (int)(row % C);
+    r.p0 = ((row / C) << 8) + ((i & 31) << 3);
+    r.off = i << 3;
+    return r;
+}
 
 __global__ void __launch_bounds__(256)
 bn_elu_apply_t_kernel(const __nv_bfloat16* __restrict__ yT, const float* __restrict__ scale,
-                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ outT, int64_t ld, int64_t P) {
-    const int c = blockIdx.y;
-    const float sc = __ldg(scale + c), sh = __ldg(shift + c);
-    const __nv_bfloat16* src = yT + (int64_t)c * ld;
-    __nv_bfloat16* dst = outT + (int64_t)c * ld;
-    const int64_t base = ((int64_t)blockIdx.x * EW_UNROLL * 256 + threadIdx.x) * 8;
+                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ outT, int64_t nchunks, int64_t P,
+                      int C) {
     uint4 raw[EW_UNROLL];
+    ChunkPos cp[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-        const int64_t p0 = base + (int64_t)u * 256 * 8;
-        if (p0 < P) raw[u] = __ldg(reinterpret_cast<const uint4*>(src + p0));
+        cp[u] = chunk_pos(u, nchunks, C);
+        if (cp[u].ok) raw[u] = __ldg(reinterpret_cast<const uint4*>(yT + cp[u].off));
     }
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-        const int64_t p0 = base + (int64_t)u * 256 * 8;
-        if (p0 < P) {
-            float v[8];
-            unpack8(raw[u], v);
+        if (!cp[u].ok) continue;
+        const float sc = __ldg(scale + cp[u].c), sh = __ldg(shift + cp[u].c);
+        float v[8];
+        unpack8(raw[u], v);
+        const bool full = cp[u].p0 + 8 <= P;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = elu_fast(fmaf(v[j], sc, sh));
-            *reinterpret_cast<uint4*>(dst + p0) = pack8(v);
-        }
+        for (int j = 0; j < 8; ++j) v[j] = (full || cp[u].p0 + j < P) ? elu_fast(fmaf(v[j], sc, sh)) : 0.f;
+        *reinterpret_cast<uint4*>(outT + cp[u].off) = pack8(v);
     }
 }
 
@@ -207,41 +228,38 @@ bn_elu_apply_t_kernel(const __nv_bfloat16* __restrict__ yT, const float* __restr
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_t_kernel(const __nv_bfloat16* __restrict__ dzT, const __nv_bfloat16* __restrict__ yT,
                       const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ c3,
-                      __nv_bfloat16* __restrict__ dyT, int64_t ld, int64_t P) {
-    const int c = blockIdx.y;
-    const float a1 = __ldg(c1 + c), a2 = __ldg(c2 + c), a3 = __ldg(c3 + c);
-    const int64_t row = (int64_t)c * ld;
-    const int64_t base = ((int64_t)blockIdx.x * EW_UNROLL * 256 + threadIdx.x) * 8;
+                      __nv_bfloat16* __restrict__ dyT, int64_t nchunks, int64_t P, int C) {
     uint4 rz[EW_UNROLL], ry[EW_UNROLL];
+    ChunkPos cp[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-        const int64_t p0 = base + (int64_t)u * 256 * 8;
-        if (p0 < P) {
-            rz[u] = __ldg(reinterpret_cast<const uint4*>(dzT + row + p0));
-            ry[u] = __ldg(reinterpret_cast<const uint4*>(yT + row + p0));
+        cp[u] = chunk_pos(u, nchunks, C);
+        if (cp[u].ok) {
+            rz[u] = __ldg(reinterpret_cast<const uint4*>(dzT + cp[u].off));
+            ry[u] = __ldg(reinterpret_cast<const uint4*>(yT + cp[u].off));
         }
     }
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-        const int64_t p0 = base + (int64_t)u * 256 * 8;
-        if (p0 < P) {
-            float z[8], y[8];
-            unpack8(rz[u], z);
-            unpack8(ry[u], y);
+        if (!cp[u].ok) continue;
+        const float a1 = __ldg(c1 + cp[u].c), a2 = __ldg(c2 + cp[u].c), a3 = __ldg(c3 + cp[u].c);
+        float z[8], y[8];
+        unpack8(rz[u], z);
+        unpack8(ry[u], y);
+        const bool full = cp[u].p0 + 8 <= P;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) z[j] = fmaf(a1, z[j], fmaf(a2, y[j], a3));
-            *reinterpret_cast<uint4*>(dyT + row + p0) = pack8(z);
-        }
+        for (int j = 0; j < 8; ++j) z[j] = (full || cp[u].p0 + j < P) ? fmaf(a1, z[j], fmaf(a2, y[j], a3)) : 0.f;
+        *reinterpret_cast<uint4*>(dyT + cp[u].off) = pack8(z);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ mean pool over points
-// pooled[g][c] = mean_{i<n} ELU(scale[c]*yT[c][g*n+i] + shift[c]); when e1/e2 are given (training) also
+// pooled[g][c] = mean_{i<n} ELU(scale[c]*y(c, g*n+i) + shift[c]); when e1/e2 are given (training) also
 // e1[g][c] = sum_i ELU'(z), e2[g][c] = sum_i ELU'(z)*xhat -- the group sums from which the backward's BatchNorm
 // statistics follow without another pass over the activations (d pooled / d z is constant over a group).
 // grid (ceil(G / 8), C / 32): warp w owns group g0 + w and walks the 32 channel rows of the block.
 __global__ void __launch_bounds__(256)
-bn_elu_meanpool_t_kernel(const __nv_bfloat16* __restrict__ yT, int64_t ld, const float* __restrict__ scale,
+bn_elu_meanpool_t_kernel(const __nv_bfloat16* __restrict__ yT, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, float* __restrict__ pooled, float* __restrict__ e1,
                          float* __restrict__ e2, int64_t G, int n, int C, int apply) {
@@ -249,7 +267,8 @@ bn_elu_meanpool_t_kernel(const __nv_bfloat16* __restrict__ yT, int64_t ld, const
     const int64_t g = (int64_t)blockIdx.x * 8 + warp;
     if (g >= G) return;
     const int cb = blockIdx.y * 32;
-    const bool pairs = ((n & 1) == 0) && ((ld & 1) == 0);
+    const bool pairs = (n & 1) == 0;           // group starts are even -> a bf16 pair never straddles a tile boundary
+    const int64_t pbeg = g * n;
     float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
@@ -257,11 +276,10 @@ bn_elu_meanpool_t_kernel(const __nv_bfloat16* __restrict__ yT, int64_t ld, const
         if (c >= C) break;
         const float sc = apply ? __ldg(scale + c) : 1.f, sh = apply ? __ldg(shift + c) : 0.f;
         const float mu = e1 ? __ldg(mean + c) : 0.f, is = e1 ? __ldg(invstd + c) : 0.f;
-        const __nv_bfloat16* src = yT + (int64_t)c * ld + g * n;
         float s = 0.f, t1 = 0.f, t2 = 0.f;
         if (pairs) {
             for (int k = lane; k < n / 2; k += 32) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + 2 * k));
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(yT + t256(pbeg + 2 * k, c, C)));
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const float y = u ? f.y : f.x;
@@ -277,7 +295,7 @@ bn_elu_meanpool_t_kernel(const __nv_bfloat16* __restrict__ yT, int64_t ld, const
             }
         } else {
             for (int k = lane; k < n; k += 32) {
-                const float y = __bfloat162float(src[k]);
+                const float y = __bfloat162float(yT[t256(pbeg + k, c, C)]);
                 const float z = fmaf(y, sc, sh);
                 const float a = apply ? elu_fast(z) : z;
                 s += a;
@@ -324,49 +342,49 @@ pool_bwd_stats_kernel(const float* __restrict__ dpool, const float* __restrict__
     }
 }
 
-// dyT[c][p] = c1[c] * (dpool[g(p)][c]/n) * ELU'(scale*y+shift) + c2[c]*y + c3[c]   (mean-pool backward, ELU backward
-// and BatchNorm backward of layer 4 in ONE pass over y4)
+// dy(c,p) = c1[c] * (dpool[g(p)][c]/n) * ELU'(scale*y+shift) + c2[c]*y + c3[c]   (mean-pool backward, ELU backward and
+// BatchNorm backward of layer 4 in ONE pass over y4)
 __global__ void __launch_bounds__(256)
 pool_bwd_apply_t_kernel(const float* __restrict__ dpool, const __nv_bfloat16* __restrict__ yT,
                         const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ c1,
                         const float* __restrict__ c2, const float* __restrict__ c3, __nv_bfloat16* __restrict__ dyT,
-                        int64_t ld, int64_t P, int n, int C, float inv_n) {
-    const int c = blockIdx.y;
-    const float sc = __ldg(scale + c), sh = __ldg(shift + c);
-    const float a1 = __ldg(c1 + c) * inv_n, a2 = __ldg(c2 + c), a3 = __ldg(c3 + c);
-    const int64_t row = (int64_t)c * ld;
-    const int64_t base = ((int64_t)blockIdx.x * EW_UNROLL * 256 + threadIdx.x) * 8;
+                        int64_t nchunks, int64_t P, int n, int C, float inv_n) {
     uint4 ry[EW_UNROLL];
+    ChunkPos cp[EW_UNROLL];
     float g0v[EW_UNROLL], g1v[EW_UNROLL];
     int split[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-        const int64_t p0 = base + (int64_t)u * 256 * 8;
-        if (p0 < P) {
-            ry[u] = __ldg(reinterpret_cast<const uint4*>(yT + row + p0));
+        cp[u] = chunk_pos(u, nchunks, C);
+        if (cp[u].ok) {
+            ry[u] = __ldg(reinterpret_cast<const uint4*>(yT + cp[u].off));
+            const int64_t p0 = cp[u].p0;
             const int64_t g0 = p0 / n;
             const int64_t nxt = (g0 + 1) * n - p0;             // first index (0..8+) that belongs to the next group
             split[u] = nxt < 8 ? (int)nxt : 8;
-            g0v[u] = __ldg(dpool + g0 * C + c);
-            g1v[u] = (nxt < 8 && (g0 + 1) * n < P) ? __ldg(dpool + (g0 + 1) * C + c) : 0.f;
+            g0v[u] = p0 < P ? __ldg(dpool + g0 * C + cp[u].c) : 0.f;
+            g1v[u] = (nxt < 8 && (g0 + 1) * n < P) ? __ldg(dpool + (g0 + 1) * C + cp[u].c) : 0.f;
         }
     }
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-        const int64_t p0 = base + (int64_t)u * 256 * 8;
-        if (p0 < P) {
-            float y[8];
-            unpack8(ry[u], y);
+        if (!cp[u].ok) continue;
+        const int c = cp[u].c;
+        const int64_t p0 = cp[u].p0;
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const float a1 = __ldg(c1 + c) * inv_n, a2 = __ldg(c2 + c), a3 = __ldg(c3 + c);
+        float y[8];
+        unpack8(ry[u], y);
+        const bool full = p0 + 8 <= P;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float z = fmaf(y[j], sc, sh);
-                float gv = j < split[u] ? g0v[u] : g1v[u];
-                if (n < 8) gv = (p0 + j < P) ? __ldg(dpool + ((p0 + j) / n) * C + c) : 0.f;   // tiny clouds: > 2 groups per chunk
-                const float d = gv * (z > 0.f ? 1.f : __expf(z));
-                y[j] = fmaf(a1, d, fmaf(a2, y[j], a3));
-            }
-            *reinterpret_cast<uint4*>(dyT + row + p0) = pack8(y);
+        for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(y[j], sc, sh);
+            float gv = j < split[u] ? g0v[u] : g1v[u];
+            if (n < 8) gv = (p0 + j < P) ? __ldg(dpool + ((p0 + j) / n) * C + c) : 0.f;   // tiny clouds: > 2 groups per chunk
+            const float d = gv * (z > 0.f ? 1.f : __expf(z));
+            y[j] = (full || p0 + j < P) ? fmaf(a1, d, fmaf(a2, y[j], a3)) : 0.f;
         }
+        *reinterpret_cast<uint4*>(dyT + cp[u].off) = pack8(y);
     }
 }
 
@@ -375,61 +393,59 @@ pool_bwd_apply_t_kernel(const float* __restrict__ dpool, const __nv_bfloat16* __
 using namespace pcaa;
 #define ST(s) ((cudaStream_t)(s))
 
-static inline unsigned ew_blocks(int64_t P) { return (unsigned)ceil_div(ceil_div(P, 8), 256 * EW_UNROLL); }
+static inline int64_t t256_chunks(int64_t P, int C) { return ((P + 255) / 256) * (int64_t)C * 32; }
+static inline unsigned ew_blocks(int64_t nchunks) { return (unsigned)ceil_div(nchunks, 256 * EW_UNROLL); }
 
 extern "C" {
 
 int pcaa_pointnet_l1_fwd_t(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
-                           void* yT, int64_t ld, double* stats, int64_t B, int64_t TN, int Cout, pcaa_stream stream) {
+                           void* yT, double* stats, int64_t B, int64_t TN, int Cout, pcaa_stream stream) {
     if (B == 0) return PCAA_OK;
     const int64_t P = B * TN;
-    PCAA_REQUIRE(ld % 8 == 0 && ld >= P && ((uintptr_t)yT & 15) == 0, PCAA_ERR_ALIGN, "pointnet_l1_fwd_t: ld must be a multiple of 8 and >= B*TN");
-    PCAA_REQUIRE(Cout > 0 && ((uintptr_t)w & 15) == 0, PCAA_ERR_SHAPE, "pointnet_l1_fwd_t: bad Cout / weight alignment");
+    PCAA_REQUIRE(((uintptr_t)yT & 15) == 0 && ((uintptr_t)w & 15) == 0 && Cout > 0, PCAA_ERR_ALIGN, "pointnet_l1_fwd_t: alignment / Cout");
     PCAA_REQUIRE((scale == nullptr) == (shift == nullptr), PCAA_ERR_SHAPE, "pointnet_l1_fwd_t: scale and shift go together");
     dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
-    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, ld, stats, P, TN, Cout);
+    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, stats, P, TN, Cout);
     return check_launch("pointnet_l1_fwd_t");
 }
 
-int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, int64_t ld, const float* c1,
-                             const float* c2, const float* c3, float* dW, int64_t B, int64_t TN, int Cout,
-                             pcaa_stream stream) {
+int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, const float* c1, const float* c2,
+                             const float* c3, float* dW, int64_t B, int64_t TN, int Cout, pcaa_stream stream) {
     if (cudaMemsetAsync(dW, 0, sizeof(float) * 4 * Cout, ST(stream)) != cudaSuccess) return check_launch("pointnet_l1_wgrad_t memset");
     if (B == 0) return PCAA_OK;
     const int64_t P = B * TN;
-    PCAA_REQUIRE(ld % 8 == 0 && ld >= P, PCAA_ERR_ALIGN, "pointnet_l1_wgrad_t: ld must be a multiple of 8 and >= B*TN");
     PCAA_REQUIRE(yT == nullptr || (c1 && c2 && c3), PCAA_ERR_SHAPE, "pointnet_l1_wgrad_t: y needs the BatchNorm-backward coefficients");
     dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
-    pointnet_l1_wgrad_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, (const __nv_bfloat16*)dzT, (const __nv_bfloat16*)yT, ld, c1, c2, c3, dW, P, TN, Cout);
+    pointnet_l1_wgrad_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, (const __nv_bfloat16*)dzT, (const __nv_bfloat16*)yT, c1, c2, c3, dW, P, TN, Cout);
     return check_launch("pointnet_l1_wgrad_t");
 }
 
-int pcaa_bn_elu_apply_t(const void* yT, const float* scale, const float* shift, void* outT, int64_t ld, int64_t P, int C,
+int pcaa_bn_elu_apply_t(const void* yT, const float* scale, const float* shift, void* outT, int64_t P, int C,
                         pcaa_stream stream) {
     if (P == 0 || C == 0) return PCAA_OK;
-    PCAA_REQUIRE(ld % 8 == 0 && ld >= P && C <= 65535, PCAA_ERR_ALIGN, "bn_elu_apply_t: ld must be a multiple of 8 and >= P");
-    bn_elu_apply_t_kernel<<<dim3(ew_blocks(P), C), 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, (__nv_bfloat16*)outT, ld, P);
+    const int64_t nch = t256_chunks(P, C);
+    bn_elu_apply_t_kernel<<<ew_blocks(nch), 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, (__nv_bfloat16*)outT, nch, P, C);
     return check_launch("bn_elu_apply_t");
 }
 
 int pcaa_bn_bwd_apply_t(const void* dzT, const void* yT, const float* c1, const float* c2, const float* c3, void* dyT,
-                        int64_t ld, int64_t P, int C, pcaa_stream stream) {
+                        int64_t P, int C, pcaa_stream stream) {
     if (P == 0 || C == 0) return PCAA_OK;
-    PCAA_REQUIRE(ld % 8 == 0 && ld >= P && C <= 65535, PCAA_ERR_ALIGN, "bn_bwd_apply_t: ld must be a multiple of 8 and >= P");
-    bn_bwd_apply_t_kernel<<<dim3(ew_blocks(P), C), 256, 0, ST(stream)>>>((const __nv_bfloat16*)dzT, (const __nv_bfloat16*)yT, c1, c2, c3, (__nv_bfloat16*)dyT, ld, P);
+    const int64_t nch = t256_chunks(P, C);
+    bn_bwd_apply_t_kernel<<<ew_blocks(nch), 256, 0, ST(stream)>>>((const __nv_bfloat16*)dzT, (const __nv_bfloat16*)yT, c1, c2, c3, (__nv_bfloat16*)dyT, nch, P, C);
     return check_launch("bn_bwd_apply_t");
 }
 
-int pcaa_bn_elu_meanpool_t(const void* yT, int64_t ld, const float* scale, const float* shift, const float* mean,
+int pcaa_bn_elu_meanpool_t(const void* yT, const float* scale, const float* shift, const float* mean,
                            const float* invstd, float* pooled, float* e1, float* e2, int64_t G, int n, int C,
                            pcaa_stream stream) {
     if (G == 0 || C == 0) return PCAA_OK;
-    PCAA_REQUIRE(n > 0 && ld >= G * n, PCAA_ERR_SHAPE, "bn_elu_meanpool_t: bad group size / leading dimension");
+    PCAA_REQUIRE(n > 0, PCAA_ERR_SHAPE, "bn_elu_meanpool_t: bad group size");
     PCAA_REQUIRE((e1 == nullptr) == (e2 == nullptr) && (e1 == nullptr || (mean && invstd && scale)), PCAA_ERR_SHAPE,
                  "bn_elu_meanpool_t: e1/e2 need mean/invstd/scale");
     const int apply = scale != nullptr;
     dim3 grid((unsigned)ceil_div(G, 8), (unsigned)ceil_div(C, 32));
-    bn_elu_meanpool_t_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, ld, scale, shift, mean, invstd, pooled, e1, e2, G, n, C, apply);
+    bn_elu_meanpool_t_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, G, n, C, apply);
     return check_launch("bn_elu_meanpool_t");
 }
 
@@ -444,12 +460,12 @@ int pcaa_pool_bwd_stats(const float* dpool, const float* e1, const float* e2, do
 }
 
 int pcaa_pool_bwd_apply_t(const float* dpool, const void* yT, const float* scale, const float* shift, const float* c1,
-                          const float* c2, const float* c3, void* dyT, int64_t ld, int64_t G, int n, int C,
-                          pcaa_stream stream) {
+                          const float* c2, const float* c3, void* dyT, int64_t G, int n, int C, pcaa_stream stream) {
     if (G == 0 || C == 0) return PCAA_OK;
+    PCAA_REQUIRE(n >= 1, PCAA_ERR_SHAPE, "pool_bwd_apply_t: bad group size");
     const int64_t P = G * n;
-    PCAA_REQUIRE(ld % 8 == 0 && ld >= P && C <= 65535 && n >= 1, PCAA_ERR_ALIGN, "pool_bwd_apply_t: ld must be a multiple of 8 and >= G*n");
-    pool_bwd_apply_t_kernel<<<dim3(ew_blocks(P), C), 256, 0, ST(stream)>>>(dpool, (const __nv_bfloat16*)yT, scale, shift, c1, c2, c3, (__nv_bfloat16*)dyT, ld, P, n, C, 1.f / (float)n);
+    const int64_t nch = t256_chunks(P, C);
+    pool_bwd_apply_t_kernel<<<ew_blocks(nch), 256, 0, ST(stream)>>>(dpool, (const __nv_bfloat16*)yT, scale, shift, c1, c2, c3, (__nv_bfloat16*)dyT, nch, P, n, C, 1.f / (float)n);
     return check_launch("pool_bwd_apply_t");
 }
 

@@ -4,7 +4,7 @@ Everything here is orchestration: which kernel runs on which buffer.  Parameters
 reference's ``state_dict`` names (relative to the module: e.g. ``pc_block.pointnet2.module.0.weight``), so the same
 functions serve the drop-in ``nn.Module``s (models.py) and the fused trainer (train.py).
 
-Layouts: point activations are channel-major bf16 ``[C, pad8(B*T*N)]`` (points contiguous, ordered (b, t, n)); TCN /
+Layouts: point activations are channel-major bf16 in 256-point tiles ``[tiles, C, 256]`` (T256, include/pcaa.h); TCN /
 head / decoder activations are fp32 ``[rows, C]``.  Reference: models.py:82-160, 232-292, 340-385.
 """
 from __future__ import annotations
@@ -14,7 +14,7 @@ from typing import Dict, Optional
 import torch
 
 from . import ops
-from ._lib import (ACT_ELU, ACT_NONE, TC_BIAS_ELU, TC_BIAS_STATS, TC_DGRAD_ELUBN, TC_DGRAD_ELUOUT, TC_PLAIN,
+from ._lib import (ACT_ELU, ACT_NONE, OP_MN, OP_T256_K, OP_T256_MN, TC_BIAS_ELU, TC_BIAS_STATS, TC_DGRAD_ELUBN, TC_DGRAD_ELUOUT, TC_PLAIN,
                    TC_T_AFFINE_ELU, TC_T_BIAS_STATS, TC_T_DGRAD_ELUBN, TC_WGRAD_ACC, TC_WGRAD_STORE)
 
 T_STEPS = 30
@@ -47,7 +47,7 @@ def _conv_w(P: Params, pre: str, l: int):
 def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_block.", wb16: Optional[dict] = None):
     """x (B,4,T,N) fp32 -> pooled [B*T, 1024] fp32 (mean over the N points of ELU(BN(conv))), saved state.
 
-    Activations are channel-major bf16 ``yT [C, pad8(B*T*N)]`` (points contiguous): the tcgen05 GEMM of layer l
+    Activations are channel-major bf16 in 256-point tiles (T256 ``[tiles, C, 256]``): the tcgen05 GEMM of layer l
     computes ``y_l^T = W_l a_{l-1}^T`` with the channel as the accumulator row, so bias / BatchNorm coefficients are
     per-thread scalars and the batch statistics are in-thread sums of its epilogue.  ``wb16`` optionally maps the
     layer number to a ready bf16 copy of the [Cout, Cin] weight (the trainer's Adam-maintained shadow)."""
@@ -70,23 +70,21 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
         sv["y"][1], sv["coef"][1], sv["a"][1] = y, coef, a
     else:
         a, _ = ops.pointnet_l1_fwd_t(x, _conv_w(P, pre, 1), b1, coef=bn_coef(1, None))
-    ld = a.shape[1]
     for l in (2, 3, 4):
         W = _conv_w(P, pre, l)
         Cout, Cin = W.shape
         wb = wb16[l] if wb16 is not None else ops.pack_bf16(W)
         bias = P[f"{pre}pointnet{l}.module.0.bias"]
-        out = torch.empty((Cout, ld), device=x.device, dtype=torch.bfloat16)
         if training:
             st = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64)
-            y = ops.gemm_tc(wb, a, TC_T_BIAS_STATS, Cout, R, Cin, b_mn=True, out=out, bias=bias, stats=st)
+            y = ops.gemm_tc(wb, a, TC_T_BIAS_STATS, Cout, R, Cin, b_mn=OP_T256_MN, bias=bias, stats=st)
             coef = bn_coef(l, st)
             sv["y"][l], sv["coef"][l], sv["wb"][l] = y, coef, wb
             if l < 4:
                 a = ops.bn_elu_apply_t(y, coef, R)
                 sv["a"][l] = a
         else:
-            a = ops.gemm_tc(wb, a, TC_T_AFFINE_ELU, Cout, R, Cin, b_mn=True, out=out, bias=bias, coef=bn_coef(l, None))
+            a = ops.gemm_tc(wb, a, TC_T_AFFINE_ELU, Cout, R, Cin, b_mn=OP_T256_MN, bias=bias, coef=bn_coef(l, None))
     if training:
         pooled, e1, e2 = ops.bn_elu_meanpool_t(y, coef, B * T, N, want_e=True)
         sv["e1"], sv["e2"] = e1, e2
@@ -114,15 +112,14 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
         Cout, Cin = W.shape[0], W.shape[1]
         dW = _zeros_like_param(gradbuf, kc + "weight", W)
         # dW[Cout, Cin] += dyT [Cout, P] . a_{l-1}T [Cin, P]^T   (both operands K-major, K = points, split over the SMs)
-        ops.gemm_tc(dy, sv["a"][l - 1], TC_WGRAD_ACC, Cout, Cin, R, out=dW.view(Cout, Cin))
+        ops.gemm_tc(dy, sv["a"][l - 1], TC_WGRAD_ACC, Cout, Cin, R, a_mn=OP_T256_K, b_mn=OP_T256_K, out=dW.view(Cout, Cin))
         G[kc + "weight"] = dW
         # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero
         G[kc + "bias"] = _zeros_like_param(gradbuf, kc + "bias", P[kc + "bias"])
         # dz_{l-1}T [Cin, P] = (W^T dyT) * ELU'(BN(y_{l-1})) with the statistics of BatchNorm l-1's backward
         st2 = torch.zeros(2 * Cin, device=gpool.device, dtype=torch.float64)
-        dz = torch.empty((Cin, dy.shape[1]), device=gpool.device, dtype=torch.bfloat16)
-        ops.gemm_tc(sv["wb"][l], dy, TC_T_DGRAD_ELUBN, Cin, R, Cout, a_mn=True, b_mn=True, out=dz, stats=st2,
-                    yprev=sv["y"][l - 1], coef=sv["coef"][l - 1])
+        dz = ops.gemm_tc(sv["wb"][l], dy, TC_T_DGRAD_ELUBN, Cin, R, Cout, a_mn=OP_MN, b_mn=OP_T256_MN, stats=st2,
+                         yprev=sv["y"][l - 1], coef=sv["coef"][l - 1])
         kb = f"{pre}pointnet{l - 1}.module.1."
         c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][l - 1], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
         G[kb + "weight"], G[kb + "bias"] = dgam, dbet

@@ -227,53 +227,71 @@ def pointnet_l1_wgrad(x, dy, out: Optional[torch.Tensor] = None):
 
 
 # ------------------------------------------------------------------------------------------------ channel-major PointNet
-def pad8(n: int) -> int:
-    return (n + 7) // 8 * 8
+# T256 activation format: bf16 tensor [n_tiles, C, 256], element (c, p) at [p // 256, c, p % 256]; pad points are zeros.
+def t256_tiles(P: int) -> int:
+    return (P + 255) // 256
+
+
+def t256_empty(C: int, P: int, device) -> torch.Tensor:
+    return torch.empty((t256_tiles(P), C, 256), device=device, dtype=torch.bfloat16)
+
+
+def t256_pack(x: torch.Tensor) -> torch.Tensor:
+    """[C, P] -> T256 bf16 (torch glue for tests / tools; the hot path never converts)."""
+    C, P = x.shape
+    nt = t256_tiles(P)
+    out = torch.zeros((C, nt * 256), device=x.device, dtype=torch.bfloat16)
+    out[:, :P] = x.to(torch.bfloat16)
+    return out.view(C, nt, 256).permute(1, 0, 2).contiguous()
+
+
+def t256_unpack(xT: torch.Tensor, P: int) -> torch.Tensor:
+    """T256 -> [C, P] (same dtype)."""
+    nt, C, _ = xT.shape
+    return xT.permute(1, 0, 2).reshape(C, nt * 256)[:, :P]
 
 
 def pointnet_l1_fwd_t(x, w, bias, coef=None, want_stats=True):
-    """x (B,4,T,N) fp32 -> yT [Cout, pad8(B*T*N)] bf16 (+ row statistics); with coef = (scale, shift) the stored value is
-    ELU(scale*y + shift) (eval mode) and no statistics are produced."""
+    """x (B,4,T,N) fp32 -> yT T256 [tiles, Cout, 256] bf16 (+ row statistics); with coef = (scale, shift) the stored value
+    is ELU(scale*y + shift) (eval mode) and no statistics are produced."""
     _chk(x, torch.float32), _chk(w, torch.float32)
     B, F, T, N = x.shape
     Cout = w.shape[0]
-    ld = pad8(B * T * N)
-    yT = torch.empty((Cout, ld), device=x.device, dtype=torch.bfloat16)
+    yT = t256_empty(Cout, B * T * N, x.device)
     stats = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64) if (want_stats and coef is None) else None
     sc, sh = (None, None) if coef is None else (coef[0], coef[1])
-    call("pcaa_pointnet_l1_fwd_t", _p(x), _p(w), _p(bias), _p(sc), _p(sh), _p(yT), ld, _p(stats), B, T * N, Cout, _s())
+    call("pcaa_pointnet_l1_fwd_t", _p(x), _p(w), _p(bias), _p(sc), _p(sh), _p(yT), _p(stats), B, T * N, Cout, _s())
     return yT, stats
 
 
 def pointnet_l1_wgrad_t(x, dzT, yT=None, c=None, out: Optional[torch.Tensor] = None):
-    """dW1 [Cout,4] = sum_p (c1*dzT + c2*yT + c3)[c,p] * x[f,p]  (yT / c None: dy = dzT)."""
+    """dW1 [Cout,4] = sum_p (c1*dzT + c2*yT + c3)(c,p) * x[f,p]  (yT / c None: dy = dzT)."""
     B, F, T, N = x.shape
-    Cout = dzT.shape[0]
+    Cout = dzT.shape[1]
     if out is None:
         out = torch.empty((Cout, 4), device=x.device, dtype=torch.float32)
     c1, c2, c3 = (None, None, None) if c is None else (c[0], c[1], c[2])
-    call("pcaa_pointnet_l1_wgrad_t", _p(x), _p(dzT), _p(yT), dzT.stride(0), _p(c1), _p(c2), _p(c3), _p(out), B, T * N,
-         Cout, _s())
+    call("pcaa_pointnet_l1_wgrad_t", _p(x), _p(dzT), _p(yT), _p(c1), _p(c2), _p(c3), _p(out), B, T * N, Cout, _s())
     return out
 
 
 def bn_elu_apply_t(yT, coef, P: int):
     out = torch.empty_like(yT)
-    call("pcaa_bn_elu_apply_t", _p(yT), _p(coef[0]), _p(coef[1]), _p(out), yT.stride(0), P, yT.shape[0], _s())
+    call("pcaa_bn_elu_apply_t", _p(yT), _p(coef[0]), _p(coef[1]), _p(out), P, yT.shape[1], _s())
     return out
 
 
 def bn_bwd_apply_t(dzT, yT, c, P: int, out: Optional[torch.Tensor] = None):
     if out is None:
         out = torch.empty_like(dzT)
-    call("pcaa_bn_bwd_apply_t", _p(dzT), _p(yT), _p(c[0]), _p(c[1]), _p(c[2]), _p(out), yT.stride(0), P, yT.shape[0], _s())
+    call("pcaa_bn_bwd_apply_t", _p(dzT), _p(yT), _p(c[0]), _p(c[1]), _p(c[2]), _p(out), P, yT.shape[1], _s())
     return out
 
 
 def bn_elu_meanpool_t(yT, coef, G: int, n: int, want_e=False):
     """pooled [G, C] fp32 = mean over each group of n points of ELU(scale*yT+shift) (coef None: plain mean); with
     want_e also the group sums e1 = sum ELU'(z), e2 = sum ELU'(z)*xhat used by the backward statistics."""
-    Cc = yT.shape[0]
+    Cc = yT.shape[1]
     pooled = torch.empty((G, Cc), device=yT.device, dtype=torch.float32)
     e1 = torch.empty_like(pooled) if want_e else None
     e2 = torch.empty_like(pooled) if want_e else None
@@ -282,8 +300,7 @@ def bn_elu_meanpool_t(yT, coef, G: int, n: int, want_e=False):
         sc, sh = coef[0], coef[1]
         if want_e:
             mu, inv = coef[2], coef[3]
-    call("pcaa_bn_elu_meanpool_t", _p(yT), yT.stride(0), _p(sc), _p(sh), _p(mu), _p(inv), _p(pooled), _p(e1), _p(e2), G,
-         n, Cc, _s())
+    call("pcaa_bn_elu_meanpool_t", _p(yT), _p(sc), _p(sh), _p(mu), _p(inv), _p(pooled), _p(e1), _p(e2), G, n, Cc, _s())
     return pooled, e1, e2
 
 
@@ -299,8 +316,8 @@ def pool_bwd_apply_t(dpool, yT, coef, c, n: int):
     _chk(dpool, torch.float32)
     G, Cc = dpool.shape
     out = torch.empty_like(yT)
-    call("pcaa_pool_bwd_apply_t", _p(dpool), _p(yT), _p(coef[0]), _p(coef[1]), _p(c[0]), _p(c[1]), _p(c[2]), _p(out),
-         yT.stride(0), G, n, Cc, _s())
+    call("pcaa_pool_bwd_apply_t", _p(dpool), _p(yT), _p(coef[0]), _p(coef[1]), _p(c[0]), _p(c[1]), _p(c[2]), _p(out), G,
+         n, Cc, _s())
     return out
 
 
@@ -324,10 +341,13 @@ def gemm_tc(a, b, mode: int, M: int, N: int, K: int, *, a_mn=False, b_mn=False, 
             bias=None, stats=None, yprev=None, coef=None):
     """General tcgen05 GEMM: out[M,N] = epilogue(sum_k A(m,k) B(n,k)).  `a` is stored [M,K] (or [K,M] when a_mn),
     `b` is stored [N,K] (or [K,N] when b_mn); both bf16 2-D with unit inner stride; M, N, K are the TRUE extents
-    (buffers may be wider: leading dimensions come from the strides)."""
+    (buffers may be wider: leading dimensions come from the strides).  a_mn / b_mn may also be the pcaa_operand_layout
+    codes OP_T256_K / OP_T256_MN for 3-D T256 activation tensors (see include/pcaa.h)."""
     _chk(a, torch.bfloat16, contiguous=False), _chk(b, torch.bfloat16, contiguous=False)
-    if a.stride(1) != 1 or b.stride(1) != 1:
+    if a.stride(-1) != 1 or b.stride(-1) != 1:
         raise ValueError("gemm_tc: operands need unit inner stride")
+    if out is None and mode >= _lib.TC_T_BIAS_STATS:
+        out = t256_empty(M, N, a.device)
     if out is None:
         if out_dtype == torch.bfloat16:
             out = torch.empty((M, (N + 7) // 8 * 8), device=a.device, dtype=torch.bfloat16)
@@ -338,9 +358,9 @@ def gemm_tc(a, b, mode: int, M: int, N: int, K: int, *, a_mn=False, b_mn=False, 
         sc, sh = coef[0], coef[1]
         if len(coef) >= 4:
             mu, inv = coef[2], coef[3]
-    call("pcaa_gemm_tc", _p(a), a.stride(0), 1 if a_mn else 0, _p(b), b.stride(0), 1 if b_mn else 0, _p(out),
-         out.stride(0), _DT[out.dtype], M, N, K, mode, _p(bias), _p(stats), _p(yprev),
-         0 if yprev is None else yprev.stride(0), _p(sc), _p(sh), _p(mu), _p(inv), _s())
+    call("pcaa_gemm_tc", _p(a), a.stride(-2), int(a_mn), _p(b), b.stride(-2), int(b_mn), _p(out),
+         out.stride(-2), _DT[out.dtype], M, N, K, mode, _p(bias), _p(stats), _p(yprev),
+         0 if yprev is None else yprev.stride(-2), _p(sc), _p(sh), _p(mu), _p(inv), _s())
     return out
 
 

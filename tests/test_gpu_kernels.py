@@ -393,14 +393,20 @@ def test_gemm_tc_decoder_modes(ops, B, K, Nout):
     assert rel_err(ops.colsum_ld(dzd, Nout), dz.sum(0)) < 1e-4
 
 
-# ------------------------------------------------------------------------------------------------ channel-major ("T") PointNet path
-def _padT(t, ld=None):
-    """[C, P] fp32 CPU -> bf16 CUDA [C, pad8(P)] whose pad columns hold NaN (they must never be consumed)."""
-    C, P = t.shape
-    ld = ld or (P + 7) // 8 * 8
-    out = torch.full((C, ld), float("nan"), dtype=torch.bfloat16, device="cuda")
-    out[:, :P] = t.cuda().bfloat16()
-    return out
+# ------------------------------------------------------------------------------------------------ channel-major (T256) PointNet path
+def _t256(ops, t):
+    """[C, P] fp32 CPU -> T256 bf16 CUDA [tiles, C, 256] (pad points zero, the format's invariant)."""
+    return ops.t256_pack(t.cuda())
+
+
+def _un(ops, xT, P):
+    return ops.t256_unpack(xT, P).float().cpu()
+
+
+def _pad_is_zero(ops, xT, P):
+    nt, C, _ = xT.shape
+    flat = xT.permute(1, 0, 2).reshape(C, nt * 256)
+    return bool((flat[:, P:] == 0).all())
 
 
 T_SHAPES = [(512, 6000, 512), (1024, 4500, 512), (1024, 1000, 1024), (512, 300, 72), (264, 1003, 520), (128, 37, 64)]
@@ -413,22 +419,22 @@ def test_gemm_tc_t_bias_stats_and_affine(ops, Cout, P, Cin):
     aT = bf16_round(torch.randn(Cin, P, generator=g))
     bias = torch.randn(Cout, generator=g)
     ref = w @ aT + bias[:, None]
-    ld = (P + 7) // 8 * 8
     stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
-    out = torch.full((Cout, ld), float("nan"), dtype=torch.bfloat16, device="cuda")
-    ops.gemm_tc(cuda(w).bfloat16(), _padT(aT), ops._lib.TC_T_BIAS_STATS, Cout, P, Cin, b_mn=True, out=out, bias=cuda(bias),
-                stats=stats)
+    out = torch.full((ops.t256_tiles(P), Cout, 256), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_tc(cuda(w).bfloat16(), _t256(ops, aT), ops._lib.TC_T_BIAS_STATS, Cout, P, Cin, b_mn=ops._lib.OP_T256_MN, out=out,
+                bias=cuda(bias), stats=stats)
     torch.cuda.synchronize()
-    assert rel_err(out[:, :P].float(), ref) < 1e-2
+    assert rel_err(_un(ops, out, P), ref) < 1e-2
+    assert _pad_is_zero(ops, out, P)
     s = stats.cpu()
     assert rel_err(s[:Cout], ref.double().sum(1)) < 1e-4
     assert rel_err(s[Cout:], (ref.double() ** 2).sum(1)) < 1e-4
     # eval mode: BatchNorm (running statistics) + ELU applied in the epilogue
     sc, sh = 1 + 0.1 * torch.randn(Cout, generator=g), 0.1 * torch.randn(Cout, generator=g)
-    out2 = torch.empty((Cout, ld), dtype=torch.bfloat16, device="cuda")
-    ops.gemm_tc(cuda(w).bfloat16(), _padT(aT), ops._lib.TC_T_AFFINE_ELU, Cout, P, Cin, b_mn=True, out=out2, bias=cuda(bias),
-                coef=cuda(torch.stack([sc, sh])))
-    assert rel_err(out2[:, :P].float(), O.elu(ref * sc[:, None] + sh[:, None])) < 1e-2
+    out2 = ops.gemm_tc(cuda(w).bfloat16(), _t256(ops, aT), ops._lib.TC_T_AFFINE_ELU, Cout, P, Cin, b_mn=ops._lib.OP_T256_MN,
+                       bias=cuda(bias), coef=cuda(torch.stack([sc, sh])))
+    assert rel_err(_un(ops, out2, P), O.elu(ref * sc[:, None] + sh[:, None])) < 1e-2
+    assert _pad_is_zero(ops, out2, P)
 
 
 @pytest.mark.parametrize("Cout,P,Cin", T_SHAPES)
@@ -442,35 +448,35 @@ def test_gemm_tc_t_dgrad_elubn(ops, Cout, P, Cin):
     z = yprev * coef[0][:, None] + coef[1][:, None]
     dz = (w.t() @ dyT) * torch.where(z > 0, torch.ones_like(z), torch.exp(z))
     xh = (yprev - coef[2][:, None]) * coef[3][:, None]
-    ld = (P + 7) // 8 * 8
     stats = torch.zeros(2 * Cin, dtype=torch.float64, device="cuda")
-    out = torch.full((Cin, ld), float("nan"), dtype=torch.bfloat16, device="cuda")
-    ops.gemm_tc(cuda(w).bfloat16(), _padT(dyT), ops._lib.TC_T_DGRAD_ELUBN, Cin, P, Cout, a_mn=True, b_mn=True, out=out,
-                stats=stats, yprev=_padT(yprev), coef=cuda(coef))
+    out = ops.gemm_tc(cuda(w).bfloat16(), _t256(ops, dyT), ops._lib.TC_T_DGRAD_ELUBN, Cin, P, Cout, a_mn=ops._lib.OP_MN,
+                      b_mn=ops._lib.OP_T256_MN, stats=stats, yprev=_t256(ops, yprev), coef=cuda(coef))
     torch.cuda.synchronize()
-    assert rel_err(out[:, :P].float(), dz) < 1e-2
+    assert rel_err(_un(ops, out, P), dz) < 1e-2
+    assert _pad_is_zero(ops, out, P)
     s = stats.cpu()
     assert rel_err(s[:Cin], dz.double().sum(1)) < 1e-3
     assert rel_err(s[Cin:], (dz.double() * xh.double()).sum(1)) < 1e-3
 
 
 @pytest.mark.parametrize("Cout,P,Cin", T_SHAPES)
-def test_gemm_tc_wgrad_kmajor(ops, Cout, P, Cin):
+def test_gemm_tc_wgrad_points_k(ops, Cout, P, Cin):
     g = torch.Generator().manual_seed(Cout + P + Cin + 9)
     dyT = bf16_round(torch.randn(Cout, P, generator=g))
     aT = bf16_round(torch.randn(Cin, P, generator=g))
     dW = torch.zeros(Cout, Cin, device="cuda")
-    ops.gemm_tc(_padT(dyT), _padT(aT), ops._lib.TC_WGRAD_ACC, Cout, Cin, P, out=dW)
+    K_, MN_ = ops._lib.OP_T256_K, ops._lib.OP_T256_MN
+    ops.gemm_tc(_t256(ops, dyT), _t256(ops, aT), ops._lib.TC_WGRAD_ACC, Cout, Cin, P, a_mn=K_, b_mn=K_, out=dW)
     ref = dyT.double() @ aT.double().t()
     assert rel_err(dW, ref) < 1e-4
-    ops.gemm_tc(_padT(dyT), _padT(aT), ops._lib.TC_WGRAD_ACC, Cout, Cin, P, out=dW)      # accumulates
+    ops.gemm_tc(_t256(ops, dyT), _t256(ops, aT), ops._lib.TC_WGRAD_ACC, Cout, Cin, P, a_mn=K_, b_mn=K_, out=dW)   # accumulates
     assert rel_err(dW, 2 * ref) < 1e-4
 
 
 @pytest.mark.parametrize("B,N,C", [(2, 50, 512), (3, 7, 64), (1, 150, 1024), (5, 3, 32)])
 def test_pointnet_t_kernels(ops, B, N, C):
-    """Layer-1 conv, BN+ELU apply, mean pool (+ group sums), pooled backward and BN backward in the channel-major layout
-    against explicit fp32 formulas (P = B*30*N is not a multiple of 8 for the odd N; N < 8 takes the general path)."""
+    """Layer-1 conv, BN+ELU apply, mean pool (+ group sums), pooled backward and BN backward in the T256 layout against
+    explicit fp32 formulas (P = B*30*N is not a multiple of 256; odd N and N < 8 take the general paths)."""
     g = torch.Generator().manual_seed(B * 100 + N)
     T = 30
     P, G = B * T * N, B * T
@@ -479,8 +485,8 @@ def test_pointnet_t_kernels(ops, B, N, C):
     xr = x.permute(1, 0, 2, 3).reshape(4, P)                       # [f, p], p = (b, t, n)
     y_ref = w @ xr + b[:, None]
     yT, st = ops.pointnet_l1_fwd_t(cuda(x), cuda(w), cuda(b))
-    assert yT.shape == (C, (P + 7) // 8 * 8)
-    assert rel_err(yT[:, :P].float(), y_ref) < 1e-2
+    assert yT.shape == ((P + 255) // 256, C, 256)
+    assert rel_err(_un(ops, yT, P), y_ref) < 1e-2 and _pad_is_zero(ops, yT, P)
     s = st.cpu()
     assert rel_err(s[:C], y_ref.double().sum(1)) < 1e-5 and rel_err(s[C:], (y_ref.double() ** 2).sum(1)) < 1e-5
     coef = torch.stack([1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g),
@@ -488,12 +494,12 @@ def test_pointnet_t_kernels(ops, B, N, C):
     sc, sh, mu, inv = (coef[i][:, None] for i in range(4))
     # eval-mode layer 1: activation directly
     aT, none = ops.pointnet_l1_fwd_t(cuda(x), cuda(w), cuda(b), coef=cuda(coef[:2]))
-    assert none is None and rel_err(aT[:, :P].float(), O.elu(y_ref * sc + sh)) < 1e-2
+    assert none is None and rel_err(_un(ops, aT, P), O.elu(y_ref * sc + sh)) < 1e-2 and _pad_is_zero(ops, aT, P)
     # from here on the bf16-rounded y is the common input
-    yb = yT[:, :P].float().cpu()
+    yb = _un(ops, yT, P)
     a_ref = O.elu(yb * sc + sh)
     a = ops.bn_elu_apply_t(yT, cuda(coef), P)
-    assert rel_err(a[:, :P].float(), a_ref) < 1e-2
+    assert rel_err(_un(ops, a, P), a_ref) < 1e-2 and _pad_is_zero(ops, a, P)
     pooled, e1, e2 = ops.bn_elu_meanpool_t(yT, cuda(coef), G, N, want_e=True)
     z = yb * sc + sh
     d = torch.where(z > 0, torch.ones_like(z), torch.exp(z))
@@ -502,7 +508,7 @@ def test_pointnet_t_kernels(ops, B, N, C):
     assert rel_err(e1, d.reshape(C, G, N).sum(2).t()) < 1e-5
     assert rel_err(e2, (d * xh).reshape(C, G, N).sum(2).t()) < 1e-4
     plain, _, _ = ops.bn_elu_meanpool_t(a, None, G, N)
-    assert rel_err(plain, a[:, :P].float().cpu().reshape(C, G, N).mean(2).t()) < 1e-5
+    assert rel_err(plain, _un(ops, a, P).reshape(C, G, N).mean(2).t()) < 1e-5
     # backward of the pooled layer
     dpool = torch.randn(G, C, generator=g)
     dz_ref = (dpool.t().reshape(C, G, 1) / N).expand(C, G, N).reshape(C, P) * d
@@ -512,10 +518,10 @@ def test_pointnet_t_kernels(ops, B, N, C):
     c = torch.stack([1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)])
     dy_ref = c[0][:, None] * dz_ref + c[1][:, None] * yb + c[2][:, None]
     dy = ops.pool_bwd_apply_t(cuda(dpool), yT, cuda(coef), cuda(c), N)
-    assert rel_err(dy[:, :P].float(), dy_ref) < 1e-2
+    assert rel_err(_un(ops, dy, P), dy_ref) < 1e-2 and _pad_is_zero(ops, dy, P)
     # generic BatchNorm backward (in place) and the fused layer-1 weight gradient
-    dzb = _padT(bf16_round(dz_ref))
-    dzf = dzb[:, :P].float().cpu()
+    dzb = _t256(ops, bf16_round(dz_ref))
+    dzf = _un(ops, dzb, P)
     dW = ops.pointnet_l1_wgrad_t(cuda(x), dzb, yT, cuda(c))
     want = (c[0][:, None] * dzf + c[1][:, None] * yb + c[2][:, None]).double() @ xr.double().t()
     assert rel_err(dW, want) < 1e-4
@@ -523,4 +529,5 @@ def test_pointnet_t_kernels(ops, B, N, C):
     assert rel_err(dW0, dzf.double() @ xr.double().t()) < 1e-4
     out = ops.bn_bwd_apply_t(dzb, yT, cuda(c), P, out=dzb)
     assert out.data_ptr() == dzb.data_ptr()
-    assert rel_err(out[:, :P].float(), c[0][:, None] * dzf + c[1][:, None] * yb + c[2][:, None]) < 1e-2
+    assert rel_err(_un(ops, out, P), c[0][:, None] * dzf + c[1][:, None] * yb + c[2][:, None]) < 1e-2
+    assert _pad_is_zero(ops, out, P)
