@@ -114,6 +114,16 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// smem -> global tensor store (bulk async group) and its completion waits
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -199,33 +209,44 @@ __device__ __forceinline__ float warp_col_reduce32(float (&v)[32], int lane) {
     return v[0];
 }
 
-template <int BN>
+// Channel-major modes stage their output (and the dgrad mode its yprev tile) through shared memory, one
+// 32-row x 64-column 128B-swizzled sub-tile (4 KB) per epilogue warp, moved by TMA: the global side of the epilogue
+// costs no LSU wavefronts (a row-per-lane direct access touches 32 cache lines per instruction).
+constexpr int SUB_BYTES = 32 * 64 * 2;
+template <int BN, int MODE>
 struct SmemLayout {
+    static constexpr bool TMODE = is_t_mode<MODE>();
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr int COLP_FLOATS = 5 * BN;          // bias | scale, shift, mean, invstd
-    static constexpr int STAT_FLOATS = 4 * 2 * BN;      // per epilogue warp: sum, sum2
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + (COLP_FLOATS + STAT_FLOATS) * 4 + 256 + 1024;
+    static constexpr int STAGES = (MODE == MODE_T_DGRAD_ELUBN) ? 3 : ((BN == 256) ? 4 : 6);
+    static constexpr int COLP_FLOATS = TMODE ? 0 : 5 * BN;          // bias | scale, shift, mean, invstd
+    static constexpr int STAT_FLOATS = TMODE ? 0 : 4 * 2 * BN;      // per epilogue warp: sum, sum2
+    static constexpr int OBUF_BYTES = TMODE ? 8 * SUB_BYTES : 0;    // output staging, one sub-tile per epilogue warp
+    static constexpr int YBUF_BYTES = (MODE == MODE_T_DGRAD_ELUBN) ? 8 * SUB_BYTES : 0;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + OBUF_BYTES + YBUF_BYTES + (COLP_FLOATS + STAT_FLOATS) * 4 + 256 + 1024;
 };
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-    using L = SmemLayout<BN>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
+    using L = SmemLayout<BN, MODE>;
     constexpr int STAGES = L::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tiles = smem;
-    float* colp = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES);
+    uint8_t* obuf = smem + STAGES * L::STAGE_BYTES;                       // [8][SUB_BYTES], 1024-byte aligned
+    uint8_t* ybuf = obuf + L::OBUF_BYTES;                                 // [8][SUB_BYTES]
+    float* colp = reinterpret_cast<float*>(ybuf + L::YBUF_BYTES);
     float* wstat = colp + L::COLP_FLOATS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(wstat + L::STAT_FLOATS);
     uint64_t* full = bars;                   // [STAGES]
     uint64_t* empty = bars + STAGES;         // [STAGES]
     uint64_t* tfull = bars + 2 * STAGES;     // [2]
     uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* ybar = bars + 2 * STAGES + 4;  // [8] yprev sub-tile landed (one per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -240,6 +261,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], EPI_THREADS / 32);
+        }
+        for (int i = 0; i < 8; ++i) mbar_init(&ybar[i], 1);
+        if constexpr (is_t_mode<MODE>()) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+            if constexpr (MODE == MODE_T_DGRAD_ELUBN) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -337,17 +363,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================================================================== epilogue warps, channel-major modes
         // thread = one output row (channel): its bias / BatchNorm coefficients are scalars, its statistics are plain
         // running sums kept in registers over all tiles of the CTA (the scheduler keeps the m block fixed) and
-        // flushed with ONE double atomic per row at the end.  TMEM loads are software-pipelined: the load of chunk
-        // c+1 is in flight while chunk c is processed.
+        // flushed with ONE double atomic per row at the end.  A warp owns 32 rows x 128 columns of the tile and moves
+        // them as two 64-column sub-tiles: TMEM -> registers -> 128B-swizzled shared memory -> TMA store (and, for the
+        // data gradient, yprev sub-tiles arrive by TMA one step ahead).  TMEM loads are software-pipelined.
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        constexpr int CPW = BN / 64;                    // 32-column chunks per warp per tile
+        const int ew = warp - 2;                         // 0..7
+        constexpr int CPW = BN / 64;                     // 32-column chunks per warp per tile (4)
+        uint8_t* my_o = obuf + ew * SUB_BYTES;
+        uint8_t* my_y = ybuf + ew * SUB_BYTES;
+        const uint32_t sw = (uint32_t)(lane & 7);        // 128B swizzle: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+        const uint32_t row_off = (uint32_t)lane * 128u;
         int cur_m = -1;
         int64_t row = 0;
         bool row_ok = false;
         float r_bias = 0.f, r_scale = 0.f, r_shift = 0.f, r_mean = 0.f, r_invstd = 0.f;
         double d1 = 0.0, d2 = 0.0;
+        uint32_t yphase = 0;
         int m_blk, n_blk, ks;
+        if constexpr (MODE == MODE_T_DGRAD_ELUBN) {
+            // first yprev sub-tile of this warp
+            if (lane == 0 && tile_at(p, 0, m_blk, n_blk, ks)) {
+                mbar_expect_tx(&ybar[ew], SUB_BYTES);
+                tma_load_3d(&tmY, &ybar[ew], my_y, half * (BN / 2), m_blk * BM + q * 32, n_blk);
+            }
+        }
         for (int it = 0; tile_at(p, it, m_blk, n_blk, ks); ++it) {
             if (m_blk != cur_m) {
                 if (cur_m >= 0 && row_ok && MODE != MODE_T_AFFINE_ELU) {
@@ -375,6 +415,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * (BN / 2);
             uint32_t ra[32], rb[32];
+            uint4 yraw[8];
             float t1 = 0.f, t2 = 0.f;
             tmem_ld32_issue(taddr, ra);
 #pragma unroll
@@ -382,13 +423,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t (&r)[32] = (c & 1) ? rb : ra;
                 uint32_t (&rn)[32] = (c & 1) ? ra : rb;
                 const int64_t col0 = n0 + c * 32;
-                // tiled addressing: element (row, point) lives at ((tile * M + row) * 256 + point % 256)
-                const int64_t toff = ((int64_t)n_blk * p.M + (row_ok ? row : 0)) * BN + half * (BN / 2) + c * 32;
-                uint4 yraw[4];
                 if constexpr (MODE == MODE_T_DGRAD_ELUBN) {
-                    const uint4* yp = reinterpret_cast<const uint4*>(p.yprev + toff);
+                    if ((c & 1) == 0) {
+                        // the 64-column yprev sub-tile of this step: shared memory -> registers, then refill the buffer
+                        mbar_wait(&ybar[ew], yphase);
+                        yphase ^= 1;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) yraw[g] = row_ok ? __ldg(yp + g) : make_uint4(0, 0, 0, 0);
+                        for (int g = 0; g < 8; ++g)
+                            yraw[g] = *reinterpret_cast<const uint4*>(my_y + row_off + (((uint32_t)g ^ sw) << 4));
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            int nm = m_blk, nn = n_blk, nk, nsub = (c >> 1) + 1;
+                            bool more = true;
+                            if (nsub == CPW / 2) { nsub = 0; more = tile_at(p, it + 1, nm, nn, nk); }
+                            if (more) {
+                                mbar_expect_tx(&ybar[ew], SUB_BYTES);
+                                tma_load_3d(&tmY, &ybar[ew], my_y, half * (BN / 2) + nsub * 64, nm * BM + q * 32, nn);
+                            }
+                        }
+                    }
                 }
                 tmem_ld_wait(r);
                 if (c + 1 < CPW) tmem_ld32_issue(taddr + (c + 1) * 32, rn);
@@ -412,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yraw[g]);
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yraw[(c & 1) * 4 + g]);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float2 f = __bfloat1622float2(h[e]);
@@ -421,9 +475,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const int j = g * 8 + 2 * e + u;
                                 const float yv = u ? f.y : f.x;
                                 const float z = fmaf(yv, r_scale, r_shift);
-                                const bool in = full_chunk || col0 + j < p.N;   // pad columns may hold NaN bits
+                                const bool in = full_chunk || col0 + j < p.N;   // pad columns of yprev are zeros, the accumulator's are not
                                 const float gq = in ? v[j] * (z > 0.f ? 1.f : __expf(z)) : 0.f;
-                                const float xh = in ? (yv - r_mean) * r_invstd : 0.f;
+                                const float xh = (yv - r_mean) * r_invstd;
                                 v[j] = gq;
                                 t1 += gq;
                                 t2 = fmaf(gq, xh, t2);
@@ -431,15 +485,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (row_ok) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + toff;
+                if ((c & 1) == 0) {
+                    // the previous TMA store must have finished READING the staging buffer before it is overwritten
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 u;
-                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                for (int g = 0; g < 4; ++g) {
+                    uint4 u;
+                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-                        *reinterpret_cast<uint4*>(o + g * 8) = u;
+                    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4*>(my_o + row_off + (((uint32_t)((c & 1) * 4 + g) ^ sw) << 4)) = u;
+                }
+                if (c & 1) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        // rows >= M are clipped by the tensor map
+                        tma_store_3d(&tmO, my_o, half * (BN / 2) + (c >> 1) * 64, m_blk * BM + q * 32, n_blk);
+                        tma_store_commit();
                     }
                 }
             }
@@ -454,6 +519,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             atomicAdd(&p.stats[row], d1);
             atomicAdd(&p.stats[p.M + row], d2);
         }
+        if (lane == 0) tma_store_wait_all();
     } else {
         // ===================================================================== epilogue warps
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
@@ -669,6 +735,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t d0, int64_t d1, int
 
 // 3-D bf16 tensor map of a tiled operand [n_tiles][C][256]: box = b0 points x b1 channels x 1 tile
 static int make_map_tiled(CUtensorMap* m, const void* ptr, int64_t C, int64_t n_tiles, int b0, int b1) {
+    PCAA_REQUIRE(ptr != nullptr, PCAA_ERR_SHAPE, "gemm_tc: null T256 tensor");
     EncodeTiledFn enc = get_encode();
     PCAA_REQUIRE(enc != nullptr, PCAA_ERR_DRIVER, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
     PCAA_REQUIRE(((uintptr_t)ptr & 15) == 0, PCAA_ERR_ALIGN, "tiled tensor-core operand must be 16-byte aligned");
@@ -695,13 +762,16 @@ static int num_sms() {
 }
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& ty,
+                     const GemmParams& p, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, A_MN, B_MN, MODE>;
+    using L = SmemLayout<BN, MODE>;
+    static_assert(L::TOTAL <= 232448, "shared memory budget of one CTA exceeded");
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
         if (e != cudaSuccess) {
-            set_error("gemm_tc: cannot reserve %d bytes of shared memory: %s", SmemLayout<BN>::TOTAL,
+            set_error("gemm_tc: cannot reserve %d bytes of shared memory: %s", L::TOTAL,
                       cudaGetErrorString(e));
             return PCAA_ERR_LAUNCH;
         }
@@ -719,7 +789,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
         }
         grid = per * p.m_tiles;
     }
-    kern<<<grid, NUM_THREADS, SmemLayout<BN>::TOTAL, st>>>(ta, tb, p);
+    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ta, tb, to, ty, p);
     return check_launch("gemm_tc");
 }
 
@@ -770,6 +840,16 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
     else rc = b_mn ? make_map(&tb, B, N, K, ldb, 64, BK) : make_map(&tb, B, K, N, ldb, BK, BN);
     if (rc) return rc;
     PCAA_REQUIRE(a_tiled == (b_tiled && !b_mn), PCAA_ERR_UNSUPPORTED, "gemm_tc: k = points needs BOTH operands tiled (PCAA_OP_T256_K)");
+    // channel-major modes: the epilogue moves 64-point x 32-channel sub-tiles of out (and yprev) by TMA
+    CUtensorMap to = ta, ty = ta;
+    if (tmode) {
+        rc = make_map_tiled(&to, out, M, ceil_div(N, 256), 64, 32);
+        if (rc) return rc;
+        if (mode == PCAA_TC_T_DGRAD_ELUBN) {
+            rc = make_map_tiled(&ty, yprev, M, ceil_div(N, 256), 64, 32);
+            if (rc) return rc;
+        }
+    }
     GemmParams p{};
     p.M = M;
     p.N = N;
@@ -804,25 +884,25 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
     p.sched_mfixed = tmode ? 1 : 0;
     const int key = (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
     if (key == 0) {
-        if (wgrad) return launch_tc<BN, false, false, MODE_WGRAD>(ta, tb, p, st);
+        if (wgrad) return launch_tc<BN, false, false, MODE_WGRAD>(ta, tb, to, ty, p, st);
         switch (mode) {
-            case PCAA_TC_BIAS_STATS: return launch_tc<BN, false, false, MODE_BIAS_STATS>(ta, tb, p, st);
-            case PCAA_TC_BIAS_ELU: return launch_tc<BN, false, false, MODE_BIAS_ELU>(ta, tb, p, st);
-            case PCAA_TC_PLAIN: return launch_tc<BN, false, false, MODE_PLAIN>(ta, tb, p, st);
-            case PCAA_TC_DGRAD_ELUBN: return launch_tc<BN, false, false, MODE_DGRAD_ELUBN>(ta, tb, p, st);
+            case PCAA_TC_BIAS_STATS: return launch_tc<BN, false, false, MODE_BIAS_STATS>(ta, tb, to, ty, p, st);
+            case PCAA_TC_BIAS_ELU: return launch_tc<BN, false, false, MODE_BIAS_ELU>(ta, tb, to, ty, p, st);
+            case PCAA_TC_PLAIN: return launch_tc<BN, false, false, MODE_PLAIN>(ta, tb, to, ty, p, st);
+            case PCAA_TC_DGRAD_ELUBN: return launch_tc<BN, false, false, MODE_DGRAD_ELUBN>(ta, tb, to, ty, p, st);
             default: break;
         }
     } else if (key == 1) {
         switch (mode) {
-            case PCAA_TC_PLAIN: return launch_tc<BN, false, true, MODE_PLAIN>(ta, tb, p, st);
-            case PCAA_TC_DGRAD_ELUOUT: return launch_tc<BN, false, true, MODE_DGRAD_ELUOUT>(ta, tb, p, st);
-            case PCAA_TC_T_BIAS_STATS: return launch_tc<BN, false, true, MODE_T_BIAS_STATS>(ta, tb, p, st);
-            case PCAA_TC_T_AFFINE_ELU: return launch_tc<BN, false, true, MODE_T_AFFINE_ELU>(ta, tb, p, st);
+            case PCAA_TC_PLAIN: return launch_tc<BN, false, true, MODE_PLAIN>(ta, tb, to, ty, p, st);
+            case PCAA_TC_DGRAD_ELUOUT: return launch_tc<BN, false, true, MODE_DGRAD_ELUOUT>(ta, tb, to, ty, p, st);
+            case PCAA_TC_T_BIAS_STATS: return launch_tc<BN, false, true, MODE_T_BIAS_STATS>(ta, tb, to, ty, p, st);
+            case PCAA_TC_T_AFFINE_ELU: return launch_tc<BN, false, true, MODE_T_AFFINE_ELU>(ta, tb, to, ty, p, st);
             default: break;
         }
     } else if (key == 3) {
-        if (wgrad) return launch_tc<BN, true, true, MODE_WGRAD>(ta, tb, p, st);
-        if (mode == PCAA_TC_T_DGRAD_ELUBN) return launch_tc<BN, true, true, MODE_T_DGRAD_ELUBN>(ta, tb, p, st);
+        if (wgrad) return launch_tc<BN, true, true, MODE_WGRAD>(ta, tb, to, ty, p, st);
+        if (mode == PCAA_TC_T_DGRAD_ELUBN) return launch_tc<BN, true, true, MODE_T_DGRAD_ELUBN>(ta, tb, to, ty, p, st);
     }
     set_error("gemm_tc: operand layout (a=%d, b=%d) is not instantiated for mode %d", a_layout, b_layout, mode);
     return PCAA_ERR_UNSUPPORTED;
