@@ -91,9 +91,9 @@ static int launch(const void* A, int64_t sam, int64_t sak, const void* B, int64_
     // tall-K products with few output tiles (weight gradients of the TCN / heads: K = rows) would leave most SMs idle:
     // split K over grid.z and reduce with fp32 atomics into a zeroed, contiguous fp32 C
     const int64_t tiles = (int64_t)grid.x * grid.y;
-    if (sizeof(TC) == 4 && act == PCAA_ACT_NONE && !accumulate && scn == 1 && scm == N && K >= 2048 && tiles <= 74) {
-        int splits = (int)((2 * 148 + tiles - 1) / tiles);
-        int max_splits = (int)(K / 256);
+    if (sizeof(TC) == 4 && act == PCAA_ACT_NONE && !accumulate && scn == 1 && scm == N && K >= 512 && tiles < 2 * 148) {
+        int splits = (int)((4 * 148 + tiles - 1) / tiles);
+        int max_splits = (int)(K / 128);
         if (splits > max_splits) splits = max_splits;
         if (splits > 1) {
             k_per_split = ((K + splits - 1) / splits + TK - 1) / TK * TK;

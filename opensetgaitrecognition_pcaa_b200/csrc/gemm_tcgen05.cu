@@ -290,6 +290,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int it = 0; tile_at(p, it, m_blk, n_blk, ks); ++it) {
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                if constexpr (MODE == MODE_T_DGRAD_ELUBN) {
+                    // the epilogue reads this CTA's [128 x 256] block of yprev (contiguous in T256) two tiles from now:
+                    // pull it into L2 so its per-warp sub-tile loads do not wait on DRAM
+                    for (int t = (it == 0 ? 0 : it + 2); t <= it + 2; ++t) {
+                        int pm, pn, pk;
+                        if (tile_at(p, t, pm, pn, pk)) {
+                            const int64_t rows = min((int64_t)BM, p.M - (int64_t)pm * BM);
+                            const __nv_bfloat16* src = p.yprev + ((int64_t)pn * p.M + (int64_t)pm * BM) * 256;
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(rows * 512)) : "memory");
+                        }
+                    }
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = tiles + stage * L::STAGE_BYTES;

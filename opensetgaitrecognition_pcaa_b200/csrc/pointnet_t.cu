@@ -388,6 +388,177 @@ pool_bwd_apply_t_kernel(const float* __restrict__ dpool, const __nv_bfloat16* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------ row-streaming variants
+// (groups of n >= 8 points).  A warp streams whole 512-byte tile rows (one channel x 256 points, 8 points per lane): the
+// position of the group boundaries inside a tile depends on the lane only, so the per-lane group bookkeeping is set
+// up once and reused for every channel row of the block.
+struct LaneGroups {
+    int64_t g0;        // group of the lane's first point
+    int split;         // elements j < split belong to g0, the others to g0 + 1  (n >= 8: at most one boundary per chunk)
+    int vcnt;          // elements j < vcnt are real points (the last tile is zero padded)
+};
+__device__ __forceinline__ LaneGroups lane_groups(int64_t tile, int lane, int n, int64_t P) {
+    LaneGroups r;
+    const int64_t p0 = (tile << 8) + (lane << 3);
+    r.g0 = p0 / n;
+    const int64_t nxt = (r.g0 + 1) * n - p0;
+    r.split = nxt < 8 ? (int)nxt : 8;
+    const int64_t left = P - p0;
+    r.vcnt = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
+    return r;
+}
+
+constexpr int MP_ROWS_PER_WARP = 8;
+
+// grid (ceil(C / 64), n_tiles), 8 warps; warp w owns channels cb + w + 8*i.  pooled / e1 / e2 must be zeroed: a group
+// receives one contribution per tile it touches (+ one when a lane-31 chunk straddles), added atomically.
+template <bool TRAIN>
+__global__ void __launch_bounds__(256)
+bn_elu_meanpool_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* __restrict__ scale,
+                            const float* __restrict__ shift, const float* __restrict__ mean,
+                            const float* __restrict__ invstd, float* __restrict__ pooled, float* __restrict__ e1,
+                            float* __restrict__ e2, int64_t P, int64_t G, int n, int C, int apply, float inv_n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.y;
+    const int cb = blockIdx.x * (8 * MP_ROWS_PER_WARP) + warp;
+    const LaneGroups lg = lane_groups(tile, lane, n, P);
+    float wT[8], wA[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        wT[j] = j < lg.vcnt ? 1.f : 0.f;
+        wA[j] = (j < lg.vcnt && j < lg.split) ? 1.f : 0.f;
+    }
+    // segmented reduction over the lanes of one group (contiguous run of lanes with the same g0)
+    bool same[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int64_t other = __shfl_down_sync(0xffffffffu, lg.g0, 1 << s);
+        same[s] = (lane + (1 << s) < 32) && other == lg.g0;
+    }
+    const int64_t prev = __shfl_up_sync(0xffffffffu, lg.g0, 1);
+    const bool head = lane == 0 || prev != lg.g0;
+    const bool straddle = lg.split < 8;
+    const bool prev_straddle = __shfl_up_sync(0xffffffffu, straddle ? 1 : 0, 1) != 0 && lane > 0;
+    const int64_t tile_off = tile * (int64_t)C * 256 + lane * 8;
+
+    uint4 raw[MP_ROWS_PER_WARP];
+#pragma unroll
+    for (int i = 0; i < MP_ROWS_PER_WARP; ++i) {
+        const int c = cb + 8 * i;
+        if (c < C) raw[i] = __ldg(reinterpret_cast<const uint4*>(yT + tile_off + (int64_t)c * 256));
+    }
+#pragma unroll
+    for (int i = 0; i < MP_ROWS_PER_WARP; ++i) {
+        const int c = cb + 8 * i;
+        if (c >= C) break;
+        const float sc = apply ? __ldg(scale + c) : 1.f, sh = apply ? __ldg(shift + c) : 0.f;
+        float y[8];
+        unpack8(raw[i], y);
+        float Ts = 0.f, As = 0.f, Td = 0.f, Ad = 0.f, Tu = 0.f, Au = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(y[j], sc, sh);
+            float a = z, d = 1.f;
+            if (apply) {
+                const float e = __expf(z);
+                a = z > 0.f ? z : e - 1.f;
+                d = z > 0.f ? 1.f : e;
+            }
+            Ts = fmaf(wT[j], a, Ts);
+            As = fmaf(wA[j], a, As);
+            if (TRAIN) {
+                const float dy = d * y[j];
+                Td = fmaf(wT[j], d, Td);
+                Ad = fmaf(wA[j], d, Ad);
+                Tu = fmaf(wT[j], dy, Tu);
+                Au = fmaf(wA[j], dy, Au);
+            }
+        }
+        // the part of a straddling chunk that belongs to the next group joins the next lane's run
+        float Bs = Ts - As, Bd = Td - Ad, Bu = Tu - Au;
+        const float ps = __shfl_up_sync(0xffffffffu, Bs, 1);
+        As += prev_straddle ? ps : 0.f;
+        if (TRAIN) {
+            const float pd = __shfl_up_sync(0xffffffffu, Bd, 1), pu = __shfl_up_sync(0xffffffffu, Bu, 1);
+            Ad += prev_straddle ? pd : 0.f;
+            Au += prev_straddle ? pu : 0.f;
+        }
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const float o = __shfl_down_sync(0xffffffffu, As, 1 << s);
+            As += same[s] ? o : 0.f;
+            if (TRAIN) {
+                const float od = __shfl_down_sync(0xffffffffu, Ad, 1 << s), ou = __shfl_down_sync(0xffffffffu, Au, 1 << s);
+                Ad += same[s] ? od : 0.f;
+                Au += same[s] ? ou : 0.f;
+            }
+        }
+        float mu = 0.f, is = 0.f;
+        if (TRAIN) { mu = __ldg(mean + c); is = __ldg(invstd + c); }
+        if (head && lg.g0 < G) {
+            const int64_t o = lg.g0 * C + c;
+            atomicAdd(pooled + o, As * inv_n);
+            if (TRAIN) {
+                atomicAdd(e1 + o, Ad);
+                atomicAdd(e2 + o, is * (Au - mu * Ad));     // sum d*xhat = invstd * (sum d*y - mean * sum d)
+            }
+        }
+        if (lane == 31 && straddle && lg.g0 + 1 < G) {
+            const int64_t o = (lg.g0 + 1) * C + c;
+            atomicAdd(pooled + o, Bs * inv_n);
+            if (TRAIN) {
+                atomicAdd(e1 + o, Bd);
+                atomicAdd(e2 + o, is * (Bu - mu * Bd));
+            }
+        }
+    }
+}
+
+constexpr int PB_ROWS_PER_WARP = 4;
+
+// dy(c,p) = c1[c]*(dpool[g(p)][c]/n)*ELU'(scale*y+shift) + c2[c]*y + c3[c]; grid (ceil(C / 32), n_tiles), n >= 8
+__global__ void __launch_bounds__(256)
+pool_bwd_apply_rows_kernel(const float* __restrict__ dpool, const __nv_bfloat16* __restrict__ yT,
+                           const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ c1,
+                           const float* __restrict__ c2, const float* __restrict__ c3, __nv_bfloat16* __restrict__ dyT,
+                           int64_t P, int64_t G, int n, int C, float inv_n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.y;
+    const int cb = blockIdx.x * (8 * PB_ROWS_PER_WARP) + warp;
+    const LaneGroups lg = lane_groups(tile, lane, n, P);
+    const int64_t tile_off = tile * (int64_t)C * 256 + lane * 8;
+    const bool has0 = lg.g0 < G, has1 = lg.split < 8 && lg.g0 + 1 < G;
+    uint4 raw[PB_ROWS_PER_WARP];
+    float g0v[PB_ROWS_PER_WARP], g1v[PB_ROWS_PER_WARP];
+#pragma unroll
+    for (int i = 0; i < PB_ROWS_PER_WARP; ++i) {
+        const int c = cb + 8 * i;
+        if (c < C) {
+            raw[i] = __ldg(reinterpret_cast<const uint4*>(yT + tile_off + (int64_t)c * 256));
+            g0v[i] = has0 ? __ldg(dpool + lg.g0 * C + c) : 0.f;
+            g1v[i] = has1 ? __ldg(dpool + (lg.g0 + 1) * C + c) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PB_ROWS_PER_WARP; ++i) {
+        const int c = cb + 8 * i;
+        if (c >= C) break;
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const float a1 = __ldg(c1 + c) * inv_n, a2 = __ldg(c2 + c), a3 = __ldg(c3 + c);
+        const float ga = a1 * g0v[i], gb = a1 * g1v[i];
+        float y[8];
+        unpack8(raw[i], y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(y[j], sc, sh);
+            const float d = z > 0.f ? 1.f : __expf(z);
+            const float gv = j < lg.split ? ga : gb;
+            y[j] = j < lg.vcnt ? fmaf(gv, d, fmaf(a2, y[j], a3)) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dyT + tile_off + (int64_t)c * 256) = pack8(y);
+    }
+}
+
 }  // namespace pcaa
 
 using namespace pcaa;
@@ -444,6 +615,19 @@ int pcaa_bn_elu_meanpool_t(const void* yT, const float* scale, const float* shif
     PCAA_REQUIRE((e1 == nullptr) == (e2 == nullptr) && (e1 == nullptr || (mean && invstd && scale)), PCAA_ERR_SHAPE,
                  "bn_elu_meanpool_t: e1/e2 need mean/invstd/scale");
     const int apply = scale != nullptr;
+    if (n >= 8) {
+        const int64_t P = G * n;
+        const size_t bytes = sizeof(float) * (size_t)G * C;
+        if (cudaMemsetAsync(pooled, 0, bytes, ST(stream)) != cudaSuccess || (e1 && cudaMemsetAsync(e1, 0, bytes, ST(stream)) != cudaSuccess) ||
+            (e2 && cudaMemsetAsync(e2, 0, bytes, ST(stream)) != cudaSuccess))
+            return check_launch("bn_elu_meanpool_t memset");
+        dim3 grid((unsigned)ceil_div(C, 8 * MP_ROWS_PER_WARP), (unsigned)((P + 255) / 256));
+        if (e1)
+            bn_elu_meanpool_rows_kernel<true><<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, P, G, n, C, apply, 1.f / (float)n);
+        else
+            bn_elu_meanpool_rows_kernel<false><<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, P, G, n, C, apply, 1.f / (float)n);
+        return check_launch("bn_elu_meanpool_t");
+    }
     dim3 grid((unsigned)ceil_div(G, 8), (unsigned)ceil_div(C, 32));
     bn_elu_meanpool_t_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, G, n, C, apply);
     return check_launch("bn_elu_meanpool_t");
@@ -464,6 +648,11 @@ int pcaa_pool_bwd_apply_t(const float* dpool, const void* yT, const float* scale
     if (G == 0 || C == 0) return PCAA_OK;
     PCAA_REQUIRE(n >= 1, PCAA_ERR_SHAPE, "pool_bwd_apply_t: bad group size");
     const int64_t P = G * n;
+    if (n >= 8) {
+        dim3 grid((unsigned)ceil_div(C, 8 * PB_ROWS_PER_WARP), (unsigned)((P + 255) / 256));
+        pool_bwd_apply_rows_kernel<<<grid, 256, 0, ST(stream)>>>(dpool, (const __nv_bfloat16*)yT, scale, shift, c1, c2, c3, (__nv_bfloat16*)dyT, P, G, n, C, 1.f / (float)n);
+        return check_launch("pool_bwd_apply_t");
+    }
     const int64_t nch = t256_chunks(P, C);
     pool_bwd_apply_t_kernel<<<ew_blocks(nch), 256, 0, ST(stream)>>>(dpool, (const __nv_bfloat16*)yT, scale, shift, c1, c2, c3, (__nv_bfloat16*)dyT, nch, P, n, C, 1.f / (float)n);
     return check_launch("pool_bwd_apply_t");

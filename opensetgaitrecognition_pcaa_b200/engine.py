@@ -179,7 +179,8 @@ def tcn_backward(dout: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = N
         o = _out(gradbuf, k + "conv1d.weight")
         dW = ops.gemm(dy, col, trans_a=True, out=None if o is None else o.view(Cout, Cin * 3))
         G[k + "conv1d.weight"] = dW.view(W.shape) if o is None else o
-        G[k + "conv1d.bias"] = ops.colsum(dy, _out(gradbuf, k + "conv1d.bias"))
+        # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero (sum_rows dy = 0)
+        G[k + "conv1d.bias"] = _zeros_like_param(gradbuf, k + "conv1d.bias", P[k + "conv1d.bias"])
         dcol = ops.gemm(dy, W.view(Cout, Cin * 3))
         d = ops.tcn_col2im(dcol, B, T, Cin, DTC_DILATIONS[l - 1]).view(R, Cin)
     return d.view(B, T, -1), G
