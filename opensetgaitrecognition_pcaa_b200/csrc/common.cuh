@@ -25,6 +25,17 @@ __device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : expm1f(z)
 // derivative of ELU(alpha=1) at pre-activation z
 __device__ __forceinline__ float elu_grad_f(float z) { return z > 0.f ? 1.f : __expf(z); }
 
+// 2^x on the SFU (one MUFU.EX2, no range fix-up); ELU / ELU' from z and zl = z * log2(e) (zl comes from a second FMA with
+// pre-scaled BatchNorm coefficients, so the exponential costs no extra multiply)
+constexpr float LOG2E_F = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float elu_l2(float z, float zl) { return z > 0.f ? z : ex2_fast(zl) - 1.f; }
+__device__ __forceinline__ float elu_grad_l2(float z, float zl) { return z > 0.f ? 1.f : ex2_fast(zl); }
+
 template <typename T> __device__ __forceinline__ float ld_as_float(const T* p);
 template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }

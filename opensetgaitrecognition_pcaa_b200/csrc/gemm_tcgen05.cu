@@ -227,6 +227,48 @@ struct SmemLayout {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OBUF_BYTES + YBUF_BYTES + (COLP_FLOATS + STAT_FLOATS) * 4 + 256 + 1024;
 };
 
+
+// epilogue arithmetic of one 32-column chunk of a channel-major tile (thread = row).  FULL: every column is a real
+// point; otherwise columns >= valid are pad points and are stored as zeros / kept out of the statistics.
+struct TRow { float bias, scale, shift, scale_l2, shift_l2, invstd, nmean_invstd; };
+template <int MODE, bool FULL>
+__device__ __forceinline__ void t_chunk(float (&v)[32], const uint4* yraw4, const TRow& r, int valid, float& t1, float& t2) {
+    if constexpr (MODE == MODE_T_BIAS_STATS) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            v[j] = (FULL || j < valid) ? v[j] + r.bias : 0.f;
+            t1 += v[j];
+            t2 = fmaf(v[j], v[j], t2);
+        }
+    } else if constexpr (MODE == MODE_T_AFFINE_ELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float z = fmaf(v[j], r.scale, r.shift), zl = fmaf(v[j], r.scale_l2, r.shift_l2);
+            v[j] = (FULL || j < valid) ? elu_l2(z, zl) : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yraw4[g]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = g * 8 + 2 * e + u;
+                    const float yv = u ? f.y : f.x;
+                    const float z = fmaf(yv, r.scale, r.shift), zl = fmaf(yv, r.scale_l2, r.shift_l2);
+                    const float gq = (FULL || j < valid) ? v[j] * elu_grad_l2(z, zl) : 0.f;
+                    const float xh = fmaf(yv, r.invstd, r.nmean_invstd);
+                    v[j] = gq;
+                    t1 += gq;
+                    t2 = fmaf(gq, xh, t2);
+                }
+            }
+        }
+    }
+}
+
 template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -389,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int cur_m = -1;
         int64_t row = 0;
         bool row_ok = false;
-        float r_bias = 0.f, r_scale = 0.f, r_shift = 0.f, r_mean = 0.f, r_invstd = 0.f;
+        TRow tr{};
         double d1 = 0.0, d2 = 0.0;
         uint32_t yphase = 0;
         int m_blk, n_blk, ks;
@@ -411,14 +453,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 row = (int64_t)m_blk * BM + q * 32 + lane;
                 row_ok = row < p.M;
                 if (row_ok) {
-                    if constexpr (MODE == MODE_T_BIAS_STATS) r_bias = p.bias ? p.bias[row] : 0.f;
+                    if constexpr (MODE == MODE_T_BIAS_STATS) tr.bias = p.bias ? p.bias[row] : 0.f;
                     if constexpr (MODE == MODE_T_AFFINE_ELU) {
-                        r_scale = p.scale[row];
-                        r_shift = p.bias ? fmaf(p.bias[row], r_scale, p.shift[row]) : p.shift[row];
+                        tr.scale = p.scale[row];
+                        tr.shift = p.bias ? fmaf(p.bias[row], tr.scale, p.shift[row]) : p.shift[row];
                     }
                     if constexpr (MODE == MODE_T_DGRAD_ELUBN) {
-                        r_scale = p.scale[row]; r_shift = p.shift[row]; r_mean = p.mean[row]; r_invstd = p.invstd[row];
+                        tr.scale = p.scale[row]; tr.shift = p.shift[row];
+                        tr.invstd = p.invstd[row]; tr.nmean_invstd = -p.mean[row] * tr.invstd;
                     }
+                    tr.scale_l2 = tr.scale * LOG2E_F;
+                    tr.shift_l2 = tr.shift * LOG2E_F;
                 }
             }
             const int buf = it & 1;
@@ -461,42 +506,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                const bool full_chunk = col0 + 32 <= p.N;
-                if constexpr (MODE == MODE_T_BIAS_STATS) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = (full_chunk || col0 + j < p.N) ? v[j] + r_bias : 0.f;     // pad points are stored as zeros
-                        t1 += v[j];
-                        t2 = fmaf(v[j], v[j], t2);
-                    }
-                } else if constexpr (MODE == MODE_T_AFFINE_ELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float z = fmaf(v[j], r_scale, r_shift);
-                        v[j] = (full_chunk || col0 + j < p.N) ? (z > 0.f ? z : __expf(z) - 1.f) : 0.f;
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&yraw[(c & 1) * 4 + g]);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 f = __bfloat1622float2(h[e]);
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const int j = g * 8 + 2 * e + u;
-                                const float yv = u ? f.y : f.x;
-                                const float z = fmaf(yv, r_scale, r_shift);
-                                const bool in = full_chunk || col0 + j < p.N;   // pad columns of yprev are zeros, the accumulator's are not
-                                const float gq = in ? v[j] * (z > 0.f ? 1.f : __expf(z)) : 0.f;
-                                const float xh = (yv - r_mean) * r_invstd;
-                                v[j] = gq;
-                                t1 += gq;
-                                t2 = fmaf(gq, xh, t2);
-                            }
-                        }
-                    }
-                }
+                if (col0 + 32 <= p.N) t_chunk<MODE, true>(v, &yraw[(c & 1) * 4], tr, 32, t1, t2);
+                else t_chunk<MODE, false>(v, &yraw[(c & 1) * 4], tr, (int)max((int64_t)0, p.N - col0), t1, t2);
                 if ((c & 1) == 0) {
                     // the previous TMA store must have finished READING the staging buffer before it is overwritten
                     if (lane == 0) tma_store_wait_read();

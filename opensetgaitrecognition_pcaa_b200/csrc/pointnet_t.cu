@@ -63,23 +63,34 @@ __device__ __forceinline__ void load_x8(const float* __restrict__ x, int64_t p0,
 constexpr int L1_CH_PER_WARP = 8;
 constexpr int L1_TILE_POINTS = 2048;
 
-__global__ void __launch_bounds__(256)
+// per-channel constants of the block's 64 channels live in shared memory (broadcast reads) so that the register budget
+// allows three resident CTAs per SM: the kernels are bound by the latency of their global accesses
+struct L1Coef { float w[4]; float bias, scale, shift, scale_l2, shift_l2, pad0, pad1, pad2; };
+
+__global__ void __launch_bounds__(256, 3)
 pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          __nv_bfloat16* __restrict__ yT, double* __restrict__ stats, int64_t P, int64_t TN, int Cout) {
+    __shared__ L1Coef coef[8 * L1_CH_PER_WARP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 8 * L1_CH_PER_WARP) {
+        const int c = min(blockIdx.y * 8 * L1_CH_PER_WARP + (int)threadIdx.x, Cout - 1);
+        L1Coef k;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(w) + c);
+        k.w[0] = t.x; k.w[1] = t.y; k.w[2] = t.z; k.w[3] = t.w;
+        k.bias = bias ? __ldg(bias + c) : 0.f;
+        k.scale = scale ? __ldg(scale + c) : 1.f;
+        k.shift = shift ? __ldg(shift + c) : 0.f;
+        k.scale_l2 = k.scale * LOG2E_F;
+        k.shift_l2 = k.shift * LOG2E_F;
+        k.pad0 = k.pad1 = k.pad2 = 0.f;
+        coef[threadIdx.x] = k;
+    }
+    __syncthreads();
     const int c0 = (blockIdx.y * 8 + warp) * L1_CH_PER_WARP;
     if (c0 >= Cout) return;
-    float wr[L1_CH_PER_WARP][4], br[L1_CH_PER_WARP], sc[L1_CH_PER_WARP], sh[L1_CH_PER_WARP];
-#pragma unroll
-    for (int k = 0; k < L1_CH_PER_WARP; ++k) {
-        const int c = min(c0 + k, Cout - 1);
-        const float4 t = __ldg(reinterpret_cast<const float4*>(w) + c);
-        wr[k][0] = t.x; wr[k][1] = t.y; wr[k][2] = t.z; wr[k][3] = t.w;
-        br[k] = bias ? __ldg(bias + c) : 0.f;
-        sc[k] = scale ? __ldg(scale + c) : 1.f;
-        sh[k] = shift ? __ldg(shift + c) : 0.f;
-    }
+    const L1Coef* ck = coef + warp * L1_CH_PER_WARP;
+    const bool act = scale != nullptr;
     float s1[L1_CH_PER_WARP], s2[L1_CH_PER_WARP];
 #pragma unroll
     for (int k = 0; k < L1_CH_PER_WARP; ++k) s1[k] = s2[k] = 0.f;
@@ -91,21 +102,27 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
         float xv[4][8];
 #pragma unroll
         for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);
-        const bool full = p0 + 8 <= P;
+        const int vcnt = p0 + 8 <= P ? 8 : (p0 < P ? (int)(P - p0) : 0);
 #pragma unroll
         for (int k = 0; k < L1_CH_PER_WARP; ++k) {
+            const float4 wk = *reinterpret_cast<const float4*>(ck[k].w);
+            const float4 bk = *reinterpret_cast<const float4*>(&ck[k].bias);       // bias, scale, shift, scale_l2
+            const float shl = ck[k].shift_l2;
             float y[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float v = fmaf(wr[k][3], xv[3][j], br[k]);
-                v = fmaf(wr[k][2], xv[2][j], v);
-                v = fmaf(wr[k][1], xv[1][j], v);
-                v = fmaf(wr[k][0], xv[0][j], v);
-                const bool in = full || p0 + j < P;
-                const float m = in ? v : 0.f;
-                s1[k] += m;
-                s2[k] = fmaf(m, m, s2[k]);
-                y[j] = in ? (scale ? elu_fast(fmaf(v, sc[k], sh[k])) : v) : 0.f;       // pad points are stored as zeros
+                float v = fmaf(wk.w, xv[3][j], bk.x);
+                v = fmaf(wk.z, xv[2][j], v);
+                v = fmaf(wk.y, xv[1][j], v);
+                v = fmaf(wk.x, xv[0][j], v);
+                v = j < vcnt ? v : 0.f;                                    // pad points are stored as zeros
+                s1[k] += v;
+                s2[k] = fmaf(v, v, s2[k]);
+                y[j] = v;
+            }
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = j < vcnt ? elu_l2(fmaf(y[j], bk.y, bk.z), fmaf(y[j], bk.w, shl)) : 0.f;
             }
             if (c0 + k < Cout) *reinterpret_cast<uint4*>(yT + t256(p0, c0 + k, Cout)) = pack8(y);
         }
@@ -125,22 +142,20 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------ layer 1 weight gradient
 // dW1[c][f] = sum_p dy[c][p] * x[f][p] with dy = c1[c]*dz + c2[c]*y + c3[c] formed on the fly (BatchNorm backward of
 // layer 1 fused in: its dy is never written) or dy = dz when y is null.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dzT,
                            const __nv_bfloat16* __restrict__ yT, const float* __restrict__ c1,
                            const float* __restrict__ c2, const float* __restrict__ c3, float* __restrict__ dW,
                            int64_t P, int64_t TN, int Cout) {
+    __shared__ float4 coef[8 * L1_CH_PER_WARP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 8 * L1_CH_PER_WARP) {
+        const int c = min(blockIdx.y * 8 * L1_CH_PER_WARP + (int)threadIdx.x, Cout - 1);
+        coef[threadIdx.x] = yT ? make_float4(__ldg(c1 + c), __ldg(c2 + c), __ldg(c3 + c), 0.f) : make_float4(1.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
     const int c0 = (blockIdx.y * 8 + warp) * L1_CH_PER_WARP;
     if (c0 >= Cout) return;
-    float a1[L1_CH_PER_WARP], a2[L1_CH_PER_WARP], a3[L1_CH_PER_WARP];
-#pragma unroll
-    for (int k = 0; k < L1_CH_PER_WARP; ++k) {
-        const int c = min(c0 + k, Cout - 1);
-        a1[k] = yT ? __ldg(c1 + c) : 1.f;
-        a2[k] = yT ? __ldg(c2 + c) : 0.f;
-        a3[k] = yT ? __ldg(c3 + c) : 0.f;
-    }
     float acc[L1_CH_PER_WARP][4];
 #pragma unroll
     for (int k = 0; k < L1_CH_PER_WARP; ++k)
@@ -152,18 +167,19 @@ pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __r
         if (p0 >= P) break;
         float xv[4][8];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);
-        const bool full = p0 + 8 <= P;
+        for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);     // out-of-range points read as 0: they add nothing
+        const int vcnt = p0 + 8 <= P ? 8 : (int)(P - p0);
 #pragma unroll
         for (int k = 0; k < L1_CH_PER_WARP; ++k) {
             const int64_t off = t256(p0, min(c0 + k, Cout - 1), Cout);
+            const float4 a = coef[warp * L1_CH_PER_WARP + k];
             float dz[8], yv[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(dzT + off)), dz);
             if (yT) unpack8(__ldg(reinterpret_cast<const uint4*>(yT + off)), yv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float d = yT ? fmaf(a1[k], dz[j], fmaf(a2[k], yv[j], a3[k])) : dz[j];
-                d = (full || p0 + j < P) ? d : 0.f;
+                float d = yT ? fmaf(a.x, dz[j], fmaf(a.y, yv[j], a.z)) : dz[j];
+                d = j < vcnt ? d : 0.f;
 #pragma unroll
                 for (int f = 0; f < 4; ++f) acc[k][f] = fmaf(d, xv[f][j], acc[k][f]);
             }
@@ -198,30 +214,6 @@ __device__ __forceinline__ ChunkPos chunk_pos(int u, int64_t nchunks, int C) {
     r.p0 = ((row / C) << 8) + ((i & 31) << 3);
     r.off = i << 3;
     return r;
-}
-
-__global__ void __launch_bounds__(256)
-bn_elu_apply_t_kernel(const __nv_bfloat16* __restrict__ yT, const float* __restrict__ scale,
-                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ outT, int64_t nchunks, int64_t P,
-                      int C) {
-    uint4 raw[EW_UNROLL];
-    ChunkPos cp[EW_UNROLL];
-#pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
-        cp[u] = chunk_pos(u, nchunks, C);
-        if (cp[u].ok) raw[u] = __ldg(reinterpret_cast<const uint4*>(yT + cp[u].off));
-    }
-#pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
-        if (!cp[u].ok) continue;
-        const float sc = __ldg(scale + cp[u].c), sh = __ldg(shift + cp[u].c);
-        float v[8];
-        unpack8(raw[u], v);
-        const bool full = cp[u].p0 + 8 <= P;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (full || cp[u].p0 + j < P) ? elu_fast(fmaf(v[j], sc, sh)) : 0.f;
-        *reinterpret_cast<uint4*>(outT + cp[u].off) = pack8(v);
-    }
 }
 
 // dy = c1[c]*dz + c2[c]*y + c3[c]  (BatchNorm backward), may run in place on dz
@@ -440,6 +432,7 @@ bn_elu_meanpool_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* _
     const bool straddle = lg.split < 8;
     const bool prev_straddle = __shfl_up_sync(0xffffffffu, straddle ? 1 : 0, 1) != 0 && lane > 0;
     const int64_t tile_off = tile * (int64_t)C * 256 + lane * 8;
+    const bool full_tile = ((tile + 1) << 8) <= P;                  // block-uniform: no pad points in this tile
 
     uint4 raw[MP_ROWS_PER_WARP];
 #pragma unroll
@@ -454,24 +447,47 @@ bn_elu_meanpool_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* _
         const float sc = apply ? __ldg(scale + c) : 1.f, sh = apply ? __ldg(shift + c) : 0.f;
         float y[8];
         unpack8(raw[i], y);
+        const float scl = sc * LOG2E_F, shl = sh * LOG2E_F;
         float Ts = 0.f, As = 0.f, Td = 0.f, Ad = 0.f, Tu = 0.f, Au = 0.f;
+        if (full_tile) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(y[j], sc, sh);
-            float a = z, d = 1.f;
-            if (apply) {
-                const float e = __expf(z);
-                a = z > 0.f ? z : e - 1.f;
-                d = z > 0.f ? 1.f : e;
+            for (int j = 0; j < 8; ++j) {
+                const float z = fmaf(y[j], sc, sh);
+                float a = z, d = 1.f;
+                if (apply) {
+                    const float e = ex2_fast(fmaf(y[j], scl, shl));
+                    a = z > 0.f ? z : e - 1.f;
+                    d = z > 0.f ? 1.f : e;
+                }
+                Ts += a;
+                As = fmaf(wA[j], a, As);
+                if (TRAIN) {
+                    const float wd = wA[j] * d;
+                    Td += d;
+                    Tu = fmaf(d, y[j], Tu);
+                    Ad += wd;
+                    Au = fmaf(wd, y[j], Au);
+                }
             }
-            Ts = fmaf(wT[j], a, Ts);
-            As = fmaf(wA[j], a, As);
-            if (TRAIN) {
-                const float dy = d * y[j];
-                Td = fmaf(wT[j], d, Td);
-                Ad = fmaf(wA[j], d, Ad);
-                Tu = fmaf(wT[j], dy, Tu);
-                Au = fmaf(wA[j], dy, Au);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float z = fmaf(y[j], sc, sh);
+                float a = z, d = 1.f;
+                if (apply) {
+                    const float e = ex2_fast(fmaf(y[j], scl, shl));
+                    a = z > 0.f ? z : e - 1.f;
+                    d = z > 0.f ? 1.f : e;
+                }
+                Ts = fmaf(wT[j], a, Ts);
+                As = fmaf(wA[j], a, As);
+                if (TRAIN) {
+                    const float dy = d * y[j];
+                    Td = fmaf(wT[j], d, Td);
+                    Ad = fmaf(wA[j], d, Ad);
+                    Tu = fmaf(wT[j], dy, Tu);
+                    Au = fmaf(wA[j], dy, Au);
+                }
             }
         }
         // the part of a straddling chunk that belongs to the next group joins the next lane's run
@@ -514,6 +530,43 @@ bn_elu_meanpool_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* _
     }
 }
 
+constexpr int EA_ROWS_PER_WARP = 4;
+
+// outT = ELU(scale[c]*yT + shift[c]); grid (ceil(C / 32), n_tiles): warp w streams the 512-byte rows of channels cb + w + 8*i
+__global__ void __launch_bounds__(256)
+bn_elu_apply_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* __restrict__ scale,
+                         const float* __restrict__ shift, __nv_bfloat16* __restrict__ outT, int64_t P, int C) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.y;
+    const int cb = blockIdx.x * (8 * EA_ROWS_PER_WARP) + warp;
+    const int64_t tile_off = tile * (int64_t)C * 256 + lane * 8;
+    const int64_t left = P - ((tile << 8) + (lane << 3));
+    const int vcnt = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
+    const bool full_tile = ((tile + 1) << 8) <= P;                  // block-uniform
+    uint4 raw[EA_ROWS_PER_WARP];
+#pragma unroll
+    for (int i = 0; i < EA_ROWS_PER_WARP; ++i) {
+        const int c = cb + 8 * i;
+        if (c < C) raw[i] = __ldg(reinterpret_cast<const uint4*>(yT + tile_off + (int64_t)c * 256));
+    }
+#pragma unroll
+    for (int i = 0; i < EA_ROWS_PER_WARP; ++i) {
+        const int c = cb + 8 * i;
+        if (c >= C) break;
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const float scl = sc * LOG2E_F, shl = sh * LOG2E_F;
+        float v[8];
+        unpack8(raw[i], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = elu_l2(fmaf(v[j], sc, sh), fmaf(v[j], scl, shl));
+        if (!full_tile) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = j < vcnt ? v[j] : 0.f;
+        }
+        *reinterpret_cast<uint4*>(outT + tile_off + (int64_t)c * 256) = pack8(v);
+    }
+}
+
 constexpr int PB_ROWS_PER_WARP = 4;
 
 // dy(c,p) = c1[c]*(dpool[g(p)][c]/n)*ELU'(scale*y+shift) + c2[c]*y + c3[c]; grid (ceil(C / 32), n_tiles), n >= 8
@@ -528,6 +581,10 @@ pool_bwd_apply_rows_kernel(const float* __restrict__ dpool, const __nv_bfloat16*
     const LaneGroups lg = lane_groups(tile, lane, n, P);
     const int64_t tile_off = tile * (int64_t)C * 256 + lane * 8;
     const bool has0 = lg.g0 < G, has1 = lg.split < 8 && lg.g0 + 1 < G;
+    const bool full_tile = ((tile + 1) << 8) <= P;                  // block-uniform
+    float wsel[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wsel[j] = j < lg.split ? 1.f : 0.f;
     uint4 raw[PB_ROWS_PER_WARP];
     float g0v[PB_ROWS_PER_WARP], g1v[PB_ROWS_PER_WARP];
 #pragma unroll
@@ -545,15 +602,19 @@ pool_bwd_apply_rows_kernel(const float* __restrict__ dpool, const __nv_bfloat16*
         if (c >= C) break;
         const float sc = __ldg(scale + c), sh = __ldg(shift + c);
         const float a1 = __ldg(c1 + c) * inv_n, a2 = __ldg(c2 + c), a3 = __ldg(c3 + c);
-        const float ga = a1 * g0v[i], gb = a1 * g1v[i];
+        const float scl = sc * LOG2E_F, shl = sh * LOG2E_F;
+        const float gb = a1 * g1v[i], gd = a1 * g0v[i] - gb;          // gv_j = gb + wsel_j * gd
         float y[8];
         unpack8(raw[i], y);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(y[j], sc, sh);
-            const float d = z > 0.f ? 1.f : __expf(z);
-            const float gv = j < lg.split ? ga : gb;
-            y[j] = j < lg.vcnt ? fmaf(gv, d, fmaf(a2, y[j], a3)) : 0.f;
+            const float d = elu_grad_l2(fmaf(y[j], sc, sh), fmaf(y[j], scl, shl));
+            const float gv = fmaf(wsel[j], gd, gb);
+            y[j] = fmaf(gv, d, fmaf(a2, y[j], a3));
+        }
+        if (!full_tile) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = j < lg.vcnt ? y[j] : 0.f;
         }
         *reinterpret_cast<uint4*>(dyT + tile_off + (int64_t)c * 256) = pack8(y);
     }
@@ -594,8 +655,8 @@ int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, co
 int pcaa_bn_elu_apply_t(const void* yT, const float* scale, const float* shift, void* outT, int64_t P, int C,
                         pcaa_stream stream) {
     if (P == 0 || C == 0) return PCAA_OK;
-    const int64_t nch = t256_chunks(P, C);
-    bn_elu_apply_t_kernel<<<ew_blocks(nch), 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, (__nv_bfloat16*)outT, nch, P, C);
+    dim3 grid((unsigned)ceil_div(C, 8 * EA_ROWS_PER_WARP), (unsigned)((P + 255) / 256));
+    bn_elu_apply_rows_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, (__nv_bfloat16*)outT, P, C);
     return check_launch("bn_elu_apply_t");
 }
 
