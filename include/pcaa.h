@@ -178,8 +178,9 @@ int pcaa_pack_bf16(const float* in, int64_t R, int64_t C, int64_t ld_in, void* o
 typedef enum { PCAA_EW_MUL = 0, PCAA_EW_ADD = 1, PCAA_EW_ELU = 2, PCAA_EW_ELU_GRAD = 3, PCAA_EW_ELU_GRAD2 = 4,
                PCAA_EW_ADD_ROWVEC = 5 } pcaa_ew_op;
 int pcaa_ew(int op, const float* a, const float* b, float* out, int64_t n, int ncols, pcaa_stream stream);
-/* causal dilated Conv1d as GEMM: col[(b,t), ci*3+k] = x[b, t-(2-k)*dil, ci] (0 for negative time), models.py:59-76 */
-int pcaa_tcn_im2col(const float* x, float* col, int64_t B, int T, int Cin, int dil, pcaa_stream stream);
+/* causal dilated Conv1d as GEMM: col[(b,t), ci*3+k] = x[b, t-(2-k)*dil, ci] (0 for negative time), models.py:59-76;
+ * col is fp32 or bf16 (col_dtype: the tensor-core GEMM operand) */
+int pcaa_tcn_im2col(const float* x, void* col, int col_dtype, int64_t B, int T, int Cin, int dil, pcaa_stream stream);
 int pcaa_tcn_col2im(const float* dcol, float* dx, int64_t B, int T, int Cin, int dil, pcaa_stream stream);
 /* out[g,c] = mean_i x[g,i,c] (AvgPool1d(NSTEPS), models.py:249,284) and its backward */
 int pcaa_mean_rows(const float* x, float* out, int64_t G, int n, int C, pcaa_stream stream);

@@ -47,7 +47,7 @@ SIGNATURES = {
     "pcaa_colsum_ld": [_p, _i, _l, _i, _l, _p, _p],
     "pcaa_convert": [_p, _i, _p, _i, _l, _p],
     "pcaa_pack_bf16": [_p, _l, _l, _l, _p, _l, _i, _p],
-    "pcaa_tcn_im2col": [_p, _p, _l, _i, _i, _i, _p],
+    "pcaa_tcn_im2col": [_p, _p, _i, _l, _i, _i, _i, _p],
     "pcaa_tcn_col2im": [_p, _p, _l, _i, _i, _i, _p],
     "pcaa_mean_rows": [_p, _p, _l, _i, _i, _p],
     "pcaa_mean_rows_bwd": [_p, _p, _l, _i, _i, _p],

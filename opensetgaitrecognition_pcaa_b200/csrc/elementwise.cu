@@ -368,7 +368,8 @@ __global__ void pack_bf16_kernel(const float* __restrict__ in, int64_t R, int64_
     }
 }
 
-__global__ void tcn_im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int64_t BT, int T, int Cin,
+template <typename TO>
+__global__ void tcn_im2col_kernel(const float* __restrict__ x, TO* __restrict__ col, int64_t BT, int T, int Cin,
                                   int dil) {
     int64_t total = BT * Cin * 3;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,7 +381,7 @@ __global__ void tcn_im2col_kernel(const float* __restrict__ x, float* __restrict
         int64_t bt = q / Cin;
         int t = (int)(bt % T);
         int ts = t - (2 - k) * dil;
-        col[i] = ts >= 0 ? x[(bt - t + ts) * Cin + ci] : 0.f;
+        st_from_float<TO>(col + i, ts >= 0 ? x[(bt - t + ts) * Cin + ci] : 0.f);
     }
 }
 
@@ -743,6 +744,9 @@ int pcaa_bn_bwd_apply(const void* dz, int dz_dtype, const void* y, int y_dtype, 
     else if (dz_dtype == PCAA_F32 && y_dtype == PCAA_F32 && dy_dtype == PCAA_F32)
         bn_bwd_apply_kernel<float, float, float><<<grid, 256, 0, ST(stream)>>>((const float*)dz, (const float*)y, c1, c2, c3,
                                                                             (float*)dy, nchunks, ncg, hoist);
+    else if (dz_dtype == PCAA_F32 && y_dtype == PCAA_F32 && dy_dtype == PCAA_BF16)
+        bn_bwd_apply_kernel<float, float, __nv_bfloat16><<<grid, 256, 0, ST(stream)>>>((const float*)dz, (const float*)y, c1, c2, c3,
+                                                                                    (__nv_bfloat16*)dy, nchunks, ncg, hoist);
     else {
         set_error("bn_bwd_apply: unsupported dtype combination");
         return PCAA_ERR_UNSUPPORTED;
@@ -793,9 +797,13 @@ int pcaa_pack_bf16(const float* in, int64_t R, int64_t C, int64_t ld_in, void* o
     return check_launch("pack_bf16");
 }
 
-int pcaa_tcn_im2col(const float* x, float* col, int64_t B, int T, int Cin, int dil, pcaa_stream stream) {
+int pcaa_tcn_im2col(const float* x, void* col, int col_dtype, int64_t B, int T, int Cin, int dil, pcaa_stream stream) {
     int64_t total = B * T * Cin * 3;
-    tcn_im2col_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, col, B * T, T, Cin, dil);
+    if (total == 0) return PCAA_OK;
+    if (col_dtype == PCAA_BF16)
+        tcn_im2col_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)col, B * T, T, Cin, dil);
+    else
+        tcn_im2col_kernel<float><<<ew_grid(total), 256, 0, ST(stream)>>>(x, (float*)col, B * T, T, Cin, dil);
     return check_launch("tcn_im2col");
 }
 

@@ -142,40 +142,49 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------ layer 1 weight gradient
 // dW1[c][f] = sum_p dy[c][p] * x[f][p] with dy = c1[c]*dz + c2[c]*y + c3[c] formed on the fly (BatchNorm backward of
 // layer 1 fused in: its dy is never written) or dy = dz when y is null.
+constexpr int L1W_CH_PER_WARP = 4;
+
 __global__ void __launch_bounds__(256, 2)
 pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dzT,
                            const __nv_bfloat16* __restrict__ yT, const float* __restrict__ c1,
                            const float* __restrict__ c2, const float* __restrict__ c3, float* __restrict__ dW,
                            int64_t P, int64_t TN, int Cout) {
-    __shared__ float4 coef[8 * L1_CH_PER_WARP];
+    __shared__ float4 coef[8 * L1W_CH_PER_WARP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 8 * L1_CH_PER_WARP) {
-        const int c = min(blockIdx.y * 8 * L1_CH_PER_WARP + (int)threadIdx.x, Cout - 1);
+    if (threadIdx.x < 8 * L1W_CH_PER_WARP) {
+        const int c = min(blockIdx.y * 8 * L1W_CH_PER_WARP + (int)threadIdx.x, Cout - 1);
         coef[threadIdx.x] = yT ? make_float4(__ldg(c1 + c), __ldg(c2 + c), __ldg(c3 + c), 0.f) : make_float4(1.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    const int c0 = (blockIdx.y * 8 + warp) * L1_CH_PER_WARP;
+    const int c0 = (blockIdx.y * 8 + warp) * L1W_CH_PER_WARP;
     if (c0 >= Cout) return;
-    float acc[L1_CH_PER_WARP][4];
+    float acc[L1W_CH_PER_WARP][4];
 #pragma unroll
-    for (int k = 0; k < L1_CH_PER_WARP; ++k)
+    for (int k = 0; k < L1W_CH_PER_WARP; ++k)
 #pragma unroll
         for (int f = 0; f < 4; ++f) acc[k][f] = 0.f;
     const int64_t tile0 = (int64_t)blockIdx.x * L1_TILE_POINTS;
     for (int ch = 0; ch < L1_TILE_POINTS / 256; ++ch) {
         const int64_t p0 = tile0 + ch * 256 + lane * 8;
         if (p0 >= P) break;
+        // every global load of this step is issued before the first use (the kernel is latency bound)
+        uint4 rz[L1W_CH_PER_WARP], ry[L1W_CH_PER_WARP];
+#pragma unroll
+        for (int k = 0; k < L1W_CH_PER_WARP; ++k) {
+            const int64_t off = t256(p0, min(c0 + k, Cout - 1), Cout);
+            rz[k] = __ldg(reinterpret_cast<const uint4*>(dzT + off));
+            if (yT) ry[k] = __ldg(reinterpret_cast<const uint4*>(yT + off));
+        }
         float xv[4][8];
 #pragma unroll
         for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);     // out-of-range points read as 0: they add nothing
         const int vcnt = p0 + 8 <= P ? 8 : (int)(P - p0);
 #pragma unroll
-        for (int k = 0; k < L1_CH_PER_WARP; ++k) {
-            const int64_t off = t256(p0, min(c0 + k, Cout - 1), Cout);
-            const float4 a = coef[warp * L1_CH_PER_WARP + k];
+        for (int k = 0; k < L1W_CH_PER_WARP; ++k) {
+            const float4 a = coef[warp * L1W_CH_PER_WARP + k];
             float dz[8], yv[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(dzT + off)), dz);
-            if (yT) unpack8(__ldg(reinterpret_cast<const uint4*>(yT + off)), yv);
+            unpack8(rz[k], dz);
+            if (yT) unpack8(ry[k], yv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float d = yT ? fmaf(a.x, dz[j], fmaf(a.y, yv[j], a.z)) : dz[j];
@@ -186,7 +195,7 @@ pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __r
         }
     }
 #pragma unroll
-    for (int k = 0; k < L1_CH_PER_WARP; ++k)
+    for (int k = 0; k < L1W_CH_PER_WARP; ++k)
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
             const float t = warp_sum(acc[k][f]);
@@ -647,7 +656,7 @@ int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, co
     if (B == 0) return PCAA_OK;
     const int64_t P = B * TN;
     PCAA_REQUIRE(yT == nullptr || (c1 && c2 && c3), PCAA_ERR_SHAPE, "pointnet_l1_wgrad_t: y needs the BatchNorm-backward coefficients");
-    dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
+    dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1W_CH_PER_WARP));
     pointnet_l1_wgrad_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, (const __nv_bfloat16*)dzT, (const __nv_bfloat16*)yT, c1, c2, c3, dW, P, TN, Cout);
     return check_launch("pointnet_l1_wgrad_t");
 }

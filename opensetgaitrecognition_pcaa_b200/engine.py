@@ -136,17 +136,20 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
 
 
 # ====================================================================================================== TCN
-def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block."):
-    """h [B, T, 1024] fp32 -> [B, T, 512]; causal dilated conv (im2col GEMM) + BatchNorm1d + ELU, six times."""
+def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block.", wb16: Optional[dict] = None):
+    """h [B, T, 1024] fp32 -> [B, T, 512]; causal dilated conv (im2col + tcgen05 GEMM, bf16 operands, fp32 accumulate /
+    output) + BatchNorm1d + ELU, six times.  ``wb16`` optionally maps the layer number to a ready bf16 copy of the
+    [Cout, Cin*3] weight (the trainer's Adam-maintained shadow)."""
     B, T, _ = h.shape
     R = B * T
-    sv = {"B": B, "T": T, "col": [], "y": [], "coef": [], "cin": []}
+    sv = {"B": B, "T": T, "col": [], "y": [], "coef": [], "cin": [], "wb": []}
     for l in range(1, 7):
         k = f"{pre}dtc{l}."
         W = P[k + "conv1d.weight"]
         Cout, Cin, _ = W.shape
-        col = ops.tcn_im2col(h, DTC_DILATIONS[l - 1])
-        y = ops.gemm(col, W.view(Cout, Cin * 3), trans_b=True, bias=P[k + "conv1d.bias"])
+        wb = wb16[l] if wb16 is not None else ops.pack_bf16(W.view(Cout, Cin * 3))
+        col = ops.tcn_im2col(h, DTC_DILATIONS[l - 1], torch.bfloat16)
+        y = ops.gemm_tc(col, wb, TC_PLAIN, R, Cout, Cin * 3, bias=P[k + "conv1d.bias"], out_dtype=torch.float32)
         if training:
             st = ops.colstats(y)
             coef = ops.bn_finalize(st, R, P[k + "batch_norm.weight"], P[k + "batch_norm.bias"],
@@ -155,7 +158,7 @@ def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block
             coef = ops.bn_eval_coeffs(P[k + "batch_norm.weight"], P[k + "batch_norm.bias"],
                                       P[k + "batch_norm.running_mean"], P[k + "batch_norm.running_var"], BN_EPS)
         a = ops.bn_elu_apply(y, coef[0], coef[1])
-        sv["col"].append(col), sv["y"].append(y), sv["coef"].append(coef), sv["cin"].append(Cin)
+        sv["col"].append(col), sv["y"].append(y), sv["coef"].append(coef), sv["cin"].append(Cin), sv["wb"].append(wb)
         h = a.view(B, T, Cout)
     return h, sv
 
@@ -170,18 +173,19 @@ def tcn_backward(dout: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = N
         k = f"{pre}dtc{l}."
         W = P[k + "conv1d.weight"]
         Cout, Cin, _ = W.shape
-        y, coef, col = sv["y"][l - 1], sv["coef"][l - 1], sv["col"][l - 1]
+        y, coef, col, wb = sv["y"][l - 1], sv["coef"][l - 1], sv["col"][l - 1], sv["wb"][l - 1]
         dz, st2 = ops.elu_bwd_colstats(d, y, coef)
         c, dgam, dbet = ops.bn_bwd_finalize(st2, R, coef, _out(gradbuf, k + "batch_norm.weight"),
                                             _out(gradbuf, k + "batch_norm.bias"))
         G[k + "batch_norm.weight"], G[k + "batch_norm.bias"] = dgam, dbet
-        dy = ops.bn_bwd_apply(dz, y, c, out=dz)
-        o = _out(gradbuf, k + "conv1d.weight")
-        dW = ops.gemm(dy, col, trans_a=True, out=None if o is None else o.view(Cout, Cin * 3))
-        G[k + "conv1d.weight"] = dW.view(W.shape) if o is None else o
+        dy = ops.bn_bwd_apply(dz, y, c, out_dtype=torch.bfloat16)
+        # dW [Cout, Cin*3] += dy^T col (k = the B*T rows, split over the SMs), dcol = dy W
+        dW = _zeros_like_param(gradbuf, k + "conv1d.weight", W)
+        ops.gemm_tc(dy, col, TC_WGRAD_ACC, Cout, Cin * 3, R, a_mn=OP_MN, b_mn=OP_MN, out=dW.view(Cout, Cin * 3))
+        G[k + "conv1d.weight"] = dW
         # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero (sum_rows dy = 0)
         G[k + "conv1d.bias"] = _zeros_like_param(gradbuf, k + "conv1d.bias", P[k + "conv1d.bias"])
-        dcol = ops.gemm(dy, W.view(Cout, Cin * 3))
+        dcol = ops.gemm_tc(dy, wb, TC_PLAIN, R, Cin * 3, Cout, b_mn=OP_MN, out_dtype=torch.float32)
         d = ops.tcn_col2im(dcol, B, T, Cin, DTC_DILATIONS[l - 1]).view(R, Cin)
     return d.view(B, T, -1), G
 
@@ -235,10 +239,11 @@ def heads_backward(dlogits: Optional[torch.Tensor], dfv_ext: Optional[torch.Tens
 
 
 # ====================================================================================================== encoder
-def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_head: bool, wb16: Optional[dict] = None):
+def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_head: bool, wb16: Optional[dict] = None,
+                    tcn_wb16: Optional[dict] = None):
     B, F, T, N = x.shape
     pooled, sv_p = pointnet_forward(x, P, training, wb16=wb16)
-    h6, sv_t = tcn_forward(pooled.view(B, T, -1), P, training)
+    h6, sv_t = tcn_forward(pooled.view(B, T, -1), P, training, wb16=tcn_wb16)
     logits, fv, sv_h = heads_forward(h6, P, use_projection_head)
     return logits, fv, (sv_p, sv_t, sv_h)
 

@@ -120,10 +120,10 @@ def bn_bwd_finalize(stats2, R, coef, dgamma: Optional[torch.Tensor] = None, dbet
     return c, dgamma, dbeta
 
 
-def bn_bwd_apply(dz, y, c, out: Optional[torch.Tensor] = None):
+def bn_bwd_apply(dz, y, c, out: Optional[torch.Tensor] = None, out_dtype=None):
     R, Cc = y.shape
     if out is None:
-        out = torch.empty_like(dz)
+        out = torch.empty_like(dz) if out_dtype is None else torch.empty(dz.shape, device=dz.device, dtype=out_dtype)
     call("pcaa_bn_bwd_apply", _p(dz), _DT[dz.dtype], _p(y), _DT[y.dtype], _p(c[0]), _p(c[1]), _p(c[2]), _p(out),
          _DT[out.dtype], R, Cc, _s())
     return out
@@ -166,11 +166,11 @@ def pack_bf16(w: torch.Tensor, ld_out: Optional[int] = None, transpose=False, ou
     return out
 
 
-def tcn_im2col(x, dil: int):
+def tcn_im2col(x, dil: int, dtype=torch.float32):
     _chk(x, torch.float32)
     B, T, Cin = x.shape
-    col = torch.empty((B * T, Cin * 3), device=x.device, dtype=torch.float32)
-    call("pcaa_tcn_im2col", _p(x), _p(col), B, T, Cin, dil, _s())
+    col = torch.empty((B * T, Cin * 3), device=x.device, dtype=dtype)
+    call("pcaa_tcn_im2col", _p(x), _p(col), _DT[dtype], B, T, Cin, dil, _s())
     return col
 
 

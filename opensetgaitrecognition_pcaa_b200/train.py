@@ -111,6 +111,10 @@ class PCAATrainer:
         for l in (2, 3, 4):
             W = self.P_E[f"pc_block.pointnet{l}.module.0.weight"]
             self._enc_wb16[l] = self.G.view(self.G.shadow, f"E.pc_block.pointnet{l}.module.0.weight").view(W.shape[0], W.shape[1])
+        self._tcn_wb16 = {}
+        for l in range(1, 7):
+            W = self.P_E[f"tc_block.dtc{l}.conv1d.weight"]
+            self._tcn_wb16[l] = self.G.view(self.G.shadow, f"E.tc_block.dtc{l}.conv1d.weight").view(W.shape[0], W.shape[1] * 3)
         self._dec_shadow = {}
         for l in range(1, 6):
             W = self.P_G[f"dense{l}.weight"]
@@ -135,7 +139,8 @@ class PCAATrainer:
         gscale = 1.0 / self.world
         self.enc.train(), self.dec.train(), self.dis.train()
         # ---- encoder forward (train-mode BatchNorm; running statistics updated in place)
-        logits, fv, saved = engine.encoder_forward(pcs, self.P_E, True, self.enc.use_projection_head, self._enc_wb16)
+        logits, fv, saved = engine.encoder_forward(pcs, self.P_E, True, self.enc.use_projection_head, self._enc_wb16,
+                                                   self._tcn_wb16)
         for t in self._nbt:
             t.add_(1)
         # ---- critic step (PCAA_ablation.py:900-980), one fused kernel + Adam
@@ -178,7 +183,8 @@ class PCAATrainer:
     def evaluate(self, pcs: torch.Tensor, gt: torch.Tensor):
         """Validation pass of PCAA_ablation.py:1046-1064: eval-mode encoder, decoder, Chamfer, CE, argmax."""
         self.enc.eval(), self.dec.eval()
-        logits, fv, _ = engine.encoder_forward(pcs, self.P_E, False, self.enc.use_projection_head, self._enc_wb16)
+        logits, fv, _ = engine.encoder_forward(pcs, self.P_E, False, self.enc.use_projection_head, self._enc_wb16,
+                                              self._tcn_wb16)
         h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
         rec, _ = engine.decoder_forward_tc(h0, self.P_G, self._decoder_weights_bf16())
         fl, _, _ = ops.chamfer_fwd(rec.view(pcs.shape), pcs, want_idx=False)
