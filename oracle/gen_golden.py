@@ -448,6 +448,73 @@ def scoring_case():
     assert pins["lik_rel"] < 1e-9 and pins["thr"] == 0 and all(pins[f"vote_mismatch_k{k}"] == 0 for k in (1, 2, 4, 6))
 
 
+def procedure_case():
+    """The reference's UNMODIFIED inference_PCAA.naive_sequential_procedure (phase-1 scoring, ROC threshold, phase-2
+    k-window vote with its skip rules) run on a stand-in dataset whose "point clouds" carry a pre-computed embedding
+    and logits, and a stand-in encoder that unpacks them: pins oracle.naive_sequential_procedure."""
+    import contextlib
+    import io
+    import tempfile
+    import inference_PCAA as ref_inf
+    rng = np.random.default_rng(23)
+    C, D = 4, 32
+    means = O.sample_distant_points(D, C, 10, 10).float()
+    # TEST split: 4 known subjects x 3 tracks of unequal length (so windows of k straddle label changes); UNSEEN: 6 subjects
+    def make(subjects, known):
+        emb, logits, labels = [], [], []
+        for sidx, s in enumerate(subjects):
+            for _ in range(3):
+                n = int(rng.integers(7, 15))
+                if known:
+                    e = means[sidx].numpy() + rng.normal(0, 1.0, (n, D)) * rng.uniform(0.7, 1.5)
+                    lg = rng.normal(0, 1, (n, C)); lg[:, sidx] += 2.0
+                else:
+                    e = rng.normal(0, 3.5, (n, D)) + 0.6 * means[int(rng.integers(0, C))].numpy()
+                    lg = rng.normal(0, 1, (n, C))
+                emb.append(e.astype(np.float32)); logits.append(lg.astype(np.float32)); labels += [s] * n
+        return np.concatenate(emb), np.concatenate(logits), np.array(labels, dtype=np.int64)
+    t_emb, t_log, t_lab = make([0, 1, 2, 3], True)
+    u_emb, u_log, u_lab = make([11, 12, 13, 14, 15, 16], False)
+
+    class FakeDataset(torch.utils.data.Dataset):
+        def __init__(self, split, scenarios=None, subsample_factor=1.0, sequential=True):
+            e, l, y = (t_emb, t_log, t_lab) if split == ref_inf.SPLIT.TEST else (u_emb, u_log, u_lab)
+            self.x = torch.from_numpy(np.concatenate([e, l], axis=1)); self.y = torch.from_numpy(y)
+        def __len__(self):
+            return len(self.y)
+        def __getitem__(self, i):
+            if i >= len(self.y):
+                raise IndexError
+            return self.x[i], self.y[i]
+
+    class FakeEncoder(torch.nn.Module):
+        def forward(self, x):
+            return x[:, D:], x[:, :D]
+
+    g = dict(means=means.numpy(), t_emb=t_emb, t_pred=t_log.argmax(1), t_lab=t_lab, u_emb=u_emb, u_pred=u_log.argmax(1), u_lab=u_lab)
+    saved = (ref_inf.MSRadarDataset, ref_inf.plot_confusion_matrix_cgaae, ref_inf.constants.DEVICE)
+    ref_inf.MSRadarDataset = FakeDataset
+    ref_inf.plot_confusion_matrix_cgaae = lambda k, f, n, p_, l, t: (p_, l.astype(int))
+    ref_inf.constants.DEVICE = "cpu"
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            for k in (1, 2, 4, 6):
+                with contextlib.redirect_stdout(io.StringIO()):          # the reference prints every window
+                    log, preds, labels = ref_inf.naive_sequential_procedure(k, FakeEncoder(), means, tmp, tmp, seed=0,
+                                                                            unseen_valid_ratio=0.2)
+                o = O.naive_sequential_procedure(k, t_emb, g["t_pred"], t_lab, u_emb, g["u_pred"], u_lab, means.numpy(), 0, 0.2)
+                assert np.array_equal(o["preds"], preds) and np.array_equal(o["labels"], labels), k
+                for m in ("accuracy", "f1_micro", "f1_macro", "f1_weighted"):
+                    assert abs(o["metrics"][m] - log[m]) < 1e-12, (k, m, o["metrics"][m], log[m])
+                g[f"preds_k{k}"], g[f"labels_k{k}"] = np.asarray(preds), np.asarray(labels)
+                g[f"metrics_k{k}"] = np.array([log[m] for m in ("accuracy", "f1_micro", "f1_macro", "f1_weighted")])
+                g["threshold"] = np.float64(o["threshold"])
+                print(f"[procedure] k={k}: {len(preds)} windows, accuracy {log['accuracy']:.3f}, oracle == reference")
+    finally:
+        ref_inf.MSRadarDataset, ref_inf.plot_confusion_matrix_cgaae, ref_inf.constants.DEVICE = saved
+    np.savez_compressed(os.path.join(GOLD, "procedure.npz"), **g)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -457,6 +524,7 @@ if __name__ == "__main__":
     step_case(constants, models, utils_mod, "n50_c2_b4", 4, 50, 2, seed=0)
     step_case(constants, models, utils_mod, "n150_c4_b2", 2, 150, 4, seed=2, nsteps=1)
     scoring_case()
+    procedure_case()
     w, frac = trainer_pin(constants, models, utils_mod)
     with open(os.path.join(GOLD, "PIN.txt"), "w") as f:
         f.write("oracle pinned against the reference run in the build container (oracle/gen_golden.py)\n"

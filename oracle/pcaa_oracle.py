@@ -406,6 +406,69 @@ def openset_vote(likelihoods: np.ndarray, preds: np.ndarray, threshold: float, k
     return out
 
 
+def f1_scores(labels: np.ndarray, preds: np.ndarray) -> Dict[str, float]:
+    """accuracy and micro / macro / weighted F1 as sklearn.metrics.f1_score computes them for single-label
+    multi-class input (classes = union of labels and preds; zero_division -> 0).  inference_PCAA.py:326-332."""
+    labels, preds = np.asarray(labels).astype(np.int64), np.asarray(preds).astype(np.int64)
+    classes = np.unique(np.concatenate([labels, preds]))
+    f1, support = [], []
+    for c in classes:
+        tp = float(np.sum((preds == c) & (labels == c)))
+        fp = float(np.sum((preds == c) & (labels != c)))
+        fn = float(np.sum((preds != c) & (labels == c)))
+        f1.append(0.0 if 2 * tp + fp + fn == 0 else 2 * tp / (2 * tp + fp + fn))
+        support.append(float(np.sum(labels == c)))
+    f1, support = np.array(f1), np.array(support)
+    acc = float(np.mean(labels == preds))
+    return {"accuracy": acc, "f1_micro": acc, "f1_macro": float(f1.mean()),
+            "f1_weighted": float((f1 * support).sum() / support.sum())}
+
+
+def naive_sequential_procedure(k: int, test_emb, test_pred, test_labels, unseen_emb, unseen_pred, unseen_labels, means,
+                               seed: int = 0, unseen_valid_ratio: float = 0.2):
+    """inference_PCAA.py:117-347 restated on per-crop embeddings / class predictions (the eval-mode encoder gives the
+    same embedding for a crop whether it is encoded alone (phase 1) or inside a batch of k (phase 2)).
+
+    test_* : the TEST split in `sequential=True` order; unseen_* : the UNSEEN split (labels = unseen subject ids).
+    Returns dict(threshold, preds, labels, val_subjects, metrics)."""
+    rng = np.random.default_rng(seed)                                             # :127
+    test_labels, unseen_labels = np.asarray(test_labels), np.asarray(unseen_labels)
+    subj = np.unique(unseen_labels)                                               # :178
+    val_subj = rng.choice(subj, size=np.ceil(unseen_valid_ratio * len(subj)).astype(int), replace=False)   # :181-182
+    is_val = np.isin(unseen_labels, val_subj)                                     # :184-187
+    lik_test = joint_likelihood(test_emb, means)                                  # :195-202
+    lik_unseen = joint_likelihood(unseen_emb, means)                              # :204-217
+    scores = np.concatenate([lik_unseen[is_val], lik_test])                       # :225-228
+    det = np.concatenate([np.zeros(int(is_val.sum())), np.ones(len(lik_test))])
+    thr = roc_youden_threshold(det, scores)                                       # :230-231
+    n_labels = len(np.unique(test_labels))                                        # :237
+    preds, labels = [], []
+    test_pred, unseen_pred = np.asarray(test_pred), np.asarray(unseen_pred)
+    for w in range(len(test_labels) // k):                                        # :241, DataLoader(batch_size=k, drop_last=True)
+        sl = slice(w * k, (w + 1) * k)
+        if len(np.unique(test_labels[sl])) != 1:                                  # :243-244
+            continue
+        labels.append(int(test_labels[sl][0]))
+        if np.sum(lik_test[sl] > thr) > k / 2:                                    # :262-263
+            preds.append(int(np.argmax(np.bincount(test_pred[sl]))))              # :265-266
+        else:
+            preds.append(n_labels)                                                # :270
+    for w in range(len(unseen_labels) // k):                                      # :276
+        sl = slice(w * k, (w + 1) * k)
+        if len(np.unique(unseen_labels[sl])) != 1:                                # :279-280
+            continue
+        if unseen_labels[sl][0] in val_subj:                                      # :284
+            continue
+        labels.append(n_labels)
+        if np.sum(lik_unseen[sl] > thr) > k / 2:
+            preds.append(int(np.argmax(np.bincount(unseen_pred[sl]))))
+        else:
+            preds.append(n_labels)
+    preds, labels = np.array(preds, dtype=np.int64), np.array(labels, dtype=np.int64)
+    return {"threshold": thr, "preds": preds, "labels": labels, "val_subjects": np.sort(val_subj),
+            "metrics": f1_scores(labels, preds)}
+
+
 # --------------------------------------------------------------------------- #
 # deterministic parameters / inputs shared by the golden generator and the tests
 # --------------------------------------------------------------------------- #

@@ -185,3 +185,30 @@ def test_sample_distant_points_matches_oracle():
         b = O.sample_distant_points(32, C, 10, 10)
         assert a.dtype == torch.float64 and torch.equal(a, b)
         assert torch.allclose(a.norm(dim=1), torch.full((C,), 10.0, dtype=torch.float64))
+
+
+def test_inference_host_logic_matches_sklearn():
+    """The host-side pieces of the open-set procedure (ROC / Youden threshold, F1 metrics, log-domain threshold) against
+    sklearn, incl. tied scores and scores that underflowed to exactly 0.0."""
+    from sklearn.metrics import f1_score, roc_curve
+    from opensetgaitrecognition_pcaa_b200 import inference as I
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        n = int(rng.integers(5, 200))
+        labels = (rng.random(n) < 0.6).astype(np.float64)
+        labels[0], labels[1] = 0, 1
+        scores = np.exp(rng.normal(-40, 25, n))
+        if trial % 3 == 0:
+            scores[rng.random(n) < 0.3] = 0.0                  # underflowed likelihoods: all tied at 0
+        if trial % 4 == 0:
+            scores = np.round(scores, 3)                       # more ties
+        fpr, tpr, thr = roc_curve(labels, scores)
+        assert I.roc_youden_threshold(labels, scores) == thr[np.argmax(tpr - fpr)]
+        y = rng.integers(0, 5, n)
+        p = np.where(rng.random(n) < 0.7, y, rng.integers(0, 6, n))
+        m = I.f1_scores(y, p)
+        for avg in ("micro", "macro", "weighted"):
+            assert abs(m[f"f1_{avg}"] - f1_score(y, p, average=avg)) < 1e-12
+    # `pdf > thr` in float64 <=> `log pdf > log_threshold(thr)`
+    assert I.log_threshold(0.0) == I.LOG_MIN_POSITIVE and np.exp(I.LOG_MIN_POSITIVE - 1e-9) == 0.0 < np.exp(I.LOG_MIN_POSITIVE + 0.7)
+    assert I.log_threshold(np.inf) == np.inf and abs(I.log_threshold(1e-30) - np.log(1e-30)) < 1e-12

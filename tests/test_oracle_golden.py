@@ -188,3 +188,16 @@ def test_chamfer_matches_expanded_form_and_ties():
     P = ((x[:, :, :, None, :] - y[:, :, None, :, :]) ** 2).sum(-1)
     want = (P.min(2).values.sum(-1) + P.min(3).values.sum(-1)).mean()
     assert abs(float(loss) - float(want)) < 1e-4
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 6])
+def test_procedure_oracle_vs_reference_golden(golden_dir, k):
+    """oracle.naive_sequential_procedure == the reference's unmodified inference_PCAA.naive_sequential_procedure run on a
+    stand-in dataset / encoder (oracle/gen_golden.py::procedure_case): window skip rules, validation-subject draw,
+    ROC threshold, vote, label conventions and metrics."""
+    g = np.load(os.path.join(golden_dir, "procedure.npz"))
+    o = O.naive_sequential_procedure(k, g["t_emb"], g["t_pred"], g["t_lab"], g["u_emb"], g["u_pred"], g["u_lab"], g["means"], 0, 0.2)
+    assert np.array_equal(o["preds"], g[f"preds_k{k}"]) and np.array_equal(o["labels"], g[f"labels_k{k}"])
+    m = o["metrics"]
+    assert np.allclose([m["accuracy"], m["f1_micro"], m["f1_macro"], m["f1_weighted"]], g[f"metrics_k{k}"], atol=1e-12)
+    assert o["threshold"] == float(g["threshold"])
