@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 
 NMAX, NCLS = 150, 4
 METRIC, UNIT = "pcaa_train_samples_per_sec", "samples/s"
+INFER_METRIC, INFER_UNIT = "pcaa_openset_inference_seq_per_sec", "seq/s"
+FLOP_PER_POINT_FWD = 2 * (512 * 512 + 512 * 1024 + 1024 * 1024)          # PointNet layers 2-4, forward only
 # algorithmic tensor-core work of one train step, per sample (SURVEY.md 8d / DESIGN.md): PointNet layers 2-4,
 # forward + data gradient + weight gradient = 3 x 2 x (512*512 + 512*1024 + 1024*1024) MAC-FLOPs per point,
 # minus the layer-2 data gradient... (layer 2 HAS a data gradient towards layer 1's BatchNorm) -> 3 GEMMs per layer.
@@ -40,6 +42,19 @@ def peaks():
             d = json.load(f)
         return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(kind: str, batch: int, nmax: int):
+    """DRAM bytes per launch of the dominant kernel family from the committed `ncu --set full` capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum averaged over the PointNet GEMM launches of one
+    step at the profiled batch); None when no capture exists for this configuration."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    e = d.get(f"{kind}_B{batch}_N{nmax}")
+    return None if e is None else e.get("bytes_per_launch")
 
 
 class ClockSampler:
@@ -90,7 +105,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference / CPU arm
-def cpu_step_rate(batch: int, steps: int, warmup: int, threads: int):
+def cpu_step_rate(batch: int, steps: int, warmup: int, threads: int, NMAX: int = NMAX):
     """The reference's algorithm on the host cores (oracle port of PCAA_ablation.py:882-1021), fp32, `threads` threads."""
     from oracle import pcaa_oracle as O
     torch.set_num_threads(threads)
@@ -117,8 +132,19 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    NMAX = args.nmax
+    if args.workload == "infer":
+        cb = cpu_infer_rate(NMAX, args.k)
+        print(json.dumps({
+            "impl": "reference", "metric": INFER_METRIC, "value": cb["value"], "unit": INFER_UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"pcaa_openset_inference_N{NMAX}_C{NCLS}_k{args.k}",
+                       "note": "reference algorithm (oracle port of inference_PCAA.py:239-271) on the host CPU cores"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": INFER_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     b = 32
-    rate, dt = cpu_step_rate(b, max(1, min(args.steps, 3)), 1, threads)
+    rate, dt = cpu_step_rate(b, max(1, min(args.steps, 3)), 1, threads, NMAX)
     sample = f"variant-4 train step, batch {b}, N={NMAX}, C={NCLS}, fp32, 1 warm-up + {max(1, min(args.steps, 3))} timed steps"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -133,6 +159,130 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- sm_100a arm
+def run_infer(args, world, rank, local, dev):
+    """Config 5 of BASELINE.json: batch-sharded open-set inference, no collective.  One step = one batch of crops:
+    eval-mode encoder (BatchNorm folded into the GEMM epilogues), float64 log-likelihood, k-window vote."""
+    from opensetgaitrecognition_pcaa_b200 import _lib, inference, models, ops, synth, utils
+    B, nmax, k = args.batch, args.nmax, args.k
+    B = (B // k) * k
+    torch.manual_seed(0)
+    enc = models.CGEncoder(n_out_labels=NCLS, use_projection_head=True, nmax_points=nmax).to(dev).float().eval()
+    means = utils.sample_distant_points(32, NCLS, 10, 10).float().to(dev)
+    nb = 3
+    host = [synth.synth_batch(B, nmax, NCLS, seed=4321 + 17 * rank + i)[0].pin_memory() for i in range(nb)]
+    devb = [h.to(dev) for h in host]
+    lthr = -60.0
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    tc_events = []
+    orig_tc = ops.gemm_tc
+    record = {"on": False}
+
+    def timed_gemm_tc(a, b, mode, M, N, K, **kw):
+        if not record["on"] or mode != _lib.TC_T_AFFINE_ELU:
+            return orig_tc(a, b, mode, M, N, K, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_tc(a, b, mode, M, N, K, **kw)
+        e1.record()
+        tc_events.append((e0, e1, 2.0 * M * N * K))
+        return r
+
+    ops.gemm_tc = timed_gemm_tc
+    for i in range(args.warmup):
+        inference.sharded_stream_inference(enc, means, devb[i % nb], k, lthr, NCLS, encode_batch=B)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    calls0 = _lib.CALLS
+    record["on"] = True
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        ll, votes, pred = inference.sharded_stream_inference(enc, means, devb[i % nb], k, lthr, NCLS, encode_batch=B)
+    t1.record()
+    barrier()
+    record["on"] = False
+    launches = _lib.CALLS - calls0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = t0.elapsed_time(t1)
+    tc_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in tc_events)
+    tc_flops = sum(f for _, _, f in tc_events)
+    # end to end: pinned host crops -> H2D -> encode + score + vote -> D2H of the window labels
+    votes_host = torch.empty(B // k, dtype=torch.int32).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        x = host[i % nb].to(dev, non_blocking=True)
+        ll, votes, pred = inference.sharded_stream_inference(enc, means, x, k, lthr, NCLS, encode_batch=B)
+        votes_host.copy_(votes, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    peak_tf, peak_hbm, peak_src = peaks()
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    line = {
+        "metric": INFER_METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": INFER_UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"pcaa_openset_inference_N{nmax}_C{NCLS}_k{k}", "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world} (batch-sharded stream, no collective)",
+                   "l2": "3 rotating input batches; per-step activations exceed the 126 MB L2"},
+        "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": INFER_UNIT, "h2d_bytes_per_step": host[0].numel() * 4,
+                "d2h_bytes_per_step": votes_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("infer", B, nmax),
+                     "kernel": "gemm_tc_kernel (tcgen05 PointNet forward GEMMs, BatchNorm + ELU epilogue)",
+                     "launches_timed": len(tc_events), "share_of_step": tc_ms / ms if ms else None, "peak_source": peak_src,
+                     "whole_step_tensor_frac": (world * B * args.steps * 30 * nmax * FLOP_PER_POINT_FWD) / (ms * 1e-3) / 1e12 / (peak_tf * world)},
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_infer_rate(nmax, k)
+    print(json.dumps(line))
+
+
+def cpu_infer_rate(nmax: int, k: int, n: int = 48):
+    """The reference's inference arithmetic on the host cores (oracle port): eval-mode encoder forward in batches of k
+    plus the float64 mixture likelihood and the vote, as inference_PCAA.py:239-271 does per window."""
+    from oracle import pcaa_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    p = O.det_params(NCLS, nmax, seed=0)
+    means = O.sample_distant_points(32, NCLS, 10, 10).float().numpy()
+    pcs, _ = O.synth_batch(n, nmax, NCLS, seed=99)
+    n = (n // k) * k
+
+    def run():
+        out = []
+        with torch.no_grad():
+            for w in range(n // k):
+                logits, fv = O.encoder_forward(p, pcs[w * k:(w + 1) * k], False, True)
+                lik = O.joint_likelihood(fv.numpy(), means)
+                out.append(O.openset_vote(lik, logits.argmax(1).numpy(), 1e-30, k, NCLS))
+        return out
+    run()
+    t0 = time.perf_counter()
+    run()
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": INFER_UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle port: eval encoder forward in windows of {k} + float64 likelihood + vote, {n} crops, N={nmax} ({dt:.2f} s)"}
+
+
 def run_b200(args):
     from opensetgaitrecognition_pcaa_b200 import _lib, ops, synth
     from opensetgaitrecognition_pcaa_b200.train import build_variant4
@@ -146,6 +296,9 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=dev)
     B = args.batch
+    NMAX = args.nmax
+    if args.workload == "infer":
+        return run_infer(args, world, rank, local, dev)
     trainer = build_variant4(NCLS, NMAX, seed=0, device=dev)
     if world > 1:
         # identical replicas: broadcast rank 0's initial weights (flat buffers)
@@ -253,7 +406,7 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                     "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("train", B, NMAX),
                      "kernel": "gemm_tc_kernel (tcgen05 PointNet fwd/dgrad/wgrad GEMMs)",
                      "launches_timed": len(tc_events), "share_of_step": tc_ms / ms if ms else None, "peak_source": peak_src,
                      "whole_step_tensor_frac": (world * B * args.steps * 30 * NMAX * FLOP_PER_POINT_TC) / (ms * 1e-3) / 1e12 / (peak_tf * world)},
@@ -261,7 +414,7 @@ def run_b200(args):
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         bc = 32
-        rate, dt = cpu_step_rate(bc, 2, 1, threads)
+        rate, dt = cpu_step_rate(bc, 2, 1, threads, NMAX)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"oracle port of the variant-4 step, batch {bc}, N={NMAX}, C={NCLS}, fp32, 1 warm-up + 2 timed steps ({dt:.2f} s/step)"}
     print(json.dumps(line))
@@ -276,6 +429,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train: one variant-4 AAE iteration per step (default, BASELINE.json metric); infer: eval-mode "
+                         "encoder + fused open-set scoring + k-window vote over one batch of crops per step")
+    ap.add_argument("--nmax", type=int, default=NMAX, help="points per frame (train_pointsubsampling sweep: 50..150)")
+    ap.add_argument("--k", type=int, default=6, help="voting window of the inference workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -411,7 +411,7 @@ __device__ __forceinline__ LaneGroups lane_groups(int64_t tile, int lane, int n,
 
 constexpr int MP_ROWS_PER_WARP = 8;
 
-// grid (ceil(C / 64), n_tiles), 8 warps; warp w owns channels cb + w + 8*i.  pooled / e1 / e2 must be zeroed: a group
+// grid (n_tiles, ceil(C / 64)), 8 warps; warp w owns channels cb + w + 8*i.  pooled / e1 / e2 must be zeroed: a group
 // receives one contribution per tile it touches (+ one when a lane-31 chunk straddles), added atomically.
 template <bool TRAIN>
 __global__ void __launch_bounds__(256)
@@ -420,8 +420,8 @@ bn_elu_meanpool_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* _
                             const float* __restrict__ invstd, float* __restrict__ pooled, float* __restrict__ e1,
                             float* __restrict__ e2, int64_t P, int64_t G, int n, int C, int apply, float inv_n) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tile = blockIdx.y;
-    const int cb = blockIdx.x * (8 * MP_ROWS_PER_WARP) + warp;
+    const int64_t tile = blockIdx.x;
+    const int cb = blockIdx.y * (8 * MP_ROWS_PER_WARP) + warp;
     const LaneGroups lg = lane_groups(tile, lane, n, P);
     float wT[8], wA[8];
 #pragma unroll
@@ -541,13 +541,13 @@ bn_elu_meanpool_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* _
 
 constexpr int EA_ROWS_PER_WARP = 4;
 
-// outT = ELU(scale[c]*yT + shift[c]); grid (ceil(C / 32), n_tiles): warp w streams the 512-byte rows of channels cb + w + 8*i
+// outT = ELU(scale[c]*yT + shift[c]); grid (n_tiles, ceil(C / 32)): warp w streams the 512-byte rows of channels cb + w + 8*i
 __global__ void __launch_bounds__(256)
 bn_elu_apply_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* __restrict__ scale,
                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ outT, int64_t P, int C) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tile = blockIdx.y;
-    const int cb = blockIdx.x * (8 * EA_ROWS_PER_WARP) + warp;
+    const int64_t tile = blockIdx.x;
+    const int cb = blockIdx.y * (8 * EA_ROWS_PER_WARP) + warp;
     const int64_t tile_off = tile * (int64_t)C * 256 + lane * 8;
     const int64_t left = P - ((tile << 8) + (lane << 3));
     const int vcnt = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
@@ -578,15 +578,15 @@ bn_elu_apply_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* __re
 
 constexpr int PB_ROWS_PER_WARP = 4;
 
-// dy(c,p) = c1[c]*(dpool[g(p)][c]/n)*ELU'(scale*y+shift) + c2[c]*y + c3[c]; grid (ceil(C / 32), n_tiles), n >= 8
+// dy(c,p) = c1[c]*(dpool[g(p)][c]/n)*ELU'(scale*y+shift) + c2[c]*y + c3[c]; grid (n_tiles, ceil(C / 32)), n >= 8
 __global__ void __launch_bounds__(256)
 pool_bwd_apply_rows_kernel(const float* __restrict__ dpool, const __nv_bfloat16* __restrict__ yT,
                            const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ c1,
                            const float* __restrict__ c2, const float* __restrict__ c3, __nv_bfloat16* __restrict__ dyT,
                            int64_t P, int64_t G, int n, int C, float inv_n) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tile = blockIdx.y;
-    const int cb = blockIdx.x * (8 * PB_ROWS_PER_WARP) + warp;
+    const int64_t tile = blockIdx.x;
+    const int cb = blockIdx.y * (8 * PB_ROWS_PER_WARP) + warp;
     const LaneGroups lg = lane_groups(tile, lane, n, P);
     const int64_t tile_off = tile * (int64_t)C * 256 + lane * 8;
     const bool has0 = lg.g0 < G, has1 = lg.split < 8 && lg.g0 + 1 < G;
@@ -664,7 +664,7 @@ int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, co
 int pcaa_bn_elu_apply_t(const void* yT, const float* scale, const float* shift, void* outT, int64_t P, int C,
                         pcaa_stream stream) {
     if (P == 0 || C == 0) return PCAA_OK;
-    dim3 grid((unsigned)ceil_div(C, 8 * EA_ROWS_PER_WARP), (unsigned)((P + 255) / 256));
+    dim3 grid((unsigned)((P + 255) / 256), (unsigned)ceil_div(C, 8 * EA_ROWS_PER_WARP));
     bn_elu_apply_rows_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, (__nv_bfloat16*)outT, P, C);
     return check_launch("bn_elu_apply_t");
 }
@@ -691,7 +691,7 @@ int pcaa_bn_elu_meanpool_t(const void* yT, const float* scale, const float* shif
         if (cudaMemsetAsync(pooled, 0, bytes, ST(stream)) != cudaSuccess || (e1 && cudaMemsetAsync(e1, 0, bytes, ST(stream)) != cudaSuccess) ||
             (e2 && cudaMemsetAsync(e2, 0, bytes, ST(stream)) != cudaSuccess))
             return check_launch("bn_elu_meanpool_t memset");
-        dim3 grid((unsigned)ceil_div(C, 8 * MP_ROWS_PER_WARP), (unsigned)((P + 255) / 256));
+        dim3 grid((unsigned)((P + 255) / 256), (unsigned)ceil_div(C, 8 * MP_ROWS_PER_WARP));
         if (e1)
             bn_elu_meanpool_rows_kernel<true><<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, P, G, n, C, apply, 1.f / (float)n);
         else
@@ -719,7 +719,7 @@ int pcaa_pool_bwd_apply_t(const float* dpool, const void* yT, const float* scale
     PCAA_REQUIRE(n >= 1, PCAA_ERR_SHAPE, "pool_bwd_apply_t: bad group size");
     const int64_t P = G * n;
     if (n >= 8) {
-        dim3 grid((unsigned)ceil_div(C, 8 * PB_ROWS_PER_WARP), (unsigned)((P + 255) / 256));
+        dim3 grid((unsigned)((P + 255) / 256), (unsigned)ceil_div(C, 8 * PB_ROWS_PER_WARP));
         pool_bwd_apply_rows_kernel<<<grid, 256, 0, ST(stream)>>>(dpool, (const __nv_bfloat16*)yT, scale, shift, c1, c2, c3, (__nv_bfloat16*)dyT, P, G, n, C, 1.f / (float)n);
         return check_launch("pool_bwd_apply_t");
     }
