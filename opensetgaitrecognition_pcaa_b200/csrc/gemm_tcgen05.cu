@@ -39,6 +39,7 @@ struct GemmParams {
     int out_f32;                  // store fp32 instead of bf16 (modes 1, 2)
     int wgrad_store;              // MODE_WGRAD: overwrite instead of atomicAdd (requires k_splits == 1)
     int out_scalar;               // fp32 rows are not 16-byte aligned (ldo % 4 != 0): scalar stores
+    int out_tma;                  // MODE_WGRAD: fp32 rows are 16-byte aligned -> staged in shared memory, TMA store / reduce-add
     const float* bias;
     double* stats;                // [2*N]
     const __nv_bfloat16* yprev;   // [M, ldy] (MODE_DGRAD_ELUBN)
@@ -118,6 +119,17 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// global += smem (element-wise fp32 add performed by the memory system: split-K accumulation without per-thread atomics)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1)
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -220,9 +232,10 @@ struct SmemLayout {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (MODE == MODE_T_DGRAD_ELUBN) ? 3 : ((BN == 256) ? 4 : 6);
-    static constexpr int COLP_FLOATS = TMODE ? 0 : 5 * BN;          // bias | scale, shift, mean, invstd
-    static constexpr int STAT_FLOATS = TMODE ? 0 : 4 * 2 * BN;      // per epilogue warp: sum, sum2
-    static constexpr int OBUF_BYTES = TMODE ? 8 * SUB_BYTES : 0;    // output staging, one sub-tile per epilogue warp
+    static constexpr bool STAGED = TMODE || MODE == MODE_WGRAD;     // epilogue output goes through shared memory + TMA
+    static constexpr int COLP_FLOATS = STAGED ? 0 : 5 * BN;         // bias | scale, shift, mean, invstd
+    static constexpr int STAT_FLOATS = STAGED ? 0 : 4 * 2 * BN;     // per epilogue warp: sum, sum2
+    static constexpr int OBUF_BYTES = STAGED ? 8 * SUB_BYTES : 0;   // output staging, one sub-tile per epilogue warp
     static constexpr int YBUF_BYTES = (MODE == MODE_T_DGRAD_ELUBN) ? 8 * SUB_BYTES : 0;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OBUF_BYTES + YBUF_BYTES + (COLP_FLOATS + STAT_FLOATS) * 4 + 256 + 1024;
 };
@@ -305,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&tempty[i], EPI_THREADS / 32);
         }
         for (int i = 0; i < 8; ++i) mbar_init(&ybar[i], 1);
-        if constexpr (is_t_mode<MODE>()) {
+        if constexpr (is_t_mode<MODE>() || MODE == MODE_WGRAD) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
             if constexpr (MODE == MODE_T_DGRAD_ELUBN) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
         }
@@ -593,7 +606,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 if constexpr (MODE == MODE_WGRAD) {
-                    if (row_ok) {
+                    if (p.out_tma) {
+                        // 32 rows x 32 fp32 columns (128-byte rows) of this warp -> swizzled staging buffer -> one TMA
+                        // store (or reduce-add when k is split); rows >= M and columns >= N are clipped by the map
+                        uint8_t* my_o = obuf + (warp - 2) * SUB_BYTES;
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            *reinterpret_cast<float4*>(my_o + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                                make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0 && col0 < p.N) {
+                            if (p.wgrad_store) tma_store_2d(&tmO, my_o, (int)col0, (int)(m_blk * BM + q * 32));
+                            else tma_reduce_add_2d(&tmO, my_o, (int)col0, (int)(m_blk * BM + q * 32));
+                            tma_store_commit();
+                        }
+                    } else if (row_ok) {
                         float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
                         if (p.out_scalar) {
 #pragma unroll
@@ -709,6 +739,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     }
+    if constexpr (MODE == MODE_WGRAD) {
+        if (warp >= 2 && lane == 0) tma_store_wait_all();
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -753,6 +786,21 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t d0, int64_t d1, int
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PCAA_REQUIRE(r == CUDA_SUCCESS, PCAA_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return PCAA_OK;
+}
+
+// 2-D fp32 tensor map of a row-major output [rows, cols] (ld elements): box = 32 columns (128 bytes) x 32 rows
+static int make_map_out_f32(CUtensorMap* m, const void* ptr, int64_t cols, int64_t rows, int64_t ld) {
+    EncodeTiledFn enc = get_encode();
+    PCAA_REQUIRE(enc != nullptr, PCAA_ERR_DRIVER, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PCAA_REQUIRE(r == CUDA_SUCCESS, PCAA_ERR_DRIVER, "cuTensorMapEncodeTiled (fp32 output) failed (%d)", (int)r);
     return PCAA_OK;
 }
 
@@ -873,7 +921,13 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
             if (rc) return rc;
         }
     }
+    const bool out_tma = wgrad && ((uintptr_t)out & 15) == 0 && (ldo * 4) % 16 == 0;
+    if (out_tma) {
+        rc = make_map_out_f32(&to, out, N, M, ldo);
+        if (rc) return rc;
+    }
     GemmParams p{};
+    p.out_tma = out_tma ? 1 : 0;
     p.M = M;
     p.N = N;
     p.m_tiles = ceil_div(M, BM);

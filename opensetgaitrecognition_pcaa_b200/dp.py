@@ -64,27 +64,48 @@ class GradExchange:
     stream (or the host) wait for all started reductions.  With world size 1 both are no-ops.
     """
 
-    def __init__(self, flat: torch.Tensor, group=None):
+    def __init__(self, flat: torch.Tensor, group=None, side_stream: bool = False):
         self.flat = flat
         self.group = group
         self.rank, self.world = world_info(group)
         self._pending: List = []
-        self._stream = torch.cuda.Stream(device=flat.device) if (self.world > 1 and flat.is_cuda) else None
+        # side_stream: keep the side stream even for one rank, for work the caller chains behind a span's reduction
+        # (`then`: e.g. the optimizer update of that span) so that it too overlaps the kernels that follow
+        self._stream = torch.cuda.Stream(device=flat.device) if ((self.world > 1 or side_stream) and flat.is_cuda) else None
         self.bytes_reduced = 0
 
-    def start(self, lo: int, hi: int) -> None:
-        if self.world == 1 or hi <= lo:
+    def start(self, lo: int, hi: int, then=None) -> None:
+        """Reduce flat[lo:hi]; `then()` (optional) is enqueued right behind the reduction -- on the side stream when
+        there is one, so it overlaps whatever the caller enqueues next on the current stream."""
+        if hi <= lo:
+            return
+        if self.world == 1 and (then is None or self._stream is None):
+            if then is not None:
+                then()
             return
         buf = self.flat[lo:hi]
-        self.bytes_reduced += buf.numel() * buf.element_size()
         if self._stream is not None:
             ev = torch.cuda.Event()
             ev.record()
             with torch.cuda.stream(self._stream):
                 self._stream.wait_event(ev)
-                self._pending.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                if self.world > 1:
+                    self.bytes_reduced += buf.numel() * buf.element_size()
+                    w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                    if then is not None:
+                        w.wait()                      # side stream waits for the collective, not the host
+                    else:
+                        self._pending.append(w)
+                if then is not None:
+                    then()
         else:
-            self._pending.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self.bytes_reduced += buf.numel() * buf.element_size()
+            w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if then is not None:
+                w.wait()
+                then()
+            else:
+                self._pending.append(w)
 
     def finish(self) -> None:
         for w in self._pending:

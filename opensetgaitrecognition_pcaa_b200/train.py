@@ -89,7 +89,7 @@ class PCAATrainer:
         self.G.make_shadow()
         self._refresh_views()
         # gradient exchange (dp.py): decoder-side span first (overlaps the encoder backward), then the encoder span
-        self.xG = dp.GradExchange(self.G.g, process_group)
+        self.xG = dp.GradExchange(self.G.g, process_group, side_stream=True)
         self.xD = dp.GradExchange(self.D.g, process_group)
         self._one = torch.ones((), device=dev, dtype=torch.float32)
 
@@ -167,14 +167,19 @@ class PCAATrainer:
         dh0, _ = engine.decoder_backward_tc(drec.view(B, S), acts, self.P_G, wb, self.gb_G)
         engine.linear_backward(dh0, fv, h0, self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused, self.gb_GPH,
                                dx_out=dfv, dx_acc=True)
-        # decoder-side gradients (99 % of the bytes) are final: reduce them while the encoder backward runs
-        self.xG.start(*self._dec_span)
+        # decoder-side gradients (99 % of the bytes) are final: reduce them AND apply their Adam update (HBM bound) on
+        # the side stream while the encoder backward (tensor bound) runs on this one
+        self.G.step += 1
+
+        def adam_span(lo, hi):
+            G = self.G
+            ops.adam_flat(G.p[lo:hi], G.g[lo:hi], G.m[lo:hi], G.v[lo:hi], cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, G.step,
+                          gscale, G.shadow[lo:hi])
+        self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
         engine.encoder_backward(dlogits, dfv, saved, self.P_E, self.gb_E)
         self.xG.start(*self._enc_span)
         self.xG.finish()
-        self.G.step += 1
-        ops.adam_flat(self.G.p, self.G.g, self.G.m, self.G.v, cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, self.G.step, gscale,
-                      self.G.shadow)
+        adam_span(*self._enc_span)
         return {"rec_loss": rec_loss, "d_loss": d_losses[0], "gp": d_losses[1], "loss_g": loss_g, "sup_loss": sup_loss,
                 "pred": pred, "logits": logits, "fv": fv}
 

@@ -1,15 +1,15 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel time share of ONE train step."""
 import collections, csv, re, sys
 path = sys.argv[1]
-step = int(sys.argv[2]) if len(sys.argv) > 2 else -2       # which step (index into the generator-Adam launches)
+step = int(sys.argv[2]) if len(sys.argv) > 2 else -1       # which step (the one ending at the step-th layer-1 forward launch)
 with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 names = [r["Kernel Name"] for r in rows]
 vals = [float(r["Metric Value"].replace(",", "")) for r in rows]
-adam = [i for i, n in enumerate(names) if "adam_flat" in n]
-g_adams = adam[1::2]
-s, e = g_adams[step - 1] + 1, g_adams[step] + 1
+# a step starts with the layer-1 PointNet forward kernel
+starts = [i for i, n in enumerate(names) if "pointnet_l1_fwd" in n]
+s, e = starts[step - 1], starts[step]
 agg = collections.OrderedDict()
 for n, v in zip(names[s:e], vals[s:e]):
     k = re.sub(r"\(.*", "", n)[:100]
