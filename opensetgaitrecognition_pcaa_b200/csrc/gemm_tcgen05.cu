@@ -136,6 +136,14 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one lane of a converged warp (the same one on every call): the issuing lane of TMA / tcgen05 instructions.  The loops
+// around it run on all 32 lanes so that addresses / descriptors / phases stay warp-uniform (uniform registers) -- a
+// `lane == 0` wrapper makes the compiler treat them as divergent and emit a waterfall loop around every instruction.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -337,8 +345,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================================================================== TMA producer
-        if (lane == 0) {
+        // ===================================================================== TMA producer (warp-converged, one issuing lane)
+        {
             int stage = 0;
             uint32_t phase = 0;
             int m_blk, n_blk, ks;
@@ -350,7 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // pull it into L2 so its per-warp sub-tile loads do not wait on DRAM
                     for (int t = (it == 0 ? 0 : it + 2); t <= it + 2; ++t) {
                         int pm, pn, pk;
-                        if (tile_at(p, t, pm, pn, pk)) {
+                        if (tile_at(p, t, pm, pn, pk) && lane == 0) {
                             const int64_t rows = min((int64_t)BM, p.M - (int64_t)pm * BM);
                             const __nv_bfloat16* src = p.yprev + ((int64_t)pn * p.M + (int64_t)pm * BM) * 256;
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(rows * 512)) : "memory");
@@ -361,6 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = tiles + stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + L::A_BYTES;
+                    if (elect_one()) {
                     mbar_expect_tx(&full[stage], L::STAGE_BYTES);
                     if constexpr (!A_MN) {
                         // tiled: k = points, 4 k blocks per 256-point tile, rows = channels
@@ -384,13 +393,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int i = 0; i < BN / 64; ++i)
                             tma_load_2d(&tmB, &full[stage], sb + i * (BK * 128), n_blk * BN + i * 64, kb * BK);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================================== MMA issuer (warp-converged, one issuing lane)
+        {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                        ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                                        ((uint32_t)(BM >> 4) << 24);
@@ -416,14 +427,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sb = sa + L::A_BYTES;
                     const uint64_t da = make_desc(sa, A_LBO, 1024);
                     const uint64_t db = make_desc(sb, B_LBO, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        tc_mma_bf16(tmem_d, da + (uint64_t)(k * A_KSTEP), db + (uint64_t)(k * B_KSTEP), idesc,
-                                    (kb > kb0 || k > 0) ? 1u : 0u);
-                    tc_commit(&empty[stage]);          // smem slot free once these MMAs retire
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            tc_mma_bf16(tmem_d, da + (uint64_t)(k * A_KSTEP), db + (uint64_t)(k * B_KSTEP), idesc,
+                                        (kb > kb0 || k > 0) ? 1u : 0u);
+                        tc_commit(&empty[stage]);          // smem slot free once these MMAs retire
+                        if (kb + 1 == kb1) tc_commit(&tfull[buf]);   // ... and the accumulator is ready for the epilogue
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull[buf]);                // accumulator ready for the epilogue
             }
         }
     } else if constexpr (is_t_mode<MODE>()) {
