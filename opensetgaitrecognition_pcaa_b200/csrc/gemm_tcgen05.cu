@@ -52,13 +52,17 @@ struct GemmParams {
 // tile `it` of this CTA -> (m block, n block, k split); false when the CTA has no more work
 __device__ __forceinline__ bool tile_at(const GemmParams& p, int it, int& m_blk, int& n_blk, int& ks) {
     if (p.sched_mfixed) {
-        // gridDim.x is a multiple of m_tiles: CTAs b, b+1, .. b+m_tiles-1 work on the same n block at the same time
-        // (the activation tile is fetched from DRAM once and hit in L2 by the others) and a CTA never changes m block
-        const int per = gridDim.x / p.m_tiles;
-        m_blk = blockIdx.x % p.m_tiles;
-        n_blk = blockIdx.x / p.m_tiles + it * per;
+        // channel-major modes, CTA pairs: cluster c = blockIdx.x / 2 owns the 256-row block c % m_pairs (this CTA its
+        // upper or lower 128 rows) for the n blocks c / m_pairs + it * per.  The m_pairs clusters of one n block run at
+        // the same time (the activation tile is fetched from DRAM once and hit in L2 by the others) and a CTA never
+        // changes its rows (its per-row epilogue state lives in registers for the whole kernel)
+        const int m_pairs = (p.m_tiles + 1) >> 1;
+        const int cid = blockIdx.x >> 1;
+        const int per = (gridDim.x >> 1) / m_pairs;
+        m_blk = (cid % m_pairs) * 2 + (int)(blockIdx.x & 1);
+        n_blk = cid / m_pairs + it * per;
         ks = 0;
-        return n_blk < p.n_tiles;
+        return cid < per * m_pairs && n_blk < p.n_tiles;
     }
     const int item = blockIdx.x + it * gridDim.x;
     if (item >= p.m_tiles * p.n_tiles * p.k_splits) return false;
@@ -115,6 +119,57 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on the SMs of one TPC execute ONE 256 x 256 UMMA tile; each
+// stages its own 128 rows of A and HALF of B (so a k block costs 32 KB of shared memory per SM instead of 48 KB: more
+// stages in flight), the leader (cluster rank 0) issues the MMAs and both epilogues read their own TMEM
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on the mbarrier at
+// cluster address `bar` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar, void* smem, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t bar, void* smem, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once the MMAs issued so far retire) on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+
 // smem -> global tensor store (bulk async group) and its completion waits
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -236,10 +291,11 @@ constexpr int SUB_BYTES = 32 * 64 * 2;
 template <int BN, int MODE>
 struct SmemLayout {
     static constexpr bool TMODE = is_t_mode<MODE>();
+    static constexpr bool PAIR = TMODE;                             // channel-major modes run as CTA pairs
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // a pair splits the B tile between its two CTAs
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (MODE == MODE_T_DGRAD_ELUBN) ? 3 : ((BN == 256) ? 4 : 6);
+    static constexpr int STAGES = PAIR ? ((MODE == MODE_T_DGRAD_ELUBN) ? 5 : 6) : ((BN == 256) ? 4 : 6);
     static constexpr bool STAGED = TMODE || MODE == MODE_WGRAD;     // epilogue output goes through shared memory + TMA
     static constexpr int COLP_FLOATS = STAGED ? 0 : 5 * BN;         // bias | scale, shift, mean, invstd
     static constexpr int STAT_FLOATS = STAGED ? 0 : 4 * 2 * BN;     // per epilogue warp: sum, sum2
@@ -313,6 +369,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr bool PAIR = L::PAIR;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // 0 = leader of the CTA pair (issues the MMAs)
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -323,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], EPI_THREADS / 32);
+            mbar_init(&tempty[i], (PAIR ? 2 : 1) * (EPI_THREADS / 32));   // pair: the epilogue warps of both CTAs
         }
         for (int i = 0; i < 8; ++i) mbar_init(&ybar[i], 1);
         if constexpr (is_t_mode<MODE>() || MODE == MODE_WGRAD) {
@@ -334,13 +392,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(2 * BN)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(2 * BN)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(2 * BN)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // the peer's mbarriers must be initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -369,7 +435,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = tiles + stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + L::A_BYTES;
-                    if (elect_one()) {
+                    if constexpr (PAIR) {
+                        // each CTA loads its 128 rows of A and its half of the B tile (64-point groups 2*rank, 2*rank+1);
+                        // all bytes of the pair are counted on the LEADER's full barrier
+                        static_assert(!PAIR || (B_MN && BN == 256), "CTA pairs: B is a 256-point T256 tile read MN-major");
+                        if (elect_one()) {
+                            const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+                            if (rank == 0) mbar_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
+                            if constexpr (!A_MN) {
+                                tma_load_2d_pair(&tmA, bar, sa, kb * BK, m_blk * BM);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < BM / 64; ++i)
+                                    tma_load_2d_pair(&tmA, bar, sa + i * (BK * 128), m_blk * BM + i * 64, kb * BK);
+                            }
+#pragma unroll
+                            for (int i = 0; i < BN / 128; ++i)
+                                tma_load_3d_pair(&tmB, bar, sb + i * (BK * 128), ((int)rank * (BN / 128) + i) * 64, kb * BK, n_blk);
+                        }
+                    } else if (elect_one()) {
                     mbar_expect_tx(&full[stage], L::STAGE_BYTES);
                     if constexpr (!A_MN) {
                         // tiled: k = points, 4 k blocks per 256-point tile, rows = channels
@@ -401,10 +485,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer (warp-converged, one issuing lane)
-        {
+        if (rank == 0) {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                        ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                                       ((uint32_t)(BM >> 4) << 24);
+                                       ((uint32_t)(((PAIR ? 2 : 1) * BM) >> 4) << 24);     // pair: one 256-row UMMA
             // K-major: 8-row groups 1024 B apart (SBO), LBO unused.  MN-major: 64-element column groups BK*128 B apart
             // (LBO), 8-k-row groups 1024 B apart (SBO).
             constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, B_LBO = B_MN ? BK * 128 : 16;
@@ -428,12 +512,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t da = make_desc(sa, A_LBO, 1024);
                     const uint64_t db = make_desc(sb, B_LBO, 1024);
                     if (elect_one()) {
+                        if constexpr (PAIR) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            tc_mma_bf16(tmem_d, da + (uint64_t)(k * A_KSTEP), db + (uint64_t)(k * B_KSTEP), idesc,
-                                        (kb > kb0 || k > 0) ? 1u : 0u);
-                        tc_commit(&empty[stage]);          // smem slot free once these MMAs retire
-                        if (kb + 1 == kb1) tc_commit(&tfull[buf]);   // ... and the accumulator is ready for the epilogue
+                            for (int k = 0; k < BK / UMMA_K; ++k)
+                                tc_mma_bf16_pair(tmem_d, da + (uint64_t)(k * A_KSTEP), db + (uint64_t)(k * B_KSTEP), idesc,
+                                                 (kb > kb0 || k > 0) ? 1u : 0u);
+                            tc_commit_pair(&empty[stage]);     // frees the slot in both CTAs
+                            if (kb + 1 == kb1) tc_commit_pair(&tfull[buf]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k)
+                                tc_mma_bf16(tmem_d, da + (uint64_t)(k * A_KSTEP), db + (uint64_t)(k * B_KSTEP), idesc,
+                                            (kb > kb0 || k > 0) ? 1u : 0u);
+                            tc_commit(&empty[stage]);          // smem slot free once these MMAs retire
+                            if (kb + 1 == kb1) tc_commit(&tfull[buf]);   // ... and the accumulator is ready for the epilogue
+                        }
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -558,10 +651,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-            // all TMEM reads of this accumulator are complete -> hand the buffer back to the MMA warp
+            // all TMEM reads of this accumulator are complete -> hand the buffer back to the (leader's) MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));
             d1 += (double)t1;
             d2 += (double)t2;
         }
@@ -757,10 +850,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (warp >= 2 && lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // neither CTA may exit (or free TMEM) while the other still signals it
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
     }
 }
 
@@ -864,15 +961,46 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     }
     int items = p.m_tiles * p.n_tiles * p.k_splits;
     int grid = items < num_sms() ? items : num_sms();
-    if (p.sched_mfixed) {
-        // a multiple of m_tiles CTAs, at most one per SM and no more column groups than there are n tiles
-        int per = num_sms() / p.m_tiles;
+    if constexpr (L::PAIR) {
+        // CTA pairs (clusters of 2, one per TPC): m_pairs clusters per n block, at most one cluster per SM pair and
+        // no more column groups than there are n tiles
+        static int max_clusters = 0;
+        if (max_clusters == 0) {
+            static bool attr2 = false;
+            if (!attr2) { cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0); attr2 = true; }
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(num_sms()); q.blockDim = dim3(NUM_THREADS); q.dynamicSmemBytes = L::TOTAL;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
+            max_clusters = n < num_sms() / 2 ? n : num_sms() / 2;
+        }
+        const int m_pairs = (p.m_tiles + 1) / 2;
+        int per = max_clusters / m_pairs;
         if (per > p.n_tiles) per = p.n_tiles;
         if (per < 1) {
-            set_error("gemm_tc: %d row blocks exceed the SM count (channel-major modes)", p.m_tiles);
+            set_error("gemm_tc: %d row-block pairs exceed the resident clusters (channel-major modes)", m_pairs);
             return PCAA_ERR_UNSUPPORTED;
         }
-        grid = per * p.m_tiles;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * per * m_pairs);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = L::TOTAL;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, ty, p);
+        if (e != cudaSuccess) {
+            set_error("gemm_tc: cluster launch failed: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return PCAA_ERR_LAUNCH;
+        }
+        return check_launch("gemm_tc");
     }
     kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ta, tb, to, ty, p);
     return check_launch("gemm_tc");
