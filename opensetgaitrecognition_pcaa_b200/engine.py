@@ -94,11 +94,16 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
 
 
 def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = None,
-                      pre: str = "pc_block.") -> Grads:
-    """gpool [B*T, 1024] fp32 = d loss / d pooled.  Returns parameter gradients (written into gradbuf when given)."""
+                      pre: str = "pc_block.", side: Optional[torch.cuda.Stream] = None) -> Grads:
+    """gpool [B*T, 1024] fp32 = d loss / d pooled.  Returns parameter gradients (written into gradbuf when given).
+
+    With a `side` stream the weight-gradient GEMM of layer l (tensor bound, reads dy_l and a_{l-1}) runs there while the
+    current stream goes on with the data gradient's successor, the HBM-bound BatchNorm-backward pass of layer l-1: the
+    two are independent and have complementary bottlenecks.  The current stream waits for `side` before returning."""
     G: Grads = {}
     R, N = sv["R"], sv["N"]
     gpool = gpool.contiguous()
+    main = torch.cuda.current_stream()
     # layer 4: the BatchNorm-backward statistics follow from the forward's group sums (no pass over y4), then ONE pass
     # forms dy4 = BN'(ELU'(pool'(gpool)))
     st2 = ops.pool_bwd_stats(gpool, sv["e1"], sv["e2"], N)
@@ -110,10 +115,19 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
         kc = f"{pre}pointnet{l}.module.0."
         W = P[kc + "weight"]
         Cout, Cin = W.shape[0], W.shape[1]
-        dW = _zeros_like_param(gradbuf, kc + "weight", W)
-        # dW[Cout, Cin] += dyT [Cout, P] . a_{l-1}T [Cin, P]^T   (both operands K-major, K = points, split over the SMs)
-        ops.gemm_tc(dy, sv["a"][l - 1], TC_WGRAD_ACC, Cout, Cin, R, a_mn=OP_T256_K, b_mn=OP_T256_K, out=dW.view(Cout, Cin))
-        G[kc + "weight"] = dW
+
+        def wgrad(dy=dy, l=l, kc=kc, W=W, Cout=Cout, Cin=Cin):
+            dW = _zeros_like_param(gradbuf, kc + "weight", W)
+            # dW[Cout, Cin] += dyT [Cout, P] . a_{l-1}T [Cin, P]^T   (both operands K-major, K = points, split over the SMs)
+            ops.gemm_tc(dy, sv["a"][l - 1], TC_WGRAD_ACC, Cout, Cin, R, a_mn=OP_T256_K, b_mn=OP_T256_K, out=dW.view(Cout, Cin))
+            G[kc + "weight"] = dW
+        if side is None:
+            wgrad()
+        else:
+            side.wait_stream(main)                    # dy_l is complete
+            with torch.cuda.stream(side):
+                wgrad()
+            dy.record_stream(side)                    # dy_l is released on this stream while `side` may still read it
         # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero
         G[kc + "bias"] = _zeros_like_param(gradbuf, kc + "bias", P[kc + "bias"])
         # dz_{l-1}T [Cin, P] = (W^T dyT) * ELU'(BN(y_{l-1})) with the statistics of BatchNorm l-1's backward
@@ -132,6 +146,10 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
     dW1 = ops.pointnet_l1_wgrad_t(sv["x"], dz, sv["y"][1], c, None if o is None else o.view(W1.shape[0], 4))
     G[kc + "weight"] = dW1.view(W1.shape) if o is None else o
     G[kc + "bias"] = _zeros_like_param(gradbuf, kc + "bias", P[kc + "bias"])
+    if side is not None:
+        main.wait_stream(side)
+        for l in (1, 2, 3):
+            sv["a"][l].record_stream(side)
     return G
 
 
@@ -248,12 +266,13 @@ def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_h
     return logits, fv, (sv_p, sv_t, sv_h)
 
 
-def encoder_backward(dlogits, dfv, saved, P: Params, gradbuf: Optional[Grads] = None) -> Grads:
+def encoder_backward(dlogits, dfv, saved, P: Params, gradbuf: Optional[Grads] = None,
+                     side: Optional[torch.cuda.Stream] = None) -> Grads:
     sv_p, sv_t, sv_h = saved
     dh6, G = heads_backward(dlogits, dfv, sv_h, P, gradbuf)
     dpool, Gt = tcn_backward(dh6, sv_t, P, gradbuf)
     G.update(Gt)
-    G.update(pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf))
+    G.update(pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf, side=side))
     return G
 
 

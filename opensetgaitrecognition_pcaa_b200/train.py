@@ -12,6 +12,7 @@ the PointNet backward is still running).  ``state_dict()`` of the modules keeps 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -92,6 +93,10 @@ class PCAATrainer:
         self.xG = dp.GradExchange(self.G.g, process_group, side_stream=True)
         self.xD = dp.GradExchange(self.D.g, process_group)
         self._one = torch.ones((), device=dev, dtype=torch.float32)
+        # PCAA_WGRAD_OVERLAP=1 runs the PointNet weight-gradient GEMMs on their own stream, concurrently with the
+        # BatchNorm-backward passes (engine.pointnet_backward).  Off by default: measured on B200 the step is power
+        # capped (sw_power_cap, ~1.6-1.7 GHz under load) and the overlap buys nothing (21.99 vs 22.07 ms at B=256).
+        self._wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("PCAA_WGRAD_OVERLAP", "0") == "1" else None
 
     def _refresh_views(self):
         enc_t = {k: v for k, v in self.enc.named_parameters()}
@@ -176,7 +181,7 @@ class PCAATrainer:
             ops.adam_flat(G.p[lo:hi], G.g[lo:hi], G.m[lo:hi], G.v[lo:hi], cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, G.step,
                           gscale, G.shadow[lo:hi])
         self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
-        engine.encoder_backward(dlogits, dfv, saved, self.P_E, self.gb_E)
+        engine.encoder_backward(dlogits, dfv, saved, self.P_E, self.gb_E, side=self._wgrad_stream)
         self.xG.start(*self._enc_span)
         self.xG.finish()
         adam_span(*self._enc_span)
