@@ -138,7 +138,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (no .release.cluster): that form costs a cluster-scope memory barrier (MEMBAR + ERRBAR, 28 % of the
+    // data-gradient kernel's stall samples); the TMEM reads are ordered by tcgen05.fence::before_thread_sync
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on the mbarrier at
 // cluster address `bar` (the leader's)
@@ -420,9 +422,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 if constexpr (MODE == MODE_T_DGRAD_ELUBN) {
-                    // the epilogue reads this CTA's [128 x 256] block of yprev (contiguous in T256) two tiles from now:
-                    // pull it into L2 so its per-warp sub-tile loads do not wait on DRAM
-                    for (int t = (it == 0 ? 0 : it + 2); t <= it + 2; ++t) {
+                    // the epilogue reads this CTA's [128 x 256] block of yprev (contiguous in T256) PF_DIST tiles from now:
+                    // pull it into L2 so its per-warp sub-tile loads do not wait on DRAM.  (Two tiles ahead was too
+                    // early: ncu showed yprev fetched from DRAM twice -- the line was evicted before its use.)
+                    constexpr int PF_DIST = 1;
+                    for (int t = (it == 0 ? 0 : it + PF_DIST); t <= it + PF_DIST; ++t) {
                         int pm, pn, pk;
                         if (tile_at(p, t, pm, pn, pk) && lane == 0) {
                             const int64_t rows = min((int64_t)BM, p.M - (int64_t)pm * BM);
