@@ -89,6 +89,158 @@ chamfer_fwd_kernel(const float* __restrict__ preds, const float* __restrict__ gt
     }
 }
 
+// ---------------------------------------------------------------------------------------------- F = 4 fast path
+// The radar features are (x, y, z, doppler): F = 4 always in the reference (constants.py:29-33).  Same arithmetic as
+// chamfer_fwd_kernel bit for bit (zz = fma chain over f = 0..3 from 0, d = (r_other + r_own) - 2 zz, strict `<` scan in
+// index order => lowest index on ties), organised for the FP32 issue limit:
+//   * packed fp32x2 FMAs (FFMA2, sm_100): two candidate points per instruction with the own point's feature as the
+//     broadcast operand;
+//   * a thread owns TWO points of its cloud, so one 16-byte shared-memory read of four candidates feeds 8 pairs;
+//   * the running arg-min is kept per block of four candidates (3 FMNMX + compare + 2 selects per 4 pairs instead of
+//     3 instructions per pair); the winning block is re-evaluated once at the end with the same arithmetic to find the
+//     first index that attains the minimum;
+//   * both directions run concurrently: threads [0, tp) scan the ground truth for predicted points (torch.min(P, 2),
+//     utils.py:100), threads [tp, 2 tp) scan the predictions for ground-truth points (torch.min(P, 3), utils.py:102),
+//     tp = ceil(N / 2); same code, the cloud pointers are per thread.
+// Clouds are padded to a multiple of four candidates with r = +inf (never selected).
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+chamfer_fwd4_kernel(const float* __restrict__ preds, const float* __restrict__ gts, int T, int N, int Np, int tp,
+                    float* __restrict__ frame_loss, int32_t* __restrict__ idx_gt_for_pred,
+                    int32_t* __restrict__ idx_pred_for_gt) {
+    extern __shared__ __align__(16) float sm[];
+    // cloud 0 = ground truth, cloud 1 = predictions: feature planes [4][Np] then squared norms [Np]
+    float* const cl0 = sm;
+    float* const cl1 = sm + 5 * Np;
+    __shared__ float red[8];
+    const int bt = blockIdx.x;
+    const int b = bt / T, t = bt % T;
+    const int64_t base = ((int64_t)b * 4 * T + t) * N;
+    const int64_t fstride = (int64_t)T * N;
+    for (int i = threadIdx.x; i < 4 * Np; i += blockDim.x) {
+        const int f = i / Np, n = i - f * Np;
+        const bool ok = n < N;
+        cl0[i] = ok ? __ldg(gts + base + f * fstride + n) : 0.f;
+        cl1[i] = ok ? __ldg(preds + base + f * fstride + n) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * Np; i += blockDim.x) {
+        const int c = i >= Np, n = i - c * Np;
+        float* const cc = c ? cl1 : cl0;
+        float a = 0.f;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) a = fmaf(cc[f * Np + n], cc[f * Np + n], a);
+        cc[4 * Np + n] = n < N ? a : INFINITY;
+    }
+    __syncthreads();
+    float total = 0.f;
+    const int tid = threadIdx.x;
+    if (tid < 2 * tp) {
+        const int dir = tid >= tp;                    // 0: own = prediction, other = ground truth; 1: the reverse
+        const int k = tid - dir * tp;
+        const float* own = dir ? cl0 : cl1;
+        const float* oth = dir ? cl1 : cl0;
+        const int j0 = k, j1 = min(k + tp, N - 1);
+        const bool has1 = k + tp < N;
+        unsigned long long w0[4], w1[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            w0[f] = pk2(own[f * Np + j0], own[f * Np + j0]);
+            w1[f] = pk2(own[f * Np + j1], own[f * Np + j1]);
+        }
+        const float r0 = own[4 * Np + j0], r1 = own[4 * Np + j1];
+        const unsigned long long rr0 = pk2(r0, r0), rr1 = pk2(r1, r1);
+        const unsigned long long m2 = pk2(-2.f, -2.f), zero = pk2(0.f, 0.f);
+        float best0 = INFINITY, best1 = INFINITY;
+        int blk0 = 0, blk1 = 0;
+        const ulonglong2* o0 = reinterpret_cast<const ulonglong2*>(oth);
+        const ulonglong2* o1 = reinterpret_cast<const ulonglong2*>(oth + Np);
+        const ulonglong2* o2 = reinterpret_cast<const ulonglong2*>(oth + 2 * Np);
+        const ulonglong2* o3 = reinterpret_cast<const ulonglong2*>(oth + 3 * Np);
+        const ulonglong2* orr = reinterpret_cast<const ulonglong2*>(oth + 4 * Np);
+        const int nb = Np >> 2;
+#pragma unroll 2
+        for (int q = 0; q < nb; ++q) {
+            const ulonglong2 a0 = o0[q], a1 = o1[q], a2 = o2[q], a3 = o3[q], ar = orr[q];
+            {
+                unsigned long long zl = fma2(a0.x, w0[0], zero), zh = fma2(a0.y, w0[0], zero);
+                zl = fma2(a1.x, w0[1], zl); zh = fma2(a1.y, w0[1], zh);
+                zl = fma2(a2.x, w0[2], zl); zh = fma2(a2.y, w0[2], zh);
+                zl = fma2(a3.x, w0[3], zl); zh = fma2(a3.y, w0[3], zh);
+                const unsigned long long dl = fma2(zl, m2, add2(ar.x, rr0)), dh = fma2(zh, m2, add2(ar.y, rr0));
+                float d0, d1, d2, d3;
+                upk2(dl, d0, d1);
+                upk2(dh, d2, d3);
+                const float m = fminf(fminf(d0, d1), fminf(d2, d3));
+                if (m < best0) { best0 = m; blk0 = q; }
+            }
+            {
+                unsigned long long zl = fma2(a0.x, w1[0], zero), zh = fma2(a0.y, w1[0], zero);
+                zl = fma2(a1.x, w1[1], zl); zh = fma2(a1.y, w1[1], zh);
+                zl = fma2(a2.x, w1[2], zl); zh = fma2(a2.y, w1[2], zh);
+                zl = fma2(a3.x, w1[3], zl); zh = fma2(a3.y, w1[3], zh);
+                const unsigned long long dl = fma2(zl, m2, add2(ar.x, rr1)), dh = fma2(zh, m2, add2(ar.y, rr1));
+                float d0, d1, d2, d3;
+                upk2(dl, d0, d1);
+                upk2(dh, d2, d3);
+                const float m = fminf(fminf(d0, d1), fminf(d2, d3));
+                if (m < best1) { best1 = m; blk1 = q; }
+            }
+        }
+        // first candidate of the winning block that attains the minimum (same arithmetic, scalar)
+        int32_t* out_idx = dir ? idx_pred_for_gt : idx_gt_for_pred;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int j = a ? j1 : j0;
+            const float rj = a ? r1 : r0, best = a ? best1 : best0;
+            const int blk = a ? blk1 : blk0;
+            float wj[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) wj[f] = own[f * Np + j];
+            int bi = blk * 4;
+#pragma unroll
+            for (int e = 3; e >= 0; --e) {
+                const int i = blk * 4 + e;
+                float zz = 0.f;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) zz = fmaf(oth[f * Np + i], wj[f], zz);
+                const float d = fmaf(zz, -2.f, oth[4 * Np + i] + rj);
+                if (d == best) bi = i;
+            }
+            if (a == 0 || has1) {
+                total += best;
+                if (out_idx) out_idx[(int64_t)bt * N + j] = bi;
+            }
+        }
+    }
+    total = warp_sum(total);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        frame_loss[bt] = s;
+    }
+}
+
 // one block; avg_out: out[0] = mean over all frames, else out[b] = mean over the T frames of sample b
 __global__ void chamfer_reduce_kernel(const float* __restrict__ frame_loss, int64_t B, int T, int avg_out,
                                       float* __restrict__ out) {
@@ -218,6 +370,13 @@ extern "C" int pcaa_chamfer_fwd(const float* preds, const float* gts, int64_t B,
         cudaFuncSetAttribute(chamfer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(chamfer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr = true;
+    }
+    if (F == 4 && N <= 256) {
+        const int Np = (N + 3) & ~3, tp = (N + 1) / 2;
+        const unsigned threads = (unsigned)((2 * tp + 31) & ~31);
+        chamfer_fwd4_kernel<<<(unsigned)(B * T), threads, (size_t)10 * Np * sizeof(float), (cudaStream_t)stream>>>(
+            preds, gts, T, N, Np, tp, frame_loss, idx_gt_for_pred, idx_pred_for_gt);
+        return check_launch("chamfer_fwd");
     }
     chamfer_fwd_kernel<<<(unsigned)(B * T), CH_THREADS, smem, (cudaStream_t)stream>>>(preds, gts, F, T, N, frame_loss,
                                                                                    idx_gt_for_pred, idx_pred_for_gt);

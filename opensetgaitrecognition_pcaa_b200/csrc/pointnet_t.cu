@@ -539,6 +539,136 @@ bn_elu_meanpool_rows_kernel(const __nv_bfloat16* __restrict__ yT, const float* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------ staged mean pool
+// Same contract as bn_elu_meanpool_rows_kernel, organised for the instruction-issue limit instead of only for the
+// memory system: the CTA stages a [64 channels][256 points] block of the tile in shared memory (coalesced 16-byte
+// loads, 528-byte row pitch), then LANE = CHANNEL and a warp walks 64 consecutive points of its 32 channels, so
+//   * the reduction over points is a serial in-thread sum (no shuffles, no per-element group weights);
+//   * group boundaries depend on the point index only => every branch on them is warp-uniform;
+//   * ELU and ELU' share one exponential and need no select: with e = 2^(z*log2 e),
+//       ELU'(z) = min(e, 1),  ELU(z) = max(z, 0) + min(e, 1) - 1,
+//     i.e. 9 instructions per element in training (unpack, 2 FMA, EX2, MIN, MAX, 3 accumulates), 2 in eval.
+// Partial sums of the (at most 255/n + 2) groups a tile touches are combined in shared memory; one global atomic per
+// (group, channel, tile) as before.  grid (n_tiles, ceil(C / 64)), 256 threads, n >= 8.
+constexpr int MPS_CH = 64;
+constexpr int MPS_PITCH = 264;          // bf16 elements per staged row (528 B: 16-byte accesses of 8 lanes hit 32 banks)
+
+template <bool TRAIN, bool APPLY>
+__global__ void __launch_bounds__(256)
+bn_elu_meanpool_staged_kernel(const __nv_bfloat16* __restrict__ yT, const float* __restrict__ scale,
+                              const float* __restrict__ shift, const float* __restrict__ mean,
+                              const float* __restrict__ invstd, float* __restrict__ pooled, float* __restrict__ e1,
+                              float* __restrict__ e2, int64_t P, int64_t G, int n, int C, int kmax, float inv_n) {
+    extern __shared__ __align__(16) unsigned char mps_smem[];
+    __nv_bfloat16* rows = reinterpret_cast<__nv_bfloat16*>(mps_smem);
+    constexpr int NV = TRAIN ? 3 : 1;
+    float* acc = reinterpret_cast<float*>(mps_smem + (size_t)MPS_CH * MPS_PITCH * sizeof(__nv_bfloat16));   // [kmax][NV][64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.x;
+    const int cb = blockIdx.y * MPS_CH;
+    const int64_t tile_off = tile * (int64_t)C * 256;
+    // ---- stage: 64 rows x 32 chunks of 16 bytes, 8 per thread, all loads in flight before the first store
+    uint4 raw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int id = threadIdx.x + 256 * i;
+        const int r = id >> 5, ck = id & 31;
+        const int c = min(cb + r, C - 1);
+        raw[i] = __ldg(reinterpret_cast<const uint4*>(yT + tile_off + (int64_t)c * 256 + ck * 8));
+    }
+    for (int i = threadIdx.x; i < kmax * NV * MPS_CH; i += 256) acc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int id = threadIdx.x + 256 * i;
+        const int r = id >> 5, ck = id & 31;
+        *reinterpret_cast<uint4*>(rows + r * MPS_PITCH + ck * 8) = raw[i];
+    }
+    __syncthreads();
+    // ---- reduce: warp = (channel half, point quarter), lane = channel
+    const int chl = (warp & 1) * 32 + lane;                     // channel within the block
+    const int c = min(cb + chl, C - 1);
+    const int q = warp >> 1;
+    float sc = 1.f, sh = 0.f;
+    if (APPLY) { sc = __ldg(scale + c); sh = __ldg(shift + c); }
+    const float scl = sc * LOG2E_F, shl = sh * LOG2E_F;
+    const int64_t pt0 = tile << 8;
+    const int64_t g_first = pt0 / n;
+    const int64_t p0 = pt0 + 64 * q;
+    int64_t g = p0 / n;
+    int left = (int)((g + 1) * n - p0);                         // points of group g still ahead (warp-uniform)
+    float Sa = 0.f, Sd = 0.f, Su = 0.f;
+    const __nv_bfloat16* row = rows + chl * MPS_PITCH + 64 * q;
+
+    auto flush = [&](int64_t grp) {
+        if (grp < G) {
+            float* a = acc + (size_t)(grp - g_first) * NV * MPS_CH + chl;
+            atomicAdd(a, Sa);
+            if (TRAIN) {
+                atomicAdd(a + MPS_CH, Sd);
+                atomicAdd(a + 2 * MPS_CH, Su);
+            }
+        }
+        Sa = 0.f; Sd = 0.f; Su = 0.f;
+    };
+    auto accum = [&](float y) {
+        if (APPLY) {
+            const float z = fmaf(y, sc, sh);
+            const float d = fminf(ex2_fast(fmaf(y, scl, shl)), 1.f);
+            Sa += fmaxf(z, 0.f);
+            if (TRAIN) {
+                Sd += d;
+                Su = fmaf(d, y, Su);
+            } else {
+                Sa += d;
+            }
+        } else {
+            Sa += y;
+        }
+    };
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        float y[8];
+        unpack8(*reinterpret_cast<const uint4*>(row + 8 * k), y);
+        if (left > 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) accum(y[j]);
+            left -= 8;
+        } else {
+            // n >= 8: at most one group boundary per chunk (after element left - 1)
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                accum(y[0]);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) y[i] = y[i + 1];
+                if (--left == 0) { flush(g); ++g; left = n; }
+            }
+        }
+    }
+    flush(g);
+    __syncthreads();
+    // ---- emit: (group, channel) partial sums of this tile
+    for (int i = threadIdx.x; i < kmax * MPS_CH; i += 256) {
+        const int gl = i >> 6, ch = i & 63;
+        const int64_t grp = g_first + gl;
+        if (grp >= G || cb + ch >= C) continue;
+        // points of the group inside this tile
+        const int64_t lo = max(grp * (int64_t)n, pt0), hi = min((grp + 1) * (int64_t)n, pt0 + 256);
+        if (hi <= lo) continue;
+        const float* a = acc + (size_t)gl * NV * MPS_CH + ch;
+        const int64_t o = grp * C + cb + ch;
+        if (TRAIN) {
+            const float sd = a[MPS_CH], su = a[2 * MPS_CH];
+            atomicAdd(pooled + o, (a[0] + (sd - (float)(hi - lo))) * inv_n);
+            atomicAdd(e1 + o, sd);
+            atomicAdd(e2 + o, __ldg(invstd + cb + ch) * (su - __ldg(mean + cb + ch) * sd));
+        } else if (APPLY) {
+            atomicAdd(pooled + o, (a[0] - (float)(hi - lo)) * inv_n);
+        } else {
+            atomicAdd(pooled + o, a[0] * inv_n);
+        }
+    }
+}
+
 constexpr int EA_ROWS_PER_WARP = 4;
 
 // outT = ELU(scale[c]*yT + shift[c]); grid (n_tiles, ceil(C / 32)): warp w streams the 512-byte rows of channels cb + w + 8*i
@@ -691,11 +821,23 @@ int pcaa_bn_elu_meanpool_t(const void* yT, const float* scale, const float* shif
         if (cudaMemsetAsync(pooled, 0, bytes, ST(stream)) != cudaSuccess || (e1 && cudaMemsetAsync(e1, 0, bytes, ST(stream)) != cudaSuccess) ||
             (e2 && cudaMemsetAsync(e2, 0, bytes, ST(stream)) != cudaSuccess))
             return check_launch("bn_elu_meanpool_t memset");
-        dim3 grid((unsigned)((P + 255) / 256), (unsigned)ceil_div(C, 8 * MP_ROWS_PER_WARP));
+        const int kmax = 255 / n + 2;
+        const size_t smem = (size_t)MPS_CH * MPS_PITCH * sizeof(__nv_bfloat16) + (size_t)kmax * (e1 ? 3 : 1) * MPS_CH * sizeof(float);
+        dim3 grid((unsigned)((P + 255) / 256), (unsigned)ceil_div(C, MPS_CH));
+        const float inv_n = 1.f / (float)n;
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(bn_elu_meanpool_staged_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(bn_elu_meanpool_staged_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(bn_elu_meanpool_staged_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            attr = true;
+        }
         if (e1)
-            bn_elu_meanpool_rows_kernel<true><<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, P, G, n, C, apply, 1.f / (float)n);
+            bn_elu_meanpool_staged_kernel<true, true><<<grid, 256, smem, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, P, G, n, C, kmax, inv_n);
+        else if (apply)
+            bn_elu_meanpool_staged_kernel<false, true><<<grid, 256, smem, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, P, G, n, C, kmax, inv_n);
         else
-            bn_elu_meanpool_rows_kernel<false><<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, P, G, n, C, apply, 1.f / (float)n);
+            bn_elu_meanpool_staged_kernel<false, false><<<grid, 256, smem, ST(stream)>>>((const __nv_bfloat16*)yT, scale, shift, mean, invstd, pooled, e1, e2, P, G, n, C, kmax, inv_n);
         return check_launch("bn_elu_meanpool_t");
     }
     dim3 grid((unsigned)ceil_div(G, 8), (unsigned)ceil_div(C, 32));

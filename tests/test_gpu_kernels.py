@@ -254,7 +254,7 @@ def _check_idx(P, idx, ref_idx, dim):
     return int(bad.sum())
 
 
-@pytest.mark.parametrize("B,N", [(2, 50), (3, 150), (1, 1), (2, 7)])
+@pytest.mark.parametrize("B,N", [(2, 50), (3, 150), (1, 1), (2, 7), (1, 2), (2, 3), (2, 130), (1, 256)])
 def test_chamfer(ops, B, N):
     gts, _ = O.synth_batch(B, N, 2, seed=N)
     g = torch.Generator().manual_seed(N)
@@ -473,7 +473,7 @@ def test_gemm_tc_wgrad_points_k(ops, Cout, P, Cin):
     assert rel_err(dW, 2 * ref) < 1e-4
 
 
-@pytest.mark.parametrize("B,N,C", [(2, 50, 512), (3, 7, 64), (1, 150, 1024), (5, 3, 32)])
+@pytest.mark.parametrize("B,N,C", [(2, 50, 512), (3, 7, 64), (1, 150, 1024), (5, 3, 32), (2, 8, 96), (3, 130, 64), (1, 256, 128), (1, 300, 64)])
 def test_pointnet_t_kernels(ops, B, N, C):
     """Layer-1 conv, BN+ELU apply, mean pool (+ group sums), pooled backward and BN backward in the T256 layout against
     explicit fp32 formulas (P = B*30*N is not a multiple of 256; odd N and N < 8 take the general paths)."""
