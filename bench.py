@@ -340,46 +340,67 @@ def run_b200(args):
         return r
 
     ops.gemm_tc = timed_gemm_tc
+    # CUDA-graph replay of the step (PCAATrainer.step_graphed): first call eager, second captures, then replays
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    stepfn = trainer.step_graphed if use_graph else trainer.step
 
     for i in range(args.warmup):
-        trainer.step(*devb[i % nb])
+        stepfn(*devb[i % nb])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     calls0 = _lib.CALLS
-    record["on"] = True
+    record["on"] = not use_graph
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for i in range(args.steps):
-        out = trainer.step(*devb[i % nb])
+        out = stepfn(*devb[i % nb])
     t1.record()
     barrier()
     record["on"] = False
-    launches = _lib.CALLS - calls0
+    launches = trainer.graph_launches(devb[0][0].shape) * args.steps if use_graph else _lib.CALLS - calls0
     clocks = sampler.stop() if rank == 0 else None
     ms = t0.elapsed_time(t1)
+    ms_eager = ms / args.steps
+    if use_graph:
+        # per-launch CUDA events cannot be read back from inside a replayed graph: the tensor-core GEMM launches are
+        # timed in an eager pass of the same step (same kernels, same inputs) right after the timed region
+        r_steps = max(1, min(args.steps, 5))
+        trainer.step(*devb[0])         # untimed: graph capture emptied the allocator cache, this refills it
+        barrier()
+        record["on"] = True
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for i in range(r_steps):
+            trainer.step(*devb[i % nb])
+        r1.record()
+        barrier()
+        record["on"] = False
+        ms_eager = r0.elapsed_time(r1) / r_steps
     tc_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in tc_events)
     tc_flops = sum(f for _, _, f in tc_events)
+    tc_steps = len(tc_events) / 9 if tc_events else 1
 
-    # ---- end-to-end through the public API with HOST buffers: H2D of the step inputs + D2H of the losses inside
+    # ---- end-to-end through the public API with HOST buffers: pinned host batch -> H2D (copy stream, one batch ahead,
+    # loader.DevicePrefetcher) -> train step -> D2H of the losses and predictions, host waits for them every step
+    from opensetgaitrecognition_pcaa_b200.loader import DevicePrefetcher
     res_host = torch.empty(5, dtype=torch.float32).pin_memory()
     pred_host = torch.empty(B, dtype=torch.int32).pin_memory()
     e2e_steps = args.steps
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(e2e_steps):
-        h = host[i % nb]
-        d = tuple(t.to(dev, non_blocking=True) for t in h)
-        out = trainer.step(*d)
+    feed = DevicePrefetcher((host[i % nb] for i in range(e2e_steps)), dev, depth=2)
+    for d in feed:
+        out = stepfn(*d)
         res_host.copy_(torch.stack([out["rec_loss"], out["d_loss"], out["gp"], out["loss_g"], out["sup_loss"]]), non_blocking=True)
         pred_host.copy_(out["pred"], non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the reference reads .item() every step (PCAA_ablation.py:1023-1030)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    h2d = feed.h2d_bytes // e2e_steps
     d2h = res_host.numel() * 4 + pred_host.numel() * 4
 
     if world > 1:
@@ -400,6 +421,7 @@ def run_b200(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"pcaa_variant4_train_step_N{NMAX}_C{NCLS}", "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "l2": "per-step activations (>10 GB) and 3 rotating input batches exceed the 126 MB L2",
+                   "launch": "cuda_graph_replay" if use_graph else "eager",
                    "losses_last_step": {k: float(out[k]) for k in ("rec_loss", "d_loss", "sup_loss", "loss_g")}},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / e2e_steps},
@@ -408,7 +430,9 @@ def run_b200(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("train", B, NMAX),
                      "kernel": "gemm_tc_kernel (tcgen05 PointNet fwd/dgrad/wgrad GEMMs)",
-                     "launches_timed": len(tc_events), "share_of_step": tc_ms / ms if ms else None, "peak_source": peak_src,
+                     "launches_timed": len(tc_events), "share_of_step": tc_ms / (ms_eager * tc_steps) if tc_events else None,
+                     "timed_in": ("eager pass after the timed region (CUDA events around each launch; %.3f ms/step eager)" % ms_eager)
+                     if use_graph else "the timed region", "peak_source": peak_src,
                      "whole_step_tensor_frac": (world * B * args.steps * 30 * NMAX * FLOP_PER_POINT_TC) / (ms * 1e-3) / 1e12 / (peak_tf * world)},
     }
     if world == 1 and not args.no_cpu:
@@ -435,6 +459,8 @@ def main():
     ap.add_argument("--nmax", type=int, default=NMAX, help="points per frame (train_pointsubsampling sweep: 50..150)")
     ap.add_argument("--k", type=int, default=6, help="voting window of the inference workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the train step from a CUDA graph (auto: on)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -227,6 +227,18 @@ int pcaa_disc_fwd(const float* x, const int64_t* labels, const float* W1, const 
  * when shadow_bf16 is non-null the updated parameter is also written there as bf16 (tensor-core operand copy). */
 int pcaa_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int step, float grad_scale, void* shadow_bf16, pcaa_stream stream);
+/* ---- batch assembly: the step before the path (MSRadarDataset.__getitem__ + default collate, datasets.py:466-479) ----
+ * dst[r, :] = src[idx[r], :] for rows of row_bytes bytes (a crop is one row of 4*30*nmax fp32): gathers a batch from a
+ * packed crop store resident in HBM.  row_bytes % 16 == 0; an index outside [0, n_src) gives a zero row. */
+int pcaa_gather_rows(const void* src, const int64_t* idx, void* dst, int64_t n_idx, int64_t row_bytes, int64_t n_src,
+                     pcaa_stream stream);
+/* CUDA-graph form of the same update: the step counter lives on the device.  pcaa_adam_advance increments
+ * step_dev[0] and writes coef_dev = { lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step) } (the bias corrections
+ * torch.optim.Adam computes on the host); pcaa_adam_flat_dev reads them, so a captured train step advances the
+ * optimizer on every replay. */
+int pcaa_adam_advance(int32_t* step_dev, float* coef_dev, float lr, float beta1, float beta2, pcaa_stream stream);
+int pcaa_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                       const float* coef_dev, float grad_scale, void* shadow_bf16, pcaa_stream stream);
 
 /* ---- open-set scoring, inference_PCAA.py:129-136, 255-271 ---------------------------------------------------
  * loglik[i] = log( (1/C) sum_c N(emb_i; mu_c, I_D) ) in float64 (log-domain restatement).

@@ -460,9 +460,38 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_
     }
 }
 
+// dst[r] = src[idx[r]] for rows of row_vec 16-byte words (batch assembly from an HBM-resident packed crop store);
+// grid (rows, splits).  An index outside [0, n_src) yields a zero row.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ src, const int64_t* __restrict__ idx, uint4* __restrict__ dst,
+                   int64_t row_vec, int64_t n_src) {
+    const int64_t r = blockIdx.x;
+    const int64_t s = idx[r];
+    const bool ok = s >= 0 && s < n_src;
+    const uint4* in = src + (ok ? s : 0) * row_vec;
+    uint4* out = dst + r * row_vec;
+    for (int64_t i = (int64_t)blockIdx.y * 256 + threadIdx.x; i < row_vec; i += (int64_t)gridDim.y * 256)
+        out[i] = ok ? __ldg(in + i) : make_uint4(0u, 0u, 0u, 0u);
+}
+
+// step += 1; coef = { lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step) }: the host-side arithmetic of pcaa_adam_flat on
+// a device-resident counter, so a captured CUDA graph of the train step advances the optimizer on every replay
+__global__ void adam_advance_kernel(int32_t* __restrict__ step, float* __restrict__ coef, float lr, float beta1, float beta2) {
+    const int s = step[0] + 1;
+    step[0] = s;
+    const double bc1 = 1.0 - pow((double)beta1, (double)s), bc2 = 1.0 - pow((double)beta2, (double)s);
+    coef[0] = (float)((double)lr / bc1);
+    coef[1] = (float)(1.0 / sqrt(bc2));
+}
+
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, int64_t n, float lr_bc1, float beta1, float beta2, float eps,
-                                 float inv_sqrt_bc2, float grad_scale, __nv_bfloat16* __restrict__ shadow) {
+                                 float inv_sqrt_bc2, float grad_scale, __nv_bfloat16* __restrict__ shadow,
+                                 const float* __restrict__ coef_dev) {
+    if (coef_dev) {                      // bias corrections of a device-resident step counter (CUDA-graph replay)
+        lr_bc1 = __ldg(coef_dev);
+        inv_sqrt_bc2 = __ldg(coef_dev + 1);
+    }
     int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (; i < n; i += stride) {
@@ -840,8 +869,39 @@ int pcaa_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, floa
     int64_t nthreads = (n + 3) / 4;
     adam_flat_kernel<<<ew_grid(nthreads), 256, 0, ST(stream)>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
                                                              (float)(1.0 / sqrt(bc2)), grad_scale,
-                                                             (__nv_bfloat16*)shadow_bf16);
+                                                             (__nv_bfloat16*)shadow_bf16, nullptr);
     return check_launch("adam_flat");
+}
+
+int pcaa_gather_rows(const void* src, const int64_t* idx, void* dst, int64_t n_idx, int64_t row_bytes, int64_t n_src,
+                     pcaa_stream stream) {
+    if (n_idx == 0 || row_bytes == 0) return PCAA_OK;
+    PCAA_REQUIRE(row_bytes % 16 == 0 && ((uintptr_t)src | (uintptr_t)dst) % 16 == 0, PCAA_ERR_ALIGN,
+                 "gather_rows: rows must be multiples of 16 bytes and 16-byte aligned (row_bytes=%lld)", (long long)row_bytes);
+    PCAA_REQUIRE(n_idx <= 0x7fffffffLL && n_src >= 0, PCAA_ERR_SHAPE, "gather_rows: bad row counts");
+    const int64_t row_vec = row_bytes / 16;
+    int splits = (int)((row_vec + 1023) / 1024);
+    if (splits > 64) splits = 64;
+    gather_rows_kernel<<<dim3((unsigned)n_idx, (unsigned)splits), 256, 0, ST(stream)>>>((const uint4*)src, idx, (uint4*)dst, row_vec, n_src);
+    return check_launch("gather_rows");
+}
+
+int pcaa_adam_advance(int32_t* step_dev, float* coef_dev, float lr, float beta1, float beta2, pcaa_stream stream) {
+    PCAA_REQUIRE(step_dev && coef_dev, PCAA_ERR_SHAPE, "adam_advance: null device pointers");
+    adam_advance_kernel<<<1, 1, 0, ST(stream)>>>(step_dev, coef_dev, lr, beta1, beta2);
+    return check_launch("adam_advance");
+}
+
+int pcaa_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                       const float* coef_dev, float grad_scale, void* shadow_bf16, pcaa_stream stream) {
+    if (n == 0) return PCAA_OK;
+    PCAA_REQUIRE(coef_dev != nullptr, PCAA_ERR_SHAPE, "adam_flat_dev: null coefficient pointer");
+    PCAA_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, PCAA_ERR_ALIGN,
+                 "adam: buffers must be 16-byte aligned");
+    int64_t nthreads = (n + 3) / 4;
+    adam_flat_kernel<<<ew_grid(nthreads), 256, 0, ST(stream)>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, 0.f, grad_scale,
+                                                             (__nv_bfloat16*)shadow_bf16, coef_dev);
+    return check_launch("adam_flat_dev");
 }
 
 int pcaa_ew(int op, const float* a, const float* b, float* out, int64_t n, int ncols, pcaa_stream stream) {

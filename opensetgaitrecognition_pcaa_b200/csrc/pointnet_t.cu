@@ -34,6 +34,26 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
     return u;
 }
 
+// packed fp32x2 helpers (sm_100 FFMA2 / FADD2: two fp32 lanes per instruction)
+__device__ __forceinline__ unsigned long long pk2f(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2f(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2f(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2f(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // 8 consecutive points p0 .. p0+7 of feature plane f of x (B, 4, TN) fp32; out-of-range points read as 0
 __device__ __forceinline__ void load_x8(const float* __restrict__ x, int64_t p0, int64_t P, int64_t TN, int f,
                                         float (&v)[8]) {
@@ -596,50 +616,66 @@ bn_elu_meanpool_staged_kernel(const __nv_bfloat16* __restrict__ yT, const float*
     const int64_t p0 = pt0 + 64 * q;
     int64_t g = p0 / n;
     int left = (int)((g + 1) * n - p0);                         // points of group g still ahead (warp-uniform)
-    float Sa = 0.f, Sd = 0.f, Su = 0.f;
+    // packed fp32x2 arithmetic (FFMA2 / FADD2): even points accumulate in the low halves, odd points in the high halves
+    unsigned long long Sa2 = 0ull, Sd2 = 0ull, Su2 = 0ull;
+    const unsigned long long sc2 = pk2f(sc, sc), sh2 = pk2f(sh, sh), scl2 = pk2f(scl, scl), shl2 = pk2f(shl, shl);
     const __nv_bfloat16* row = rows + chl * MPS_PITCH + 64 * q;
 
     auto flush = [&](int64_t grp) {
         if (grp < G) {
+            float lo, hi;
             float* a = acc + (size_t)(grp - g_first) * NV * MPS_CH + chl;
-            atomicAdd(a, Sa);
+            upk2f(Sa2, lo, hi);
+            atomicAdd(a, lo + hi);
             if (TRAIN) {
-                atomicAdd(a + MPS_CH, Sd);
-                atomicAdd(a + 2 * MPS_CH, Su);
+                upk2f(Sd2, lo, hi);
+                atomicAdd(a + MPS_CH, lo + hi);
+                upk2f(Su2, lo, hi);
+                atomicAdd(a + 2 * MPS_CH, lo + hi);
             }
         }
-        Sa = 0.f; Sd = 0.f; Su = 0.f;
+        Sa2 = 0ull; Sd2 = 0ull; Su2 = 0ull;
     };
-    auto accum = [&](float y) {
+    // two points at once: w holds bf16 (point 2i | point 2i+1 << 16); mlo / mhi = 1.f or 0.f select the halves
+    auto accum2 = [&](uint32_t w, bool use_lo, bool use_hi) {
+        const float ylo = __uint_as_float(w << 16), yhi = __uint_as_float(w & 0xffff0000u);
+        const unsigned long long y2 = pk2f(ylo, yhi);
         if (APPLY) {
-            const float z = fmaf(y, sc, sh);
-            const float d = fminf(ex2_fast(fmaf(y, scl, shl)), 1.f);
-            Sa += fmaxf(z, 0.f);
+            float zl, zh, al, ah;
+            upk2f(fma2f(y2, sc2, sh2), zl, zh);
+            upk2f(fma2f(y2, scl2, shl2), al, ah);
+            float dl = fminf(ex2_fast(al), 1.f), dh = fminf(ex2_fast(ah), 1.f);
+            float rl = fmaxf(zl, 0.f), rh = fmaxf(zh, 0.f);
+            if (!use_lo) { dl = 0.f; rl = 0.f; }
+            if (!use_hi) { dh = 0.f; rh = 0.f; }
+            const unsigned long long d2 = pk2f(dl, dh);
+            Sa2 = add2f(Sa2, pk2f(rl, rh));
             if (TRAIN) {
-                Sd += d;
-                Su = fmaf(d, y, Su);
+                Sd2 = add2f(Sd2, d2);
+                Su2 = fma2f(d2, y2, Su2);
             } else {
-                Sa += d;
+                Sa2 = add2f(Sa2, d2);
             }
         } else {
-            Sa += y;
+            Sa2 = add2f(Sa2, pk2f(use_lo ? ylo : 0.f, use_hi ? yhi : 0.f));
         }
     };
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
-        float y[8];
-        unpack8(*reinterpret_cast<const uint4*>(row + 8 * k), y);
+        const uint4 u = *reinterpret_cast<const uint4*>(row + 8 * k);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
         if (left > 8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) accum(y[j]);
+            for (int j = 0; j < 4; ++j) accum2(w[j], true, true);
             left -= 8;
         } else {
             // n >= 8: at most one group boundary per chunk (after element left - 1)
 #pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                accum(y[0]);
-#pragma unroll
-                for (int i = 0; i < 7; ++i) y[i] = y[i + 1];
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t wj = j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
+                accum2(wj, true, false);
+                if (--left == 0) { flush(g); ++g; left = n; }
+                accum2(wj, false, true);
                 if (--left == 0) { flush(g); ++g; left = n; }
             }
         }
@@ -743,13 +779,20 @@ pool_bwd_apply_rows_kernel(const float* __restrict__ dpool, const __nv_bfloat16*
         const float a1 = __ldg(c1 + c) * inv_n, a2 = __ldg(c2 + c), a3 = __ldg(c3 + c);
         const float scl = sc * LOG2E_F, shl = sh * LOG2E_F;
         const float gb = a1 * g1v[i], gd = a1 * g0v[i] - gb;          // gv_j = gb + wsel_j * gd
+        // ELU'(z) = min(2^(z log2 e), 1): no select, z itself is not needed; packed fp32x2 arithmetic, two points per
+        // instruction (FFMA2)
+        const unsigned long long scl2 = pk2f(scl, scl), shl2 = pk2f(shl, shl), gd2 = pk2f(gd, gd), gb2 = pk2f(gb, gb);
+        const unsigned long long a22 = pk2f(a2, a2), a32 = pk2f(a3, a3);
+        const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
         float y[8];
-        unpack8(raw[i], y);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float d = elu_grad_l2(fmaf(y[j], sc, sh), fmaf(y[j], scl, shl));
-            const float gv = fmaf(wsel[j], gd, gb);
-            y[j] = fmaf(gv, d, fmaf(a2, y[j], a3));
+        for (int j = 0; j < 4; ++j) {
+            const unsigned long long y2 = pk2f(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u));
+            float al, ah;
+            upk2f(fma2f(y2, scl2, shl2), al, ah);
+            const unsigned long long d2 = pk2f(fminf(ex2_fast(al), 1.f), fminf(ex2_fast(ah), 1.f));
+            const unsigned long long gv2 = fma2f(pk2f(wsel[2 * j], wsel[2 * j + 1]), gd2, gb2);
+            upk2f(fma2f(gv2, d2, fma2f(a22, y2, a32)), y[2 * j], y[2 * j + 1]);
         }
         if (!full_tile) {
 #pragma unroll

@@ -455,6 +455,27 @@ def adam_flat(p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0, shadow=None):
     call("pcaa_adam_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale, _p(shadow), _s())
 
 
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = src[idx[r]] along dim 0 (idx int64 on the device); rows must be multiples of 16 bytes."""
+    _chk(src), _chk(idx, torch.int64)
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+    row_bytes = src[0].numel() * src.element_size() if src.shape[0] else 0
+    call("pcaa_gather_rows", _p(src), _p(idx), _p(out), n, row_bytes, src.shape[0], _s())
+    return out
+
+
+def adam_advance(step_dev, coef_dev, lr, b1, b2):
+    """step_dev (int32[1]) += 1 and coef_dev (float32[2]) = Adam's bias-corrected step sizes, on the device."""
+    _chk(step_dev, torch.int32), _chk(coef_dev, torch.float32)
+    call("pcaa_adam_advance", _p(step_dev), _p(coef_dev), lr, b1, b2, _s())
+
+
+def adam_flat_dev(p, g, m, v, b1, b2, eps, coef_dev, grad_scale=1.0, shadow=None):
+    call("pcaa_adam_flat_dev", _p(p), _p(g), _p(m), _p(v), p.numel(), b1, b2, eps, _p(coef_dev), grad_scale, _p(shadow), _s())
+
+
 def openset_score(emb, means):
     _chk(emb, torch.float32), _chk(means, torch.float32)
     M, D = emb.shape

@@ -41,8 +41,21 @@ class _Flat:
             o, n, shp = self.slices[name]
             self.p[o:o + n].copy_(t.detach().reshape(-1))
             t.data = self.p[o:o + n].view(shp)          # the module parameter now aliases the flat buffer
-        self.step = 0
+        # Adam step count: authoritative copy on the device (advanced by pcaa_adam_advance inside the step, so a replayed
+        # CUDA graph keeps counting), host mirror for bookkeeping; assigning .step sets both
+        self.step_dev = torch.zeros(1, device=device, dtype=torch.int32)
+        self.coef_dev = torch.zeros(2, device=device, dtype=torch.float32)
+        self._step = 0
         self.shadow = None
+
+    @property
+    def step(self) -> int:
+        return self._step
+
+    @step.setter
+    def step(self, n: int) -> None:
+        self._step = int(n)
+        self.step_dev.fill_(int(n))
 
     def make_shadow(self):
         """bf16 copy of the whole flat parameter buffer (same indexing); kept current by the fused Adam kernel."""
@@ -97,6 +110,8 @@ class PCAATrainer:
         # BatchNorm-backward passes (engine.pointnet_backward).  Off by default: measured on B200 the step is power
         # capped (sw_power_cap, ~1.6-1.7 GHz under load) and the overlap buys nothing (21.99 vs 22.07 ms at B=256).
         self._wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("PCAA_WGRAD_OVERLAP", "0") == "1" else None
+        self._graphs: Dict = {}
+        self._warm = set()
 
     def _refresh_views(self):
         enc_t = {k: v for k, v in self.enc.named_parameters()}
@@ -153,8 +168,9 @@ class PCAATrainer:
         d_losses = ops.wgangp_dstep(fv, z0, self.means, gt, alphas.reshape(-1), *self.Dw, cfg["GP_WEIGHT"], self.Dg)
         self.xD.start(0, self.D.size)
         self.xD.finish()
-        self.D.step += 1
-        ops.adam_flat(self.D.p, self.D.g, self.D.m, self.D.v, cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, self.D.step, gscale)
+        ops.adam_advance(self.D.step_dev, self.D.coef_dev, cfg["LR"], cfg["B1"], cfg["B2"])
+        self.D._step += 1
+        ops.adam_flat_dev(self.D.p, self.D.g, self.D.m, self.D.v, cfg["B1"], cfg["B2"], 1e-8, self.D.coef_dev, gscale)
         # ---- generator step (PCAA_ablation.py:985-1021)
         h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
         wb = self._decoder_weights_bf16()
@@ -174,12 +190,13 @@ class PCAATrainer:
                                dx_out=dfv, dx_acc=True)
         # decoder-side gradients (99 % of the bytes) are final: reduce them AND apply their Adam update (HBM bound) on
         # the side stream while the encoder backward (tensor bound) runs on this one
-        self.G.step += 1
+        ops.adam_advance(self.G.step_dev, self.G.coef_dev, cfg["LR"], cfg["B1"], cfg["B2"])
+        self.G._step += 1
 
         def adam_span(lo, hi):
             G = self.G
-            ops.adam_flat(G.p[lo:hi], G.g[lo:hi], G.m[lo:hi], G.v[lo:hi], cfg["LR"], cfg["B1"], cfg["B2"], 1e-8, G.step,
-                          gscale, G.shadow[lo:hi])
+            ops.adam_flat_dev(G.p[lo:hi], G.g[lo:hi], G.m[lo:hi], G.v[lo:hi], cfg["B1"], cfg["B2"], 1e-8, G.coef_dev,
+                              gscale, G.shadow[lo:hi])
         self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
         engine.encoder_backward(dlogits, dfv, saved, self.P_E, self.gb_E, side=self._wgrad_stream)
         self.xG.start(*self._enc_span)
@@ -187,6 +204,58 @@ class PCAATrainer:
         adam_span(*self._enc_span)
         return {"rec_loss": rec_loss, "d_loss": d_losses[0], "gp": d_losses[1], "loss_g": loss_g, "sup_loss": sup_loss,
                 "pred": pred, "logits": logits, "fv": fv}
+
+    # ------------------------------------------------------------------------------------------------------------
+    def step_graphed(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """`step` replayed from a CUDA graph (one graph per input shape).  The ~200 launches of an iteration become one
+        graph launch: no per-kernel host cost, back-to-back kernel scheduling on the device -- what the launch-bound
+        small-batch configurations need.  The first call with a new shape runs eagerly (it also initialises the
+        library's per-kernel attributes), the second one captures; every call performs exactly one training iteration.
+        Inputs are copied into the graph's static buffers unless they already are those buffers (`static_inputs`).
+        The returned tensors are graph-owned: read them before the next call."""
+        key = (tuple(pcs.shape), tuple(z0.shape))
+        gs = self._graphs.get(key)
+        if gs is None:
+            if key not in self._warm:
+                self._warm.add(key)
+                return self.step(pcs, gt, z0, alphas)
+            gs = self._capture(key, (pcs, gt, z0, alphas))
+        for dst, src in zip(gs["in"], (pcs, gt, z0, alphas)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        gs["graph"].replay()
+        self.G._step += 1
+        self.D._step += 1
+        return gs["out"]
+
+    def static_inputs(self, pcs_shape, z0_shape=None):
+        """The captured graph's input buffers (pcs, gt, z0, alphas) for this shape, or None before capture: a loader can
+        copy host batches straight into them (no device-to-device staging copy)."""
+        B = pcs_shape[0]
+        gs = self._graphs.get((tuple(pcs_shape), tuple(z0_shape or (B, self.means.shape[1]))))
+        return None if gs is None else gs["in"]
+
+    def _capture(self, key, example):
+        from . import _lib
+        static_in = tuple(torch.empty_like(t) for t in example)
+        for d, s_ in zip(static_in, example):
+            d.copy_(s_)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        gstep, dstep, calls0 = self.G._step, self.D._step, _lib.CALLS
+        with torch.cuda.graph(g):
+            out = self.step(*static_in)
+        self.G._step, self.D._step = gstep, dstep             # capture enqueued the kernels, it did not run them
+        gs = {"graph": g, "in": static_in, "out": out, "launches": _lib.CALLS - calls0}
+        self._graphs[key] = gs
+        return gs
+
+    def graph_launches(self, pcs_shape) -> int:
+        """C-ABI kernel launches inside the captured graph of this input shape (0 before capture)."""
+        for k, gs in self._graphs.items():
+            if k[0] == tuple(pcs_shape):
+                return gs["launches"]
+        return 0
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()

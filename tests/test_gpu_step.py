@@ -170,6 +170,58 @@ def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
     assert nbad / ntot < 0.10, nbad / ntot
 
 
+def test_graphed_step_is_the_eager_step():
+    """PCAATrainer.step_graphed (CUDA-graph replay, device-resident Adam step counter) performs exactly the iteration
+    PCAATrainer.step performs.  Two trainers, four iterations (eager / capture + replay / replay / replay) on the same
+    batches; before every iteration the graphed trainer's state is set to the eager one's, so each comparison is of
+    ONE iteration from identical weights (atomically accumulated statistics and split-K sums leave a few ulp of
+    run-to-run drift, which a bf16 rounding flip or Adam's lr*sign(g) on a near-zero gradient can amplify)."""
+    from opensetgaitrecognition_pcaa_b200.train import PCAATrainer
+    B, nmax, C, seed = 4, 50, 2, 3
+    p = O.det_params(C, nmax, seed)
+    means = O.sample_distant_points(32, C, 10, 10).float()
+    trs = []
+    for _ in range(2):
+        enc, dec, dis, gph = build(p, C, nmax)
+        trs.append((PCAATrainer(enc, dec, dis, gph, means, CFG), enc))
+    (ta, ea), (tb, eb) = trs
+    rng = np.random.default_rng(5)
+    lr = CFG["LR"]
+    for s in range(4):
+        for fa, fb in ((ta.G, tb.G), (ta.D, tb.D)):
+            fb.p.copy_(fa.p), fb.m.copy_(fa.m), fb.v.copy_(fa.v)
+        tb.G.shadow.copy_(ta.G.shadow)
+        for ba, bb in zip(ea.buffers(), eb.buffers()):
+            bb.copy_(ba)
+        before = ta.G.p.clone()
+        pcs, gt = O.synth_batch(B, nmax, C, seed=100 + s)
+        z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float().cuda()
+        al = torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32)).cuda()
+        oa = ta.step(pcs.cuda(), gt.cuda(), z0, al)
+        ob = tb.step_graphed(pcs.cuda(), gt.cuda(), z0, al)
+        torch.cuda.synchronize()
+        for k in ("rec_loss", "d_loss", "gp", "sup_loss", "loss_g"):
+            assert abs(float(ob[k]) - float(oa[k])) <= 1e-4 * max(1.0, abs(float(oa[k]))), (s, k, float(ob[k]), float(oa[k]))
+        for k in ("fv", "logits"):
+            assert relmax(ob[k], oa[k]) < 1e-3, (s, k, relmax(ob[k], oa[k]))
+        top2 = oa["logits"].topk(2, dim=1).values
+        decided = (top2[:, 0] - top2[:, 1]) > 2e-2 * float(oa["logits"].abs().max())
+        assert torch.equal(oa["pred"][decided], ob["pred"][decided])
+        # the update itself: same Adam step size (a wrong step count would change lr / (1 - beta1^t) by a large factor)
+        for fa, fb in ((ta.G, tb.G), (ta.D, tb.D)):
+            d = (fa.p - fb.p).abs()
+            assert float(d.max()) <= 2 * lr * 1.01 and float((d > 5e-6).float().mean()) < 0.02, (s, float(d.max()))
+        moved = (ta.G.p - before).abs()
+        assert 0.5 * lr < float(moved.max()) <= lr * 1.5           # |Adam update| ~ lr: bias corrections applied
+    assert tb.graph_launches((B, 4, 30, nmax)) > 100 and tb.G.step == ta.G.step == 4 and tb.D.step == 4
+    assert int(tb.G.step_dev) == 4 and int(tb.D.step_dev) == 4 and int(ta.G.step_dev) == 4
+    sd = eb.state_dict()
+    assert int(sd["pc_block.pointnet1.module.1.num_batches_tracked"]) == 4
+    # the graph's input buffers can be filled directly
+    ins = tb.static_inputs((B, 4, 30, nmax))
+    assert ins is not None and ins[0].shape == (B, 4, 30, nmax)
+
+
 def test_module_autograd_path_matches_oracle():
     """The nn.Module surface driven the way the reference trainer drives it (stock autograd, torch.optim.Adam,
     autograd.grad(create_graph=True) through the critic)."""
