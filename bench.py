@@ -341,7 +341,7 @@ def run_b200(args):
 
     ops.gemm_tc = timed_gemm_tc
     # CUDA-graph replay of the step (PCAATrainer.step_graphed): first call eager, second captures, then replays
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    use_graph = args.graph != "off"
     stepfn = trainer.step_graphed if use_graph else trainer.step
 
     for i in range(args.warmup):

@@ -112,6 +112,9 @@ class PCAATrainer:
         self._wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("PCAA_WGRAD_OVERLAP", "0") == "1" else None
         self._graphs: Dict = {}
         self._warm = set()
+        # data-parallel: never capture a collective (kernel phases -> graphs, exchanges eager in between);
+        # PCAA_SPLIT_GRAPHS=1 forces that program structure on one rank (tests)
+        self.split_graphs = self.world > 1 or os.environ.get("PCAA_SPLIT_GRAPHS", "0") == "1"
 
     def _refresh_views(self):
         enc_t = {k: v for k, v in self.enc.named_parameters()}
@@ -150,69 +153,106 @@ class PCAATrainer:
         return wb
 
     # ------------------------------------------------------------------------------------------------------------
-    def step(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """One variant-4 iteration.  pcs (B,4,30,N) fp32, gt (B,) int64, z0 (B,32) ~ N(0,1) and alphas (B,1) ~ U(0,1)
-        are the host RNG draws of PCAA_ablation.py:915-931, 944-948 (already on the device).  Returns device scalars."""
+    def _phases(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor):
+        """One variant-4 iteration as an ordered list of (kind, fn): "kernels" phases only enqueue C-ABI kernels (and
+        torch fills) on the current stream, "exchange" phases are the data-parallel gradient exchanges (NCCL all-reduce,
+        on the side stream for the generator spans, each followed by the Adam update of its span).  Running them in
+        order IS the step; the split exists so that step_graphed can capture the kernel phases into CUDA graphs and
+        keep the collectives outside of them.  Returns (phases, st) -- st["out"] holds the result dict afterwards."""
         cfg = self.cfg
         B = pcs.shape[0]
         S = pcs.shape[1] * pcs.shape[2] * pcs.shape[3]
         gscale = 1.0 / self.world
-        self.enc.train(), self.dec.train(), self.dis.train()
-        # ---- encoder forward (train-mode BatchNorm; running statistics updated in place)
-        logits, fv, saved = engine.encoder_forward(pcs, self.P_E, True, self.enc.use_projection_head, self._enc_wb16,
-                                                   self._tcn_wb16)
-        for t in self._nbt:
-            t.add_(1)
-        # ---- critic step (PCAA_ablation.py:900-980), one fused kernel + Adam
-        self.D.g.zero_()
-        d_losses = ops.wgangp_dstep(fv, z0, self.means, gt, alphas.reshape(-1), *self.Dw, cfg["GP_WEIGHT"], self.Dg)
-        self.xD.start(0, self.D.size)
-        self.xD.finish()
-        ops.adam_advance(self.D.step_dev, self.D.coef_dev, cfg["LR"], cfg["B1"], cfg["B2"])
-        self.D._step += 1
-        ops.adam_flat_dev(self.D.p, self.D.g, self.D.m, self.D.v, cfg["B1"], cfg["B2"], 1e-8, self.D.coef_dev, gscale)
-        # ---- generator step (PCAA_ablation.py:985-1021)
-        h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
-        wb = self._decoder_weights_bf16()
-        rec, acts = engine.decoder_forward_tc(h0, self.P_G, wb)
-        rec4 = rec.view(pcs.shape)
-        frame_loss, i1, i2 = ops.chamfer_fwd(rec4, pcs)
-        rec_loss = ops.chamfer_reduce(frame_loss, True)
-        drec = ops.chamfer_bwd(rec4, pcs, i1, i2, self._one, True)
-        adv = -float(cfg["ADV_WEIGHT"]) / B
-        _, dfv, loss_g = ops.disc_fwd(fv, gt, *self.Dw, self.C, want_out=False, want_dx=True, dx_scale=adv,
-                                      want_sum=True, out_scale=adv)           # critic already updated (:996)
-        sup_loss, dlogits, pred = ops.softmax_ce(logits, gt, want_grad=True)
-        # backward: Chamfer -> decoder -> projection head -> (+ adversarial) -> encoder
-        G_unused: Dict[str, torch.Tensor] = {}
-        dh0, _ = engine.decoder_backward_tc(drec.view(B, S), acts, self.P_G, wb, self.gb_G)
-        engine.linear_backward(dh0, fv, h0, self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused, self.gb_GPH,
-                               dx_out=dfv, dx_acc=True)
-        # decoder-side gradients (99 % of the bytes) are final: reduce them AND apply their Adam update (HBM bound) on
-        # the side stream while the encoder backward (tensor bound) runs on this one
-        ops.adam_advance(self.G.step_dev, self.G.coef_dev, cfg["LR"], cfg["B1"], cfg["B2"])
-        self.G._step += 1
+        st: Dict = {}
 
         def adam_span(lo, hi):
             G = self.G
             ops.adam_flat_dev(G.p[lo:hi], G.g[lo:hi], G.m[lo:hi], G.v[lo:hi], cfg["B1"], cfg["B2"], 1e-8, G.coef_dev,
                               gscale, G.shadow[lo:hi])
-        self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
-        engine.encoder_backward(dlogits, dfv, saved, self.P_E, self.gb_E, side=self._wgrad_stream)
-        self.xG.start(*self._enc_span)
-        self.xG.finish()
-        adam_span(*self._enc_span)
-        return {"rec_loss": rec_loss, "d_loss": d_losses[0], "gp": d_losses[1], "loss_g": loss_g, "sup_loss": sup_loss,
-                "pred": pred, "logits": logits, "fv": fv}
+
+        def encoder_and_critic():
+            self.enc.train(), self.dec.train(), self.dis.train()
+            # encoder forward (train-mode BatchNorm; running statistics updated in place)
+            st["logits"], st["fv"], st["saved"] = engine.encoder_forward(pcs, self.P_E, True, self.enc.use_projection_head,
+                                                                         self._enc_wb16, self._tcn_wb16)
+            for t in self._nbt:
+                t.add_(1)
+            # critic step (PCAA_ablation.py:900-980): one fused kernel forms d_loss and its parameter gradients
+            self.D.g.zero_()
+            st["d_losses"] = ops.wgangp_dstep(st["fv"], z0, self.means, gt, alphas.reshape(-1), *self.Dw, cfg["GP_WEIGHT"], self.Dg)
+
+        def exchange_critic():
+            self.xD.start(0, self.D.size)
+            self.xD.finish()
+
+        def generator_forward_and_decoder_backward():
+            fv, logits = st["fv"], st["logits"]
+            ops.adam_advance(self.D.step_dev, self.D.coef_dev, cfg["LR"], cfg["B1"], cfg["B2"])
+            ops.adam_flat_dev(self.D.p, self.D.g, self.D.m, self.D.v, cfg["B1"], cfg["B2"], 1e-8, self.D.coef_dev, gscale)
+            # generator step (PCAA_ablation.py:985-1021)
+            h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
+            wb = self._decoder_weights_bf16()
+            rec, acts = engine.decoder_forward_tc(h0, self.P_G, wb)
+            rec4 = rec.view(pcs.shape)
+            frame_loss, i1, i2 = ops.chamfer_fwd(rec4, pcs)
+            st["rec_loss"] = ops.chamfer_reduce(frame_loss, True)
+            drec = ops.chamfer_bwd(rec4, pcs, i1, i2, self._one, True)
+            adv = -float(cfg["ADV_WEIGHT"]) / B
+            _, st["dfv"], st["loss_g"] = ops.disc_fwd(fv, gt, *self.Dw, self.C, want_out=False, want_dx=True, dx_scale=adv,
+                                                      want_sum=True, out_scale=adv)           # critic already updated (:996)
+            st["sup_loss"], st["dlogits"], st["pred"] = ops.softmax_ce(logits, gt, want_grad=True)
+            # backward: Chamfer -> decoder -> projection head (+ adversarial gradient)
+            G_unused: Dict[str, torch.Tensor] = {}
+            dh0, _ = engine.decoder_backward_tc(drec.view(B, S), acts, self.P_G, wb, self.gb_G)
+            engine.linear_backward(dh0, fv, h0, self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused, self.gb_GPH,
+                                   dx_out=st["dfv"], dx_acc=True)
+            ops.adam_advance(self.G.step_dev, self.G.coef_dev, cfg["LR"], cfg["B1"], cfg["B2"])
+
+        def exchange_decoder_span():
+            # decoder-side gradients (99 % of the bytes) are final: reduce them AND apply their Adam update (HBM bound)
+            # on the side stream while the encoder backward (tensor bound) runs on the main one
+            self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
+
+        def encoder_backward():
+            engine.encoder_backward(st["dlogits"], st["dfv"], st["saved"], self.P_E, self.gb_E, side=self._wgrad_stream)
+
+        def exchange_encoder_span():
+            self.xG.start(*self._enc_span)
+            self.xG.finish()
+
+        def encoder_update():
+            adam_span(*self._enc_span)
+            st["out"] = {"rec_loss": st["rec_loss"], "d_loss": st["d_losses"][0], "gp": st["d_losses"][1],
+                         "loss_g": st["loss_g"], "sup_loss": st["sup_loss"], "pred": st["pred"], "logits": st["logits"],
+                         "fv": st["fv"]}
+            st.pop("saved", None)
+
+        return [("kernels", encoder_and_critic), ("exchange", exchange_critic),
+                ("kernels", generator_forward_and_decoder_backward), ("exchange", exchange_decoder_span),
+                ("kernels", encoder_backward), ("exchange", exchange_encoder_span), ("kernels", encoder_update)], st
+
+    def step(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """One variant-4 iteration.  pcs (B,4,30,N) fp32, gt (B,) int64, z0 (B,32) ~ N(0,1) and alphas (B,1) ~ U(0,1)
+        are the host RNG draws of PCAA_ablation.py:915-931, 944-948 (already on the device).  Returns device scalars."""
+        phases, st = self._phases(pcs, gt, z0, alphas)
+        for _, fn in phases:
+            fn()
+        self.D._step += 1
+        self.G._step += 1
+        return st["out"]
 
     # ------------------------------------------------------------------------------------------------------------
     def step_graphed(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """`step` replayed from a CUDA graph (one graph per input shape).  The ~200 launches of an iteration become one
-        graph launch: no per-kernel host cost, back-to-back kernel scheduling on the device -- what the launch-bound
-        small-batch configurations need.  The first call with a new shape runs eagerly (it also initialises the
-        library's per-kernel attributes), the second one captures; every call performs exactly one training iteration.
-        Inputs are copied into the graph's static buffers unless they already are those buffers (`static_inputs`).
-        The returned tensors are graph-owned: read them before the next call."""
+        """`step` replayed from CUDA graphs (captured once per input shape).  The ~200 launches of an iteration become
+        one graph launch: no per-kernel host cost, back-to-back kernel scheduling on the device -- what the launch-bound
+        small-batch configurations need.  With one rank the whole iteration is ONE graph (the side-stream Adam update
+        is a fork inside it); data-parallel, the kernel phases between the gradient exchanges are four graphs that
+        share a memory pool and the NCCL all-reduces (+ the decoder span's Adam update on the side stream) are issued
+        eagerly between their replays, so no collective is ever captured.
+        The first call with a new shape runs eagerly (it also initialises the library's per-kernel attributes), the
+        second one captures; every call performs exactly one training iteration.  Inputs are copied into the graphs'
+        static buffers unless they already are those buffers (`static_inputs`).  The returned tensors are graph-owned:
+        read them before the next call."""
         key = (tuple(pcs.shape), tuple(z0.shape))
         gs = self._graphs.get(key)
         if gs is None:
@@ -223,7 +263,11 @@ class PCAATrainer:
         for dst, src in zip(gs["in"], (pcs, gt, z0, alphas)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        gs["graph"].replay()
+        for kind, item in gs["program"]:
+            if kind == "graph":
+                item.replay()
+            else:
+                item()
         self.G._step += 1
         self.D._step += 1
         return gs["out"]
@@ -241,12 +285,27 @@ class PCAATrainer:
         for d, s_ in zip(static_in, example):
             d.copy_(s_)
         torch.cuda.synchronize(self.dev)
-        g = torch.cuda.CUDAGraph()
-        gstep, dstep, calls0 = self.G._step, self.D._step, _lib.CALLS
-        with torch.cuda.graph(g):
-            out = self.step(*static_in)
-        self.G._step, self.D._step = gstep, dstep             # capture enqueued the kernels, it did not run them
-        gs = {"graph": g, "in": static_in, "out": out, "launches": _lib.CALLS - calls0}
+        calls0 = _lib.CALLS
+        phases, st = self._phases(*static_in)
+        program = []
+        if not self.split_graphs:
+            # the exchanges are no collectives here, only the fork / join of the side-stream Adam update: one graph
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _, fn in phases:
+                    fn()
+            program.append(("graph", g))
+        else:
+            pool = torch.cuda.graph_pool_handle()
+            for kind, fn in phases:
+                if kind == "kernels":
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):      # capture enqueues the kernels, it does not run them
+                        fn()
+                    program.append(("graph", g))
+                else:
+                    program.append(("exchange", fn))          # issued eagerly between the replays
+        gs = {"program": program, "in": static_in, "out": st["out"], "launches": _lib.CALLS - calls0, "state": st}
         self._graphs[key] = gs
         return gs
 

@@ -170,7 +170,8 @@ def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
     assert nbad / ntot < 0.10, nbad / ntot
 
 
-def test_graphed_step_is_the_eager_step():
+@pytest.mark.parametrize("split", [False, True])
+def test_graphed_step_is_the_eager_step(split):
     """PCAATrainer.step_graphed (CUDA-graph replay, device-resident Adam step counter) performs exactly the iteration
     PCAATrainer.step performs.  Two trainers, four iterations (eager / capture + replay / replay / replay) on the same
     batches; before every iteration the graphed trainer's state is set to the eager one's, so each comparison is of
@@ -185,6 +186,9 @@ def test_graphed_step_is_the_eager_step():
         enc, dec, dis, gph = build(p, C, nmax)
         trs.append((PCAATrainer(enc, dec, dis, gph, means, CFG), enc))
     (ta, ea), (tb, eb) = trs
+    # split: the data-parallel program structure (four kernel-phase graphs, gradient exchanges issued eagerly between
+    # their replays) on one rank
+    tb.split_graphs = split
     rng = np.random.default_rng(5)
     lr = CFG["LR"]
     for s in range(4):
@@ -214,6 +218,8 @@ def test_graphed_step_is_the_eager_step():
         moved = (ta.G.p - before).abs()
         assert 0.5 * lr < float(moved.max()) <= lr * 1.5           # |Adam update| ~ lr: bias corrections applied
     assert tb.graph_launches((B, 4, 30, nmax)) > 100 and tb.G.step == ta.G.step == 4 and tb.D.step == 4
+    prog = tb._graphs[((B, 4, 30, nmax), (B, 32))]["program"]
+    assert [k for k, _ in prog] == (["graph", "exchange"] * 3 + ["graph"] if split else ["graph"])
     assert int(tb.G.step_dev) == 4 and int(tb.D.step_dev) == 4 and int(ta.G.step_dev) == 4
     sd = eb.state_dict()
     assert int(sd["pc_block.pointnet1.module.1.num_batches_tracked"]) == 4
