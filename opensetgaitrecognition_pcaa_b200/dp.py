@@ -17,6 +17,8 @@ Everything here is backend-agnostic host logic (``nccl`` on the B200 box, ``gloo
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -55,6 +57,9 @@ def global_draws(global_batch: int, latent_dim: int, rank: int, world: int, np_r
     return z0[s:e].contiguous(), alphas[s:e].contiguous()
 
 
+_SKIP_EXCHANGE = os.environ.get("PCAA_DP_SKIP_EXCHANGE", "0") == "1"
+
+
 class GradExchange:
     """Sum-all-reduce of spans of a flat gradient buffer, overlappable with the kernels that follow.
 
@@ -84,6 +89,10 @@ class GradExchange:
                 then()
             return
         buf = self.flat[lo:hi]
+        if _SKIP_EXCHANGE and self.world > 1:          # timing probe only (wrong numerics): measures what the collective costs
+            if then is not None:
+                then()
+            return
         if self._stream is not None:
             ev = torch.cuda.Event()
             ev.record()

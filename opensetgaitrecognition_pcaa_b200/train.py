@@ -18,7 +18,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import dp, engine, ops
-from ._lib import ACT_ELU
+from ._lib import ACT_ELU, EW_ADD
 
 
 class _Flat:
@@ -76,11 +76,21 @@ class _Flat:
 class PCAATrainer:
     """encoder/decoder/discriminator: the drop-in modules of models.py (CUDA, fp32).
 
-    config keys (reference constants.CONFIG): LR, B1, B2, GP_WEIGHT, ADV_WEIGHT.
+    config keys (reference constants.CONFIG): LR, B1, B2, GP_WEIGHT, ADV_WEIGHT; optional B2_G = second Adam beta of
+    optimizer_G (train_variant3 passes betas=(B1, B1), PCAA_ablation.py:452-456).
+
+    The same step serves three of the reference's loops (fixed prototypes `means`, SeqChamfer + WGAN-GP + CE):
+      * variant 4, the paper's PCAA (PCAA_ablation.py:746-1100): encoder with projection head, decoder behind the
+        32->64 `decoder_projection_head`;
+      * variant 2 = train_CGAAE (train_AAE.py:25-364): `decoder_projection_head=None`, the decoder reads sup_fv;
+      * variant 3 (PCAA_ablation.py:392-743): `decoder=None`, no reconstruction term.
+    (Variant 1's learned prototypes, PCAA_ablation.py:28-378, run through the nn.Module surface: models.GaussianMeanLearner.)
     """
 
     def __init__(self, encoder, decoder, discriminator, decoder_projection_head, means: torch.Tensor, config: dict,
                  process_group=None):
+        if decoder is None and decoder_projection_head is not None:
+            raise ValueError("PCAATrainer: a decoder projection head needs a decoder")
         self.enc, self.dec, self.dis, self.gph = encoder, decoder, discriminator, decoder_projection_head
         dev = next(encoder.parameters()).device
         if dev.type != "cuda":
@@ -94,11 +104,14 @@ class PCAATrainer:
         # ---- flat generator-side parameters: optimizer_G chain order (PCAA_ablation.py:821-826); the decoder's bn1-4
         # never receive a gradient (models.py:373-385), torch.optim.Adam skips them -> they stay outside the flat range
         named = [("E." + k, p) for k, p in encoder.named_parameters()]
-        named += [("GPH." + k, p) for k, p in decoder_projection_head.named_parameters()]
-        named += [("G." + k, p) for k, p in decoder.named_parameters() if k.startswith("dense")]
+        if decoder_projection_head is not None:
+            named += [("GPH." + k, p) for k, p in decoder_projection_head.named_parameters()]
+        if decoder is not None:
+            named += [("G." + k, p) for k, p in decoder.named_parameters() if k.startswith("dense")]
         self.G = _Flat(named, dev)
         self.D = _Flat([("D." + k, p) for k, p in discriminator.named_parameters()], dev)
-        self._dec_span = self.G.span([n for n in self.G.names if n.startswith("G.") or n.startswith("GPH.")])
+        dec_names = [n for n in self.G.names if n.startswith("G.") or n.startswith("GPH.")]
+        self._dec_span = self.G.span(dec_names) if dec_names else None
         self._enc_span = self.G.span([n for n in self.G.names if n.startswith("E.")])
         self.G.make_shadow()
         self._refresh_views()
@@ -120,11 +133,11 @@ class PCAATrainer:
         enc_t = {k: v for k, v in self.enc.named_parameters()}
         enc_t.update({k: v for k, v in self.enc.named_buffers()})
         self.P_E = enc_t
-        self.P_G = {k: v for k, v in self.dec.named_parameters()}
-        self.P_GPH = {k: v for k, v in self.gph.named_parameters()}
+        self.P_G = {k: v for k, v in self.dec.named_parameters()} if self.dec is not None else {}
+        self.P_GPH = {k: v for k, v in self.gph.named_parameters()} if self.gph is not None else {}
         self.gb_E = {k: self.G.view(self.G.g, "E." + k) for k, _ in self.enc.named_parameters()}
-        self.gb_G = {k: self.G.view(self.G.g, "G." + k) for k, _ in self.dec.named_parameters() if k.startswith("dense")}
-        self.gb_GPH = {k: self.G.view(self.G.g, "GPH." + k) for k, _ in self.gph.named_parameters()}
+        self.gb_G = {k: self.G.view(self.G.g, "G." + k) for k in self.P_G if k.startswith("dense")}
+        self.gb_GPH = {k: self.G.view(self.G.g, "GPH." + k) for k in self.P_GPH}
         self.Dw = [self.D.view(self.D.p, f"D.model.{i}.{s}") for i in (0, 2, 4) for s in ("weight", "bias")]
         self.Dg = [self.D.view(self.D.g, f"D.model.{i}.{s}") for i in (0, 2, 4) for s in ("weight", "bias")]
         self._nbt = [v for k, v in self.enc.named_buffers() if k.endswith("num_batches_tracked")]
@@ -139,7 +152,7 @@ class PCAATrainer:
             W = self.P_E[f"tc_block.dtc{l}.conv1d.weight"]
             self._tcn_wb16[l] = self.G.view(self.G.shadow, f"E.tc_block.dtc{l}.conv1d.weight").view(W.shape[0], W.shape[1] * 3)
         self._dec_shadow = {}
-        for l in range(1, 6):
+        for l in range(1, 6) if self.dec is not None else ():
             W = self.P_G[f"dense{l}.weight"]
             if W.shape[1] % 8 == 0:
                 self._dec_shadow[l] = self.G.view(self.G.shadow, f"G.dense{l}.weight")
@@ -163,15 +176,18 @@ class PCAATrainer:
         B = pcs.shape[0]
         S = pcs.shape[1] * pcs.shape[2] * pcs.shape[3]
         gscale = 1.0 / self.world
+        b2_g = cfg.get("B2_G", cfg["B2"])
         st: Dict = {}
 
         def adam_span(lo, hi):
             G = self.G
-            ops.adam_flat_dev(G.p[lo:hi], G.g[lo:hi], G.m[lo:hi], G.v[lo:hi], cfg["B1"], cfg["B2"], 1e-8, G.coef_dev,
+            ops.adam_flat_dev(G.p[lo:hi], G.g[lo:hi], G.m[lo:hi], G.v[lo:hi], cfg["B1"], b2_g, 1e-8, G.coef_dev,
                               gscale, G.shadow[lo:hi])
 
         def encoder_and_critic():
-            self.enc.train(), self.dec.train(), self.dis.train()
+            self.enc.train(), self.dis.train()
+            if self.dec is not None:
+                self.dec.train()
             # encoder forward (train-mode BatchNorm; running statistics updated in place)
             st["logits"], st["fv"], st["saved"] = engine.encoder_forward(pcs, self.P_E, True, self.enc.use_projection_head,
                                                                          self._enc_wb16, self._tcn_wb16)
@@ -190,28 +206,35 @@ class PCAATrainer:
             ops.adam_advance(self.D.step_dev, self.D.coef_dev, cfg["LR"], cfg["B1"], cfg["B2"])
             ops.adam_flat_dev(self.D.p, self.D.g, self.D.m, self.D.v, cfg["B1"], cfg["B2"], 1e-8, self.D.coef_dev, gscale)
             # generator step (PCAA_ablation.py:985-1021)
-            h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
-            wb = self._decoder_weights_bf16()
-            rec, acts = engine.decoder_forward_tc(h0, self.P_G, wb)
-            rec4 = rec.view(pcs.shape)
-            frame_loss, i1, i2 = ops.chamfer_fwd(rec4, pcs)
-            st["rec_loss"] = ops.chamfer_reduce(frame_loss, True)
-            drec = ops.chamfer_bwd(rec4, pcs, i1, i2, self._one, True)
             adv = -float(cfg["ADV_WEIGHT"]) / B
             _, st["dfv"], st["loss_g"] = ops.disc_fwd(fv, gt, *self.Dw, self.C, want_out=False, want_dx=True, dx_scale=adv,
                                                       want_sum=True, out_scale=adv)           # critic already updated (:996)
             st["sup_loss"], st["dlogits"], st["pred"] = ops.softmax_ce(logits, gt, want_grad=True)
-            # backward: Chamfer -> decoder -> projection head (+ adversarial gradient)
-            G_unused: Dict[str, torch.Tensor] = {}
-            dh0, _ = engine.decoder_backward_tc(drec.view(B, S), acts, self.P_G, wb, self.gb_G)
-            engine.linear_backward(dh0, fv, h0, self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused, self.gb_GPH,
-                                   dx_out=st["dfv"], dx_acc=True)
-            ops.adam_advance(self.G.step_dev, self.G.coef_dev, cfg["LR"], cfg["B1"], cfg["B2"])
+            if self.dec is None:                                 # variant 3: tot = loss_g + sup (PCAA_ablation.py:640)
+                st["rec_loss"] = torch.zeros((), device=self.dev, dtype=torch.float32)
+            else:
+                h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU) if self.gph is not None else fv
+                wb = self._decoder_weights_bf16()
+                rec, acts = engine.decoder_forward_tc(h0, self.P_G, wb)
+                rec4 = rec.view(pcs.shape)
+                frame_loss, i1, i2 = ops.chamfer_fwd(rec4, pcs)
+                st["rec_loss"] = ops.chamfer_reduce(frame_loss, True)
+                drec = ops.chamfer_bwd(rec4, pcs, i1, i2, self._one, True)
+                # backward: Chamfer -> decoder -> projection head (+ adversarial gradient)
+                G_unused: Dict[str, torch.Tensor] = {}
+                dh0, _ = engine.decoder_backward_tc(drec.view(B, S), acts, self.P_G, wb, self.gb_G)
+                if self.gph is not None:
+                    engine.linear_backward(dh0, fv, h0, self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused, self.gb_GPH,
+                                           dx_out=st["dfv"], dx_acc=True)
+                else:                                            # train_CGAAE: the decoder reads sup_fv (train_AAE.py:243)
+                    st["dfv"] = ops.ew(EW_ADD, st["dfv"], dh0)
+            ops.adam_advance(self.G.step_dev, self.G.coef_dev, cfg["LR"], cfg["B1"], b2_g)
 
         def exchange_decoder_span():
             # decoder-side gradients (99 % of the bytes) are final: reduce them AND apply their Adam update (HBM bound)
             # on the side stream while the encoder backward (tensor bound) runs on the main one
-            self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
+            if self._dec_span is not None:
+                self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
 
         def encoder_backward():
             engine.encoder_backward(st["dlogits"], st["dfv"], st["saved"], self.P_E, self.gb_E, side=self._wgrad_stream)
@@ -320,14 +343,40 @@ class PCAATrainer:
     @torch.no_grad()
     def evaluate(self, pcs: torch.Tensor, gt: torch.Tensor):
         """Validation pass of PCAA_ablation.py:1046-1064: eval-mode encoder, decoder, Chamfer, CE, argmax."""
-        self.enc.eval(), self.dec.eval()
+        self.enc.eval()
         logits, fv, _ = engine.encoder_forward(pcs, self.P_E, False, self.enc.use_projection_head, self._enc_wb16,
                                               self._tcn_wb16)
-        h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU)
+        ce, _, pred = ops.softmax_ce(logits, gt, want_grad=False)
+        if self.dec is None:
+            return torch.zeros((), device=self.dev), ce, pred
+        self.dec.eval()
+        h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU) if self.gph is not None else fv
         rec, _ = engine.decoder_forward_tc(h0, self.P_G, self._decoder_weights_bf16())
         fl, _, _ = ops.chamfer_fwd(rec.view(pcs.shape), pcs, want_idx=False)
-        ce, _, pred = ops.softmax_ce(logits, gt, want_grad=False)
         return ops.chamfer_reduce(fl, True), ce, pred
+
+
+def build_variant(variant: int, n_classes: int, nmax: int, config: Optional[dict] = None, device="cuda",
+                  seed: Optional[int] = None, process_group=None):
+    """Construct the networks of ablation variant 2 (= train_CGAAE, train_AAE.py:36-46), 3 (PCAA_ablation.py:407-419) or
+    4 (PCAA_ablation.py:764-786) as the reference does and wrap them in a PCAATrainer."""
+    from . import models, utils
+    if variant == 4:
+        return build_variant4(n_classes, nmax, config, device, seed, process_group)
+    if variant not in (2, 3):
+        raise ValueError("build_variant: the fused trainer covers variants 2, 3 and 4 (variant 1: nn.Module surface)")
+    if seed is not None:
+        torch.manual_seed(seed)
+    cfg = dict(LR=1e-4, B1=0.9, B2=0.99, GP_WEIGHT=15, ADV_WEIGHT=1, SUP_LATENT_DIM=32)
+    if config:
+        cfg.update(config)
+    if variant == 3:
+        cfg.setdefault("B2_G", cfg["B1"])                       # optimizer_G betas=(B1, B1), PCAA_ablation.py:452-456
+    enc = models.CGEncoder(n_out_labels=n_classes, use_projection_head=False, nmax_points=nmax).to(device).float()
+    dec = models.CGDecoder(input_dim=cfg["SUP_LATENT_DIM"], nmax_points=nmax).to(device).float() if variant == 2 else None
+    dis = models.CGDiscriminator(n_classes).to(device).float()
+    means = utils.sample_distant_points(cfg["SUP_LATENT_DIM"], n_classes, 10, 10).float()
+    return PCAATrainer(enc, dec, dis, None, means, cfg, process_group)
 
 
 def build_variant4(n_classes: int, nmax: int, config: Optional[dict] = None, device="cuda", seed: Optional[int] = None,

@@ -39,12 +39,15 @@ def split_state(p, prefix):
     return {k[len(prefix):]: v.clone() for k, v in p.items() if k.startswith(prefix)}
 
 
-def build_reference_models(models, p, C, nmax):
-    enc = models.CGEncoder(n_out_labels=C, use_projection_head=True, nmax_points=nmax).float()
-    dec = models.CGDecoder(input_dim=64, nmax_points=nmax).float()
+def build_reference_models(models, p, C, nmax, variant=4):
+    """variant 4: PCAA_ablation.py:764-786; variants 2 / 3: train_AAE.py:36-46, PCAA_ablation.py:407-419 (encoder
+    without projection head, decoder fed by sup_fv; the unused heads are still built here and never stepped)."""
+    head = variant == 4
+    enc = models.CGEncoder(n_out_labels=C, use_projection_head=head, nmax_points=nmax).float()
+    dec = models.CGDecoder(input_dim=64 if head else 32, nmax_points=nmax).float()
     dis = models.CGDiscriminator(C).float()
-    gph = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ELU()).float()
-    dph = torch.nn.Sequential(torch.nn.Linear(64, 32), torch.nn.ELU()).float()
+    gph = torch.nn.Sequential(torch.nn.Linear(32, 64 if head else 32), torch.nn.ELU()).float()
+    dph = torch.nn.Sequential(torch.nn.Linear(64 if head else 32, 32), torch.nn.ELU()).float()
     enc.load_state_dict(split_state(p, "E."))
     dec.load_state_dict(split_state(p, "G."))
     dis.load_state_dict(split_state(p, "D."))
@@ -160,9 +163,10 @@ def module_case(constants, models, utils, name, B, nmax, C, seed):
     assert max(v for k, v in pins.items() if "idx" not in k) < 5e-4, pins
 
 
-def reference_step(constants, mods, opts, pcs, gt, z0, alphas, means, C):
-    """One variant-4 iteration with the reference's own modules, in the order of
-    PCAA_ablation.py:882-1021 (driver written for this generator; arithmetic is the reference's)."""
+def reference_step(constants, mods, opts, pcs, gt, z0, alphas, means, C, variant=4):
+    """One iteration with the reference's own modules, in the order of PCAA_ablation.py:882-1021 (variant 4),
+    train_AAE.py:126-290 (variant 2) or PCAA_ablation.py:500-660 (variant 3) (driver written for this generator;
+    arithmetic is the reference's)."""
     enc, dec, dis, gph, dph = mods
     optG, optD = opts
     out = {}
@@ -188,14 +192,18 @@ def reference_step(constants, mods, opts, pcs, gt, z0, alphas, means, C):
     optD.step()
     optD.zero_grad(); dis.zero_grad()
     optG.zero_grad(); enc.zero_grad(); dec.zero_grad(); gph.zero_grad()
-    rec = dec(gph(fv))
-    rec_loss = utils_mod.SeqChamferLoss()(rec, pcs)
     loss_g = -torch.mean(dis(fv, oh)) * CFG["ADV_WEIGHT"]
     sup = torch.nn.CrossEntropyLoss()(logits, gt)
-    tot = rec_loss + loss_g + sup
+    if variant == 3:
+        rec, rec_loss = torch.zeros(()), torch.zeros(())
+        tot = loss_g + sup
+    else:
+        rec = dec(gph(fv)) if variant == 4 else dec(fv)
+        rec_loss = utils_mod.SeqChamferLoss()(rec, pcs)
+        tot = rec_loss + loss_g + sup
     tot.backward()
     gg = {}
-    for pre, m in (("E.", enc), ("GPH.", gph), ("G.", dec)):
+    for pre, m in {4: (("E.", enc), ("GPH.", gph), ("G.", dec)), 2: (("E.", enc), ("G.", dec)), 3: (("E.", enc),)}[variant]:
         for k, v in m.named_parameters():
             gg[pre + k] = None if v.grad is None else v.grad.detach().clone()
     out["g_grads"] = gg
@@ -205,15 +213,22 @@ def reference_step(constants, mods, opts, pcs, gt, z0, alphas, means, C):
     return out
 
 
-def step_case(constants, models, utils, name, B, nmax, C, seed, nsteps=2):
+def step_case(constants, models, utils, name, B, nmax, C, seed, nsteps=2, variant=4):
     import itertools
-    p0 = O.det_params(C, nmax, seed)
-    mods = build_reference_models(models, p0, C, nmax)
+    p0 = O.det_params(C, nmax, seed) if variant == 4 else O.det_params(C, nmax, seed, use_projection_head=False, dec_in=32)
+    mods = build_reference_models(models, p0, C, nmax, variant)
     enc, dec, dis, gph, dph = mods
-    optG = torch.optim.Adam(itertools.chain(enc.parameters(), gph.parameters(), dec.parameters()),
-                            lr=CFG["LR"], betas=(CFG["B1"], CFG["B2"]))
-    optD = torch.optim.Adam(itertools.chain(dph.parameters(), dis.parameters()), lr=CFG["LR"],
-                            betas=(CFG["B1"], CFG["B2"]))
+    if variant == 4:        # PCAA_ablation.py:821-833
+        optG = torch.optim.Adam(itertools.chain(enc.parameters(), gph.parameters(), dec.parameters()),
+                                lr=CFG["LR"], betas=(CFG["B1"], CFG["B2"]))
+        optD = torch.optim.Adam(itertools.chain(dph.parameters(), dis.parameters()), lr=CFG["LR"],
+                                betas=(CFG["B1"], CFG["B2"]))
+    elif variant == 2:      # train_AAE.py:82-93
+        optG = torch.optim.Adam(itertools.chain(enc.parameters(), dec.parameters()), lr=CFG["LR"], betas=(CFG["B1"], CFG["B2"]))
+        optD = torch.optim.Adam(itertools.chain(dis.parameters()), lr=CFG["LR"], betas=(CFG["B1"], CFG["B2"]))
+    else:                   # PCAA_ablation.py:452-462: optimizer_G betas are (B1, B1)
+        optG = torch.optim.Adam(itertools.chain(enc.parameters()), lr=CFG["LR"], betas=(CFG["B1"], CFG["B1"]))
+        optD = torch.optim.Adam(itertools.chain(dis.parameters()), lr=CFG["LR"], betas=(CFG["B1"], CFG["B2"]))
     means = utils.sample_distant_points(32, C, 10, 10).float()
     means_o = O.sample_distant_points(32, C, 10, 10).float()
     assert maxdiff(means, means_o) == 0.0
@@ -227,8 +242,8 @@ def step_case(constants, models, utils, name, B, nmax, C, seed, nsteps=2):
         pcs, gt = O.synth_batch(B, nmax, C, seed=4321 + 10 * seed + s)
         z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float()
         alphas = torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32))
-        r = reference_step(constants, mods, (optG, optD), pcs, gt, z0, alphas, means, C)
-        o = O.train_step_variant4(po, ost, pcs, gt, z0, alphas, means, cfg)
+        r = reference_step(constants, mods, (optG, optD), pcs, gt, z0, alphas, means, C, variant)
+        o = O.train_step(po, ost, pcs, gt, z0, alphas, means, cfg, variant)
         for k in ("d_loss", "gp", "rec_loss", "loss_g", "sup_loss", "tot_loss"):
             g[f"s{s}:{k}"] = np.float64(r[k])
             pins[f"s{s}:{k}"] = abs(float(r[k]) - float(o[k]))
@@ -264,7 +279,7 @@ def step_case(constants, models, utils, name, B, nmax, C, seed, nsteps=2):
         pins[f"s{s}:param_frac_off"] = nbad / ntot
     for k, v in pins.items():
         g["pin_" + k] = np.float64(v)
-    np.savez_compressed(os.path.join(GOLD, f"step_{name}.npz"), B=B, nmax=nmax, C=C, seed=seed, nsteps=nsteps, **g)
+    np.savez_compressed(os.path.join(GOLD, f"step_{name}.npz"), B=B, nmax=nmax, C=C, seed=seed, nsteps=nsteps, variant=variant, **g)
     print(f"[step_{name}] pins:", {k: f"{v:.2e}" for k, v in pins.items()})
     # conv biases under BatchNorm have a mathematically-zero gradient (fp noise only); Adam turns that
     # noise into +-lr steps, so post-step params may differ by up to nsteps*lr there.
@@ -519,10 +534,16 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     constants, models, utils_mod = load_reference()
+    if "--variants-only" in sys.argv:          # just the variant-2 / variant-3 step vectors
+        step_case(constants, models, utils_mod, "v2_n50_c2_b4", 4, 50, 2, seed=5, variant=2)
+        step_case(constants, models, utils_mod, "v3_n50_c4_b4", 4, 50, 4, seed=6, variant=3)
+        sys.exit(0)
     module_case(constants, models, utils_mod, "n50_c2_b4", 4, 50, 2, seed=0)
     module_case(constants, models, utils_mod, "n70_c4_b3", 3, 70, 4, seed=1)
     step_case(constants, models, utils_mod, "n50_c2_b4", 4, 50, 2, seed=0)
     step_case(constants, models, utils_mod, "n150_c4_b2", 2, 150, 4, seed=2, nsteps=1)
+    step_case(constants, models, utils_mod, "v2_n50_c2_b4", 4, 50, 2, seed=5, variant=2)
+    step_case(constants, models, utils_mod, "v3_n50_c4_b4", 4, 50, 4, seed=6, variant=3)
     scoring_case()
     procedure_case()
     w, frac = trainer_pin(constants, models, utils_mod)

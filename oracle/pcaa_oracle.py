@@ -16,6 +16,7 @@ algorithm of the reference (rmazzier/OpenSetGaitRecognition_PCAA):
 * sequence Chamfer loss                                        utils.py:98-132
 * prototype sampler                                            utils.py:216-251
 * variant-4 (paper PCAA) train step                            PCAA_ablation.py:882-1021
+* variant-2 (base train_CGAAE) / variant-3 (no decoder) steps  train_AAE.py:126-290, PCAA_ablation.py:500-660
 * open-set likelihood, ROC/Youden threshold, k-window vote     inference_PCAA.py:129-136, 225-231, 239-314
 
 Parity pin: the reference has no tests or golden vectors, so
@@ -281,16 +282,26 @@ def trainable_names(p: Params, prefixes) -> List[str]:
     return [k for pre in prefixes for k in p if k.startswith(pre) and not is_buffer(k)]
 
 
-def train_step_variant4(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict,
-                        clone_leaves: bool = True) -> dict:
-    """One iteration of the paper-PCAA loop, PCAA_ablation.py:882-1021 (in place on ``p``).
+def train_step(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict, variant: int = 4,
+               clone_leaves: bool = True) -> dict:
+    """One training iteration of the reference's AAE loops (in place on ``p``):
 
-    cfg: LR, B1, B2, GP_WEIGHT, ADV_WEIGHT, NMAX.  ``z0`` (B,32) and ``alphas`` (B,1) are the
-    host RNG draws of PCAA_ablation.py:915-931 / 944-948.  Returns losses, the
-    class predictions and every gradient (by name).
+    * variant 4 -- the paper's PCAA, ``PCAA_ablation.py:882-1021``: encoder with projection head, decoder fed by
+      the 32->64 decoder projection head;
+    * variant 2 -- the base ``train_CGAAE`` loop, ``train_AAE.py:126-290`` (= ``train_variant2``,
+      ``PCAA_ablation.py:381-389``): encoder without projection head, ``CGDecoder()`` fed by ``sup_fv`` directly;
+    * variant 3 -- no decoder, ``PCAA_ablation.py:500-660``: ``tot = loss_g + sup``, and optimizer_G uses
+      ``betas=(B1, B1)`` (``PCAA_ablation.py:452-456``).
+
+    cfg: LR, B1, B2, GP_WEIGHT, ADV_WEIGHT, NMAX.  ``z0`` (B,32) and ``alphas`` (B,1) are the host RNG draws of
+    PCAA_ablation.py:915-931 / 944-948.  Returns losses, the class predictions and every gradient (by name).
     """
+    assert variant in (2, 3, 4)
     C = means.shape[0]
     nmax = cfg["NMAX"]
+    head = variant == 4
+    g_prefixes = {4: G_PREFIXES, 2: ("E.", "G."), 3: ("E.",)}[variant]
+    b2_g = cfg["B1"] if variant == 3 else cfg["B2"]
     out: dict = {}
     # leaf copies that require grad (clone_leaves=False: differentiate the stored tensors in place -- what the
     # reference's own modules do; used by the timed CPU baseline to avoid an 861 MB copy per step)
@@ -301,7 +312,7 @@ def train_step_variant4(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, 
     q = dict(p)
     q.update(leaves)
     upd: dict = {}
-    logits, fv = encoder_forward(q, pcs, True, True, upd)
+    logits, fv = encoder_forward(q, pcs, True, head, upd)
     out["logits"], out["fv"] = logits.detach(), fv.detach()
     out["pred"] = torch.argmax(torch.softmax(logits.detach(), dim=1), dim=1)
     onehot = torch.nn.functional.one_hot(gt, C).float()
@@ -323,25 +334,35 @@ def train_step_variant4(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, 
             q[n] = p[n].detach().clone().requires_grad_(True)
 
     # ---- generator step
-    rec = decoder_forward(q, proj_head_forward(q, fv), nmax)
-    rec_loss, i1, i2 = chamfer(rec, pcs)
     loss_g = -disc_forward(q, fv, onehot).mean() * cfg["ADV_WEIGHT"]
     sup = cross_entropy(logits, gt)
-    tot = rec_loss + loss_g + sup
-    g_names = trainable_names(p, G_PREFIXES)
+    if variant == 3:
+        rec_loss = torch.zeros(())
+        tot = loss_g + sup
+    else:
+        rec = decoder_forward(q, proj_head_forward(q, fv) if variant == 4 else fv, nmax)
+        rec_loss, i1, i2 = chamfer(rec, pcs)
+        tot = rec_loss + loss_g + sup
+        out.update(rec=rec.detach(), idx_gt_for_pred=i1, idx_pred_for_gt=i2)
+    g_names = trainable_names(p, g_prefixes)
     g_grads = torch.autograd.grad(tot, [q[n] for n in g_names], allow_unused=True)
-    out.update(rec_loss=rec_loss.detach(), loss_g=loss_g.detach(), sup_loss=sup.detach(), tot_loss=tot.detach(),
-               rec=rec.detach(), idx_gt_for_pred=i1, idx_pred_for_gt=i2)
+    out.update(rec_loss=rec_loss.detach(), loss_g=loss_g.detach(), sup_loss=sup.detach(), tot_loss=tot.detach())
     out["g_grads"] = {n: (None if g is None else g.detach()) for n, g in zip(g_names, g_grads)}
     with torch.no_grad():
         adam_update([p[n] for n in g_names], list(g_grads), opt_state.setdefault("G", [dict() for _ in g_names]),
-                    cfg["LR"], cfg["B1"], cfg["B2"])
+                    cfg["LR"], cfg["B1"], b2_g)
         for k, v in upd.items():
             p[k] = v
         for k in p:
             if k.endswith("num_batches_tracked") and k.startswith("E."):
                 p[k] = p[k] + 1
     return out
+
+
+def train_step_variant4(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict,
+                        clone_leaves: bool = True) -> dict:
+    """The paper-PCAA iteration, PCAA_ablation.py:882-1021 (see train_step)."""
+    return train_step(p, opt_state, pcs, gt, z0, alphas, means, cfg, 4, clone_leaves)
 
 
 # --------------------------------------------------------------------------- #

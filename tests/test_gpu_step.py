@@ -42,15 +42,18 @@ def relnorm(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def build(p, C, nmax):
+def build(p, C, nmax, variant=4):
+    """The networks of ablation variant 4 (PCAA_ablation.py:764-786), 2 (train_AAE.py:36-46: no projection heads, the
+    decoder reads sup_fv) or 3 (PCAA_ablation.py:407-419: no decoder), loaded from reference-keyed parameters."""
     from opensetgaitrecognition_pcaa_b200 import models
-    enc = models.CGEncoder(n_out_labels=C, use_projection_head=True, nmax_points=nmax)
-    dec = models.CGDecoder(input_dim=64, nmax_points=nmax)
+    enc = models.CGEncoder(n_out_labels=C, use_projection_head=variant == 4, nmax_points=nmax)
+    dec = models.CGDecoder(input_dim=64 if variant == 4 else 32, nmax_points=nmax) if variant != 3 else None
     dis = models.CGDiscriminator(C)
-    gph = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ELU())
+    gph = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ELU()) if variant == 4 else None
     for pre, m in (("E.", enc), ("G.", dec), ("D.", dis), ("GPH.", gph)):
-        m.load_state_dict({k[len(pre):]: v.clone() for k, v in p.items() if k.startswith(pre)})   # reference keys
-        m.cuda().float()
+        if m is not None:
+            m.load_state_dict({k[len(pre):]: v.clone() for k, v in p.items() if k.startswith(pre)})   # reference keys
+            m.cuda().float()
     return enc, dec, dis, gph
 
 
@@ -107,27 +110,32 @@ def test_modules_vs_reference_golden(golden_dir, name):
     assert relmax(P, O.pairwise_dist(pcs, rec.cpu())) < 1e-5
 
 
-def _oracle_step(p, ost, pcs, gt, z0, alphas, means, nmax):
-    return O.train_step_variant4(p, ost, pcs, gt, z0, alphas, means, dict(CFG, NMAX=nmax))
+def _oracle_step(p, ost, pcs, gt, z0, alphas, means, nmax, variant=4):
+    return O.train_step(p, ost, pcs, gt, z0, alphas, means, dict(CFG, NMAX=nmax), variant)
 
 
-@pytest.mark.parametrize("name", ["n50_c2_b4", "n150_c4_b2"])
+@pytest.mark.parametrize("name", ["n50_c2_b4", "n150_c4_b2", "v2_n50_c2_b4", "v3_n50_c4_b4"])
 def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
+    """The fused trainer against the oracle and the reference's golden values: variant 4 (the paper's PCAA), variant 2
+    (= train_CGAAE, the decoder reads sup_fv) and variant 3 (no decoder, optimizer_G betas (B1, B1))."""
     from opensetgaitrecognition_pcaa_b200.train import PCAATrainer
     gd = np.load(os.path.join(golden_dir, f"step_{name}.npz"))
     B, nmax, C, seed, nsteps = (int(gd[k]) for k in ("B", "nmax", "C", "seed", "nsteps"))
-    p = O.det_params(C, nmax, seed)
+    variant = int(gd["variant"]) if "variant" in gd.files else 4
+    p = O.det_params(C, nmax, seed) if variant == 4 else O.det_params(C, nmax, seed, use_projection_head=False, dec_in=32)
+    if variant != 4:
+        p = {k: v for k, v in p.items() if not k.startswith(("GPH.", "DPH.")) and not (variant == 3 and k.startswith("G."))}
     po = {k: v.clone() for k, v in p.items()}
-    enc, dec, dis, gph = build(p, C, nmax)
+    enc, dec, dis, gph = build(p, C, nmax, variant)
     means = torch.from_numpy(gd["means"])
-    tr = PCAATrainer(enc, dec, dis, gph, means, CFG)
+    tr = PCAATrainer(enc, dec, dis, gph, means, dict(CFG, B2_G=CFG["B1"]) if variant == 3 else CFG)
     ost = {}
     rng = np.random.default_rng(999 + seed)
     for s in range(nsteps):
         pcs, gt = O.synth_batch(B, nmax, C, seed=4321 + 10 * seed + s)
         z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float()
         alphas = torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32))
-        ref = _oracle_step(po, ost, pcs, gt, z0, alphas, means, nmax)
+        ref = _oracle_step(po, ost, pcs, gt, z0, alphas, means, nmax, variant)
         out = tr.step(pcs.cuda(), gt.cuda(), z0.cuda(), alphas.cuda())
         torch.cuda.synchronize()
         # losses: oracle and the reference's golden values
@@ -155,7 +163,7 @@ def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
     lr = CFG["LR"]
     nbad = ntot = 0
     for pre, m in (("E.", enc), ("G.", dec), ("D.", dis), ("GPH.", gph)):
-        for k, v in m.state_dict().items():
+        for k, v in (m.state_dict().items() if m is not None else ()):
             if not v.dtype.is_floating_point:
                 assert int(v) == int(po[pre + k]), k
                 continue

@@ -83,11 +83,14 @@ def test_modules_oracle_vs_reference_golden(golden_dir, name):
             assert int(gd[k]) == 0, k
 
 
-def test_train_step_oracle_vs_reference_golden(golden_dir):
-    """Two variant-4 iterations (PCAA_ablation.py:882-1021) at B=4, N=50, C=2: losses, embeddings, gradient digests."""
-    gd = np.load(os.path.join(golden_dir, "step_n50_c2_b4.npz"))
+@pytest.mark.parametrize("name", ["n50_c2_b4", "v2_n50_c2_b4", "v3_n50_c4_b4"])
+def test_train_step_oracle_vs_reference_golden(golden_dir, name):
+    """Two iterations of the variant-4 (PCAA_ablation.py:882-1021), variant-2 (train_AAE.py:126-290) and variant-3
+    (PCAA_ablation.py:500-660) loops at B=4, N=50: losses, embeddings, gradient digests."""
+    gd = np.load(os.path.join(golden_dir, f"step_{name}.npz"))
+    variant = int(gd["variant"]) if "variant" in gd.files else 4
     B, nmax, C, seed, nsteps = (int(gd[k]) for k in ("B", "nmax", "C", "seed", "nsteps"))
-    p = O.det_params(C, nmax, seed)
+    p = O.det_params(C, nmax, seed) if variant == 4 else O.det_params(C, nmax, seed, use_projection_head=False, dec_in=32)
     means = torch.from_numpy(gd["means"])
     assert maxdiff(O.sample_distant_points(32, C, 10, 10).float(), means) == 0.0
     ost = {}
@@ -96,7 +99,7 @@ def test_train_step_oracle_vs_reference_golden(golden_dir):
         pcs, gt = O.synth_batch(B, nmax, C, seed=4321 + 10 * seed + s)
         z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float()
         alphas = torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32))
-        o = O.train_step_variant4(p, ost, pcs, gt, z0, alphas, means, dict(CFG, NMAX=nmax))
+        o = O.train_step(p, ost, pcs, gt, z0, alphas, means, dict(CFG, NMAX=nmax), variant)
         for k in ("d_loss", "gp", "rec_loss", "loss_g", "sup_loss", "tot_loss"):
             want = float(gd[f"s{s}:{k}"])
             assert abs(float(o[k]) - want) < 2e-3 * max(1.0, abs(want)), (s, k, float(o[k]), want)
