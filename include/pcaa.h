@@ -57,7 +57,8 @@ int pcaa_gemm_simt(const void* A, int a_dtype, int64_t sam, int64_t sak,
  * A [M,K] (lda), W [N,K] (ldw), out [M,N] (ldo); all bf16, leading dims multiples of 8 elements. */
 typedef enum { PCAA_TC_BIAS_STATS = 0, PCAA_TC_BIAS_ELU = 1, PCAA_TC_PLAIN = 2, PCAA_TC_DGRAD_ELUBN = 3,
                PCAA_TC_WGRAD_ACC = 4, PCAA_TC_DGRAD_ELUOUT = 5, PCAA_TC_WGRAD_STORE = 6,
-               PCAA_TC_T_BIAS_STATS = 7, PCAA_TC_T_AFFINE_ELU = 8, PCAA_TC_T_DGRAD_ELUBN = 9 } pcaa_tc_mode;
+               PCAA_TC_T_BIAS_STATS = 7, PCAA_TC_T_AFFINE_ELU = 8, PCAA_TC_T_DGRAD_ELUBN = 9,
+               PCAA_TC_T_AFFINE_ELU_POOL = 10 } pcaa_tc_mode;
 /* operand storage: PCAA_OP_K     A(m,k) at A[m*lda + k]  (B(n,k) at B[n*ldb + k]),  "K-major"
  *                  PCAA_OP_MN    A(m,k) at A[k*lda + m]  (B(n,k) at B[k*ldb + n]),  "MN-major"
  *                  PCAA_OP_T256_* the channel-major activation format of the PointNet path: element (channel c, point p)
@@ -78,9 +79,13 @@ typedef enum { PCAA_OP_K = 0, PCAA_OP_MN = 1, PCAA_OP_T256_K = 2, PCAA_OP_T256_M
  *                         (forward of models.py:21-29: A = W [Cout,Cin], B = aT [Cin,P] read MN-major)
  *   PCAA_TC_T_AFFINE_ELU  out[m,n] = ELU(scale[m]*(acc + bias[m]) + shift[m])  (eval mode: BatchNorm with running
  *                         statistics applied in the epilogue -> the next layer's activation in one pass)
+ *   PCAA_TC_T_AFFINE_ELU_POOL  the same activation, mean-pooled over groups of ldo consecutive points in the epilogue
+ *                         (models.py:242-243, 282 fused into the last shared-MLP layer of the eval forward): out is
+ *                         fp32 [N / ldo, M] (out_dtype PCAA_F32, ldo >= 32, ldo | N), zeroed by the call; the [M, N]
+ *                         activation is never written
  *   PCAA_TC_T_DGRAD_ELUBN out[m,n] = acc * ELU'(scale[m]*yprev[m,n] + shift[m]); stats += [sum dz, sum dz*xhat]
  *                         (A = W read MN-major = W^T, B = dyT [Cout,P] MN-major; yprev = yT of the previous layer)
- * Instantiated layouts (a,b): (K,K) modes 0-4, 6; (K,MN) 2, 5; (MN,MN) 4, 6; (K,T256_MN) 7, 8; (MN,T256_MN) 9;
+ * Instantiated layouts (a,b): (K,K) modes 0-4, 6; (K,MN) 2, 5; (MN,MN) 4, 6; (K,T256_MN) 7, 8, 10; (MN,T256_MN) 9;
  * (T256_K,T256_K) 4 (PointNet weight gradient, k = points). */
 int pcaa_gemm_tc(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* out, int64_t ldo,
                  int out_dtype, int64_t M, int64_t N, int64_t K, int mode, const float* bias, double* stats,

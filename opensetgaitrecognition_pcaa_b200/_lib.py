@@ -14,7 +14,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_ELU = 0, 1
 EW_MUL, EW_ADD, EW_ELU, EW_ELU_GRAD, EW_ELU_GRAD2, EW_ADD_ROWVEC = range(6)
 TC_BIAS_STATS, TC_BIAS_ELU, TC_PLAIN, TC_DGRAD_ELUBN, TC_WGRAD_ACC, TC_DGRAD_ELUOUT, TC_WGRAD_STORE = range(7)
-TC_T_BIAS_STATS, TC_T_AFFINE_ELU, TC_T_DGRAD_ELUBN = 7, 8, 9
+TC_T_BIAS_STATS, TC_T_AFFINE_ELU, TC_T_DGRAD_ELUBN, TC_T_AFFINE_ELU_POOL = 7, 8, 9, 10
 OP_K, OP_MN, OP_T256_K, OP_T256_MN = range(4)          # pcaa_operand_layout
 
 _p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double

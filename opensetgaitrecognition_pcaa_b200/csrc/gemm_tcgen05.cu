@@ -26,9 +26,10 @@ constexpr int EPI_THREADS = 256;
 enum { MODE_BIAS_STATS = 0, MODE_BIAS_ELU = 1, MODE_PLAIN = 2, MODE_DGRAD_ELUBN = 3, MODE_WGRAD = 4, MODE_DGRAD_ELUOUT = 5,
        // "channel-major" modes: the output ROW (TMEM lane) is the channel, the columns are points; per-channel
        // parameters are per-thread scalars and BatchNorm statistics are plain in-thread sums (no cross-lane reduction)
-       MODE_T_BIAS_STATS = 7, MODE_T_AFFINE_ELU = 8, MODE_T_DGRAD_ELUBN = 9 };
+       MODE_T_BIAS_STATS = 7, MODE_T_AFFINE_ELU = 8, MODE_T_DGRAD_ELUBN = 9, MODE_T_AFFINE_ELU_POOL = 10 };
 
-template <int MODE> constexpr bool is_t_mode() { return MODE == MODE_T_BIAS_STATS || MODE == MODE_T_AFFINE_ELU || MODE == MODE_T_DGRAD_ELUBN; }
+template <int MODE> constexpr bool is_t_mode() { return MODE == MODE_T_BIAS_STATS || MODE == MODE_T_AFFINE_ELU || MODE == MODE_T_DGRAD_ELUBN || MODE == MODE_T_AFFINE_ELU_POOL; }
+template <int MODE> constexpr bool has_row_stats() { return MODE == MODE_T_BIAS_STATS || MODE == MODE_T_DGRAD_ELUBN; }
 
 struct GemmParams {
     int64_t M, N;                 // output extent (rows, cols)
@@ -47,6 +48,8 @@ struct GemmParams {
     const float *scale, *shift, *mean, *invstd;
     int a_tiled, b_tiled;         // operand stored as 256-point tiles [n_tiles][C][256] (3-D tensor map), see pcaa.h
     int sched_mfixed;             // tile order: 0 = items strided over the grid; 1 = CTA keeps one m block (T modes)
+    int pool_n;                   // MODE_T_AFFINE_ELU_POOL: points per group (>= 32); out = fp32 pooled [N / pool_n, M], zeroed
+    float pool_inv_n;
 };
 
 // tile `it` of this CTA -> (m block, n block, k split); false when the CTA has no more work
@@ -319,7 +322,7 @@ __device__ __forceinline__ void t_chunk(float (&v)[32], const uint4* yraw4, cons
             t1 += v[j];
             t2 = fmaf(v[j], v[j], t2);
         }
-    } else if constexpr (MODE == MODE_T_AFFINE_ELU) {
+    } else if constexpr (MODE == MODE_T_AFFINE_ELU || MODE == MODE_T_AFFINE_ELU_POOL) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const float z = fmaf(v[j], r.scale, r.shift), zl = fmaf(v[j], r.scale_l2, r.shift_l2);
@@ -568,7 +571,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int it = 0; tile_at(p, it, m_blk, n_blk, ks); ++it) {
             if (m_blk != cur_m) {
-                if (cur_m >= 0 && row_ok && MODE != MODE_T_AFFINE_ELU) {
+                if (cur_m >= 0 && row_ok && has_row_stats<MODE>()) {
                     atomicAdd(&p.stats[row], d1);
                     atomicAdd(&p.stats[p.M + row], d2);
                 }
@@ -578,7 +581,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 row_ok = row < p.M;
                 if (row_ok) {
                     if constexpr (MODE == MODE_T_BIAS_STATS) tr.bias = p.bias ? p.bias[row] : 0.f;
-                    if constexpr (MODE == MODE_T_AFFINE_ELU) {
+                    if constexpr (MODE == MODE_T_AFFINE_ELU || MODE == MODE_T_AFFINE_ELU_POOL) {
                         tr.scale = p.scale[row];
                         tr.shift = p.bias ? fmaf(p.bias[row], tr.scale, p.shift[row]) : p.shift[row];
                     }
@@ -598,6 +601,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t ra[32], rb[32];
             uint4 yraw[8];
             float t1 = 0.f, t2 = 0.f;
+            // pooled mode: running sum of the current group of pool_n points (the groups' boundaries depend on the column
+            // only: warp-uniform) -- the activation tile is never written, only the [groups, M] means are
+            int64_t pool_g = 0;
+            int pool_left = 0;
+            float pool_acc = 0.f;
+            if constexpr (MODE == MODE_T_AFFINE_ELU_POOL) {
+                pool_g = n0 / p.pool_n;
+                pool_left = (int)((pool_g + 1) * p.pool_n - n0);
+            }
             tmem_ld32_issue(taddr, ra);
 #pragma unroll
             for (int c = 0; c < CPW; ++c) {
@@ -632,6 +644,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 if (col0 + 32 <= p.N) t_chunk<MODE, true>(v, &yraw[(c & 1) * 4], tr, 32, t1, t2);
                 else t_chunk<MODE, false>(v, &yraw[(c & 1) * 4], tr, (int)max((int64_t)0, p.N - col0), t1, t2);
+                if constexpr (MODE == MODE_T_AFFINE_ELU_POOL) {
+                    if (pool_left > 32) {
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) { s0 += v[j]; s1 += v[j + 1]; }
+                        pool_acc += s0 + s1;
+                        pool_left -= 32;
+                    } else {
+                        // pool_n >= 32: one group boundary in this chunk, after its first pool_left columns
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float a = j < pool_left ? v[j] : 0.f;
+                            s0 += a;
+                            s1 += v[j] - a;
+                        }
+                        pool_acc += s0;
+                        if (row_ok && (pool_g + 1) * p.pool_n <= p.N)
+                            atomicAdd(reinterpret_cast<float*>(p.out) + pool_g * p.M + row, pool_acc * p.pool_inv_n);
+                        ++pool_g;
+                        pool_acc = s1;
+                        pool_left = p.pool_n - (32 - pool_left);
+                    }
+                    if (c + 1 == CPW && row_ok && (pool_g + 1) * p.pool_n <= p.N)
+                        atomicAdd(reinterpret_cast<float*>(p.out) + pool_g * p.M + row, pool_acc * p.pool_inv_n);
+                    continue;
+                }
                 if ((c & 1) == 0) {
                     // the previous TMA store must have finished READING the staging buffer before it is overwritten
                     if (lane == 0) tma_store_wait_read();
@@ -662,7 +701,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             d1 += (double)t1;
             d2 += (double)t2;
         }
-        if (cur_m >= 0 && row_ok && MODE != MODE_T_AFFINE_ELU) {
+        if (cur_m >= 0 && row_ok && has_row_stats<MODE>()) {
             atomicAdd(&p.stats[row], d1);
             atomicAdd(&p.stats[p.M + row], d2);
         }
@@ -1024,10 +1063,18 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
     const int a_mn = a_layout & 1, b_mn = b_layout & 1;
     const bool a_tiled = a_layout >= 2, b_tiled = b_layout >= 2;
     PCAA_REQUIRE(M > 0 && N > 0 && K > 0, PCAA_ERR_SHAPE, "gemm_tc: bad shape");
-    PCAA_REQUIRE(mode >= 0 && mode <= PCAA_TC_T_DGRAD_ELUBN, PCAA_ERR_UNSUPPORTED, "gemm_tc: unknown mode %d", mode);
+    PCAA_REQUIRE(mode >= 0 && mode <= PCAA_TC_T_AFFINE_ELU_POOL, PCAA_ERR_UNSUPPORTED, "gemm_tc: unknown mode %d", mode);
     const bool tmode = mode >= PCAA_TC_T_BIAS_STATS;
+    const bool pooled = mode == PCAA_TC_T_AFFINE_ELU_POOL;
     const bool wgrad = (mode == PCAA_TC_WGRAD_ACC || mode == PCAA_TC_WGRAD_STORE);
-    const bool f32out = wgrad || out_dtype == PCAA_F32;
+    const bool f32out = !pooled && (wgrad || out_dtype == PCAA_F32);
+    if (pooled) {
+        // out = fp32 [N / ldo, M] group means, ldo = points per group
+        PCAA_REQUIRE(out_dtype == PCAA_F32 && ldo >= 32 && N % ldo == 0, PCAA_ERR_SHAPE,
+                     "gemm_tc: pooled mode writes fp32 [N / n, M] means for groups of n = ldo >= 32 points, n | N (n=%lld, N=%lld)",
+                     (long long)ldo, (long long)N);
+        if (cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(N / ldo) * (size_t)M, st) != cudaSuccess) return check_launch("gemm_tc memset");
+    }
     // bf16 rows are written in 16-byte groups: the buffer must have ldo >= round_up(N, 8) (pad columns receive the
     // epilogue of zero accumulators); fp32 rows use 16-byte stores when aligned, scalar stores otherwise (wgrad only)
     const bool scalar_out = f32out && (((uintptr_t)out & 15) != 0 || ldo % 4 != 0 || N % 4 != 0);
@@ -1042,8 +1089,8 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
         PCAA_REQUIRE(stats != nullptr, PCAA_ERR_SHAPE, "gemm_tc: stats buffer required for mode %d", mode);
     if (mode == PCAA_TC_DGRAD_ELUBN || mode == PCAA_TC_T_DGRAD_ELUBN)
         PCAA_REQUIRE(yprev && scale && shift && mean && invstd, PCAA_ERR_SHAPE, "gemm_tc: mode %d needs yprev/coefficients", mode);
-    if (mode == PCAA_TC_T_AFFINE_ELU) PCAA_REQUIRE(scale && shift, PCAA_ERR_SHAPE, "gemm_tc: mode 8 needs scale/shift");
-    if (tmode) PCAA_REQUIRE(out_dtype == PCAA_BF16, PCAA_ERR_UNSUPPORTED, "gemm_tc: channel-major modes store bf16");
+    if (mode == PCAA_TC_T_AFFINE_ELU || pooled) PCAA_REQUIRE(scale && shift, PCAA_ERR_SHAPE, "gemm_tc: modes 8 / 10 need scale/shift");
+    if (tmode && !pooled) PCAA_REQUIRE(out_dtype == PCAA_BF16, PCAA_ERR_UNSUPPORTED, "gemm_tc: channel-major modes store bf16");
     if (mode == PCAA_TC_DGRAD_ELUOUT) PCAA_REQUIRE(yprev != nullptr, PCAA_ERR_SHAPE, "gemm_tc: mode 5 needs the saved activation");
     if (yprev) PCAA_REQUIRE(((uintptr_t)yprev & 15) == 0 && (tmode || ldy % 8 == 0), PCAA_ERR_ALIGN, "gemm_tc: yprev alignment");
     constexpr int BN = 256;
@@ -1059,7 +1106,7 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
     PCAA_REQUIRE(a_tiled == (b_tiled && !b_mn), PCAA_ERR_UNSUPPORTED, "gemm_tc: k = points needs BOTH operands tiled (PCAA_OP_T256_K)");
     // channel-major modes: the epilogue moves 64-point x 32-channel sub-tiles of out (and yprev) by TMA
     CUtensorMap to = ta, ty = ta;
-    if (tmode) {
+    if (tmode && !pooled) {
         rc = make_map_tiled(&to, out, M, ceil_div(N, 256), 64, 32);
         if (rc) return rc;
         if (mode == PCAA_TC_T_DGRAD_ELUBN) {
@@ -1105,6 +1152,8 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
     p.mean = mean;
     p.invstd = invstd;
     p.sched_mfixed = tmode ? 1 : 0;
+    p.pool_n = pooled ? (int)ldo : 0;
+    p.pool_inv_n = pooled ? 1.f / (float)ldo : 0.f;
     const int key = (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
     if (key == 0) {
         if (wgrad) return launch_tc<BN, false, false, MODE_WGRAD>(ta, tb, to, ty, p, st);
@@ -1121,6 +1170,7 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
             case PCAA_TC_DGRAD_ELUOUT: return launch_tc<BN, false, true, MODE_DGRAD_ELUOUT>(ta, tb, to, ty, p, st);
             case PCAA_TC_T_BIAS_STATS: return launch_tc<BN, false, true, MODE_T_BIAS_STATS>(ta, tb, to, ty, p, st);
             case PCAA_TC_T_AFFINE_ELU: return launch_tc<BN, false, true, MODE_T_AFFINE_ELU>(ta, tb, to, ty, p, st);
+            case PCAA_TC_T_AFFINE_ELU_POOL: return launch_tc<BN, false, true, MODE_T_AFFINE_ELU_POOL>(ta, tb, to, ty, p, st);
             default: break;
         }
     } else if (key == 3) {

@@ -83,6 +83,10 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
             if l < 4:
                 a = ops.bn_elu_apply_t(y, coef, R)
                 sv["a"][l] = a
+        elif l == 4 and N >= 32:
+            # eval: the mean pool over the N points of a frame runs in the epilogue of the last layer's GEMM; the
+            # [1024, P] activation (the largest tensor of the forward) is never written or re-read
+            return ops.gemm_tc_pooled(wb, a, Cout, R, Cin, N, bias=bias, coef=bn_coef(l, None)), sv
         else:
             a = ops.gemm_tc(wb, a, TC_T_AFFINE_ELU, Cout, R, Cin, b_mn=OP_T256_MN, bias=bias, coef=bn_coef(l, None))
     if training:

@@ -346,6 +346,8 @@ def gemm_tc(a, b, mode: int, M: int, N: int, K: int, *, a_mn=False, b_mn=False, 
     _chk(a, torch.bfloat16, contiguous=False), _chk(b, torch.bfloat16, contiguous=False)
     if a.stride(-1) != 1 or b.stride(-1) != 1:
         raise ValueError("gemm_tc: operands need unit inner stride")
+    if mode == _lib.TC_T_AFFINE_ELU_POOL:
+        raise ValueError("gemm_tc: use gemm_tc_pooled for the pooled eval epilogue")
     if out is None and mode >= _lib.TC_T_BIAS_STATS:
         out = t256_empty(M, N, a.device)
     if out is None:
@@ -361,6 +363,19 @@ def gemm_tc(a, b, mode: int, M: int, N: int, K: int, *, a_mn=False, b_mn=False, 
     call("pcaa_gemm_tc", _p(a), a.stride(-2), int(a_mn), _p(b), b.stride(-2), int(b_mn), _p(out),
          out.stride(-2), _DT[out.dtype], M, N, K, mode, _p(bias), _p(stats), _p(yprev),
          0 if yprev is None else yprev.stride(-2), _p(sc), _p(sh), _p(mu), _p(inv), _s())
+    return out
+
+
+def gemm_tc_pooled(w, aT, M: int, P: int, K: int, n: int, *, bias=None, coef=None):
+    """pooled[g, m] = mean over the n points of group g of ELU(scale[m] * (sum_k w[m,k] aT[k,p] + bias[m]) + shift[m]):
+    the eval-mode shared-MLP layer with the mean pool over points fused into the GEMM epilogue (models.py:21-34 with
+    running statistics + models.py:242-243, 282).  aT is T256 [tiles, K, 256]; n >= 32 and n | P.  Returns fp32 [P/n, M]."""
+    _chk(w, torch.bfloat16, contiguous=False), _chk(aT, torch.bfloat16, contiguous=False)
+    if n < 32 or P % n:
+        raise ValueError("gemm_tc_pooled: groups of n >= 32 points with n | P")
+    out = torch.empty((P // n, M), device=w.device, dtype=torch.float32)
+    call("pcaa_gemm_tc", _p(w), w.stride(-2), int(_lib.OP_K), _p(aT), aT.stride(-2), int(_lib.OP_T256_MN), _p(out), n, F32, M, P, K,
+         _lib.TC_T_AFFINE_ELU_POOL, _p(bias), None, None, 0, _p(coef[0]), _p(coef[1]), None, None, _s())
     return out
 
 

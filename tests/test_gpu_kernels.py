@@ -437,6 +437,28 @@ def test_gemm_tc_t_bias_stats_and_affine(ops, Cout, P, Cin):
     assert _pad_is_zero(ops, out2, P)
 
 
+@pytest.mark.parametrize("Cout,G,n,Cin", [(1024, 60, 150, 1024), (256, 7, 32, 64), (384, 30, 50, 512), (128, 3, 300, 128)])
+def test_gemm_tc_pooled_eval_epilogue(ops, Cout, G, n, Cin):
+    """Eval-mode last PointNet layer with the mean pool over points fused into the GEMM epilogue: equals the unfused
+    pair (affine + ELU GEMM, mean pool); groups straddle 32-column chunks, warp halves and 256-point tiles."""
+    g = torch.Generator().manual_seed(Cout + G + n)
+    P = G * n
+    w = bf16_round(torch.randn(Cout, Cin, generator=g) / math.sqrt(Cin))
+    aT = bf16_round(torch.randn(Cin, P, generator=g))
+    bias = 0.1 * torch.randn(Cout, generator=g)
+    coef = torch.stack([1 + 0.1 * torch.randn(Cout, generator=g), 0.1 * torch.randn(Cout, generator=g)])
+    ref = O.elu((w @ aT + bias[:, None]) * coef[0][:, None] + coef[1][:, None])
+    pooled = ops.gemm_tc_pooled(cuda(w).bfloat16(), _t256(ops, aT), Cout, P, Cin, n, bias=cuda(bias), coef=cuda(coef))
+    torch.cuda.synchronize()
+    assert pooled.shape == (G, Cout)
+    assert rel_err(pooled, ref.reshape(Cout, G, n).mean(2).t()) < 2e-3
+    # against the unfused kernels (same GEMM; the only difference is the bf16 rounding of the stored activation)
+    a = ops.gemm_tc(cuda(w).bfloat16(), _t256(ops, aT), ops._lib.TC_T_AFFINE_ELU, Cout, P, Cin, b_mn=ops._lib.OP_T256_MN,
+                    bias=cuda(bias), coef=cuda(coef))
+    plain, _, _ = ops.bn_elu_meanpool_t(a, None, G, n)
+    assert rel_err(pooled, plain) < 2e-3
+
+
 @pytest.mark.parametrize("Cout,P,Cin", T_SHAPES)
 def test_gemm_tc_t_dgrad_elubn(ops, Cout, P, Cin):
     g = torch.Generator().manual_seed(Cout + P + Cin + 5)
