@@ -28,15 +28,17 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sam, int64_t sak, const TB* _
     const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
     const int64_t kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
     const bool split = gridDim.z > 1;
-    for (int64_t k0 = kbeg; k0 < kend; k0 += TK) {
-        // A tile: 64 x 16 = 1024 elements, 4 per thread
+    // register-staged software pipeline: the global loads of k block i+1 are issued before the FMAs of block i (these
+    // GEMMs are small and latency bound: few CTAs, nothing else to hide a load behind)
+    float ra[4], rb[4];
+    auto load_tiles = [&](int64_t k0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int m, k;
             if (a_kfast) { k = tid % TK; m = tid / TK + 16 * i; }
             else { m = tid % TM; k = tid / TM + 4 * i; }
             int64_t gm = m0 + m, gk = k0 + k;
-            As[k][m] = (gm < M && gk < kend) ? ld_as_float<TA>(A + gm * sam + gk * sak) : 0.f;
+            ra[i] = (gm < M && gk < kend) ? ld_as_float<TA>(A + gm * sam + gk * sak) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -44,9 +46,30 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sam, int64_t sak, const TB* _
             if (b_nfast) { n = tid % TN_; k = tid / TN_ + 4 * i; }
             else { k = tid % TK; n = tid / TK + 16 * i; }
             int64_t gn = n0 + n, gk = k0 + k;
-            Bs[k][n] = (gn < N && gk < kend) ? ld_as_float<TB>(B + gk * sbk + gn * sbn) : 0.f;
+            rb[i] = (gn < N && gk < kend) ? ld_as_float<TB>(B + gk * sbk + gn * sbn) : 0.f;
         }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int m, k;
+            if (a_kfast) { k = tid % TK; m = tid / TK + 16 * i; }
+            else { m = tid % TM; k = tid / TM + 4 * i; }
+            As[k][m] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int n, k;
+            if (b_nfast) { n = tid % TN_; k = tid / TN_ + 4 * i; }
+            else { k = tid % TK; n = tid / TK + 16 * i; }
+            Bs[k][n] = rb[i];
+        }
+    };
+    if (kbeg < kend) load_tiles(kbeg);
+    for (int64_t k0 = kbeg; k0 < kend; k0 += TK) {
+        store_tiles();
         __syncthreads();
+        if (k0 + TK < kend) load_tiles(k0 + TK);
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
             float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -91,9 +114,9 @@ static int launch(const void* A, int64_t sam, int64_t sak, const void* B, int64_
     // tall-K products with few output tiles (weight gradients of the TCN / heads: K = rows) would leave most SMs idle:
     // split K over grid.z and reduce with fp32 atomics into a zeroed, contiguous fp32 C
     const int64_t tiles = (int64_t)grid.x * grid.y;
-    if (sizeof(TC) == 4 && act == PCAA_ACT_NONE && !accumulate && scn == 1 && scm == N && K >= 512 && tiles < 2 * 148) {
+    if (sizeof(TC) == 4 && act == PCAA_ACT_NONE && !accumulate && scn == 1 && scm == N && K >= 128 && tiles < 2 * 148) {
         int splits = (int)((4 * 148 + tiles - 1) / tiles);
-        int max_splits = (int)(K / 128);
+        int max_splits = (int)(K / 32);
         if (splits > max_splits) splits = max_splits;
         if (splits > 1) {
             k_per_split = ((K + splits - 1) / splits + TK - 1) / TK * TK;

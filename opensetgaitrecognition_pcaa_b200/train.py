@@ -191,8 +191,7 @@ class PCAATrainer:
             # encoder forward (train-mode BatchNorm; running statistics updated in place)
             st["logits"], st["fv"], st["saved"] = engine.encoder_forward(pcs, self.P_E, True, self.enc.use_projection_head,
                                                                          self._enc_wb16, self._tcn_wb16)
-            for t in self._nbt:
-                t.add_(1)
+            torch._foreach_add_(self._nbt, 1)
             # critic step (PCAA_ablation.py:900-980): one fused kernel forms d_loss and its parameter gradients
             self.D.g.zero_()
             st["d_losses"] = ops.wgangp_dstep(st["fv"], z0, self.means, gt, alphas.reshape(-1), *self.Dw, cfg["GP_WEIGHT"], self.Dg)
