@@ -237,6 +237,10 @@ int pcaa_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, floa
  * packed crop store resident in HBM.  row_bytes % 16 == 0; an index outside [0, n_src) gives a zero row. */
 int pcaa_gather_rows(const void* src, const int64_t* idx, void* dst, int64_t n_idx, int64_t row_bytes, int64_t n_src,
                      pcaa_stream stream);
+/* dst[i] += sum_{k < nsrc} src[k * src_stride + i], i < n: local reduction step of the data-parallel gradient exchange
+ * over NVLink peer memory (the only exchange of the path; the reference is single-GPU).  n, src_stride
+ * multiples of 4; 16-byte aligned buffers. */
+int pcaa_sum_into(float* dst, const float* src, int64_t n, int64_t src_stride, int nsrc, pcaa_stream stream);
 /* CUDA-graph form of the same update: the step counter lives on the device.  pcaa_adam_advance increments
  * step_dev[0] and writes coef_dev = { lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step) } (the bias corrections
  * torch.optim.Adam computes on the host); pcaa_adam_flat_dev reads them, so a captured train step advances the

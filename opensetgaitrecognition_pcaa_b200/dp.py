@@ -13,6 +13,11 @@ Everything here is backend-agnostic host logic (``nccl`` on the B200 box, ``gloo
 * ``GradExchange``    bucketed sum-all-reduce of contiguous spans of one flat gradient buffer, each span launched
                       as soon as its producer kernels are enqueued (decoder gradients, 99 % of the bytes, go first
                       and overlap the PointNet backward); the 1/world factor is folded into the fused Adam kernel;
+* ``PeerExchange``    the same sum-all-reduce done by the COPY ENGINES over NVLink peer memory instead of NCCL kernels:
+                      every rank pulls its chunk of the span from each peer's gradient buffer (symmetric memory, P2P
+                      mapped), adds the pulled chunks locally (``pcaa_sum_into``) and pulls the other ranks' reduced
+                      chunks back.  No SM is taken from the persistent tcgen05 GEMMs of the encoder backward that
+                      runs beside it (NCCL's all-reduce CTAs cost the step ~1 ms on 2 GPUs, DESIGN.md section 5);
 * ``gather_scores``   the one gather inference needs (per-sample scores for the host-side ROC threshold).
 """
 from __future__ import annotations
@@ -60,6 +65,94 @@ def global_draws(global_batch: int, latent_dim: int, rank: int, world: int, np_r
 _SKIP_EXCHANGE = os.environ.get("PCAA_DP_SKIP_EXCHANGE", "0") == "1"
 
 
+def exchange_mode() -> str:
+    """"peer" (copy engines over NVLink peer memory; default, falls back to NCCL when the symmetric-memory rendezvous is
+    not possible) or "nccl"; PCAA_DP_EXCHANGE overrides."""
+    return os.environ.get("PCAA_DP_EXCHANGE", "peer").lower()
+
+
+def alloc_exchange_buffer(n: int, device, group=None):
+    """fp32 zeros(n) for a gradient buffer that will be exchanged, plus a PeerExchange when the peer mode is on and the
+    symmetric-memory rendezvous succeeds (one process per GPU of one NVLink domain); otherwise (tensor, None) and the
+    exchange goes through NCCL.  Collective when world > 1 and the peer mode is on."""
+    rank, world = world_info(group)
+    if world > 1 and exchange_mode() == "peer" and torch.device(device).type == "cuda":
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(n, dtype=torch.float32, device=torch.device(device))
+            t.zero_()
+            hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            return t, PeerExchange(t, hdl)
+        except Exception as e:                       # noqa: BLE001 -- any failure here means "no peer access": NCCL still works
+            if rank == 0:
+                print(f"[pcaa dp] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+    return torch.zeros(n, device=device, dtype=torch.float32), None
+
+
+class PeerExchange:
+    """Sum-all-reduce of spans of a symmetric-memory fp32 buffer by peer copies (copy engines) + one local add kernel.
+
+    For a span [lo, hi) split into `world` chunks (multiples of 8 elements), on the CURRENT stream:
+      barrier                      every rank's span is final (each rank's stream already waited for its producers)
+      pull   stage[k] <- peer_k.buf[my chunk]      one cudaMemcpyAsync per peer, each on its own stream (own copy engine)
+      add    buf[my chunk] += sum_k stage[k]       pcaa_sum_into
+      barrier                      every chunk is reduced
+      pull   buf[chunk_k] <- peer_k.buf[chunk_k]   the all-gather half
+      barrier                      nobody still reads this rank's buffer (the next backward overwrites it)
+    Per-rank NVLink traffic equals a ring all-reduce's (2 (w-1)/w of the span), SM time is one short HBM-bound kernel."""
+
+    def __init__(self, flat: torch.Tensor, handle):
+        self.flat, self.hdl = flat, handle
+        self.rank, self.world = handle.rank, handle.world_size
+        self.peers = [(self.rank + k) % self.world for k in range(1, self.world)]
+        self.streams = [torch.cuda.Stream(device=flat.device) for _ in self.peers]
+        self.stage: Optional[torch.Tensor] = None
+        self.bytes_pulled = 0
+
+    def chunks(self, lo: int, hi: int) -> List[Tuple[int, int]]:
+        n = hi - lo
+        c = ((n + self.world - 1) // self.world + 7) // 8 * 8
+        return [(min(hi, lo + r * c), min(hi, lo + (r + 1) * c)) for r in range(self.world)]
+
+    def all_reduce_(self, lo: int, hi: int) -> None:
+        from . import ops
+        if hi <= lo:
+            return
+        if (hi - lo) % 4 or lo % 4:
+            raise ValueError("PeerExchange: spans must be multiples of 4 floats (16-byte copies)")
+        cur = torch.cuda.current_stream(self.flat.device)
+        ch = self.chunks(lo, hi)
+        mlo, mhi = ch[self.rank]
+        width = max(e - b for b, e in ch)
+        if self.stage is None or self.stage.shape[1] < width:
+            self.stage = torch.empty((len(self.peers), width), device=self.flat.device, dtype=torch.float32)
+        self.hdl.barrier(channel=0)
+        if mhi > mlo:
+            for k, (peer, st) in enumerate(zip(self.peers, self.streams)):
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    self.stage[k, :mhi - mlo].copy_(self.hdl.get_buffer(peer, (mhi - mlo,), torch.float32, mlo))
+                self.bytes_pulled += 4 * (mhi - mlo)
+            for st in self.streams:
+                cur.wait_stream(st)
+            ops.sum_into(self.flat[mlo:mhi], self.stage[:, :mhi - mlo])
+        self.hdl.barrier(channel=1)
+        for peer, st in zip(self.peers, self.streams):
+            b, e = ch[peer]
+            if e <= b:
+                continue
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                self.flat[b:e].copy_(self.hdl.get_buffer(peer, (e - b,), torch.float32, b))
+            self.bytes_pulled += 4 * (e - b)
+        for st in self.streams:
+            cur.wait_stream(st)
+        self.hdl.barrier(channel=2)
+
+
+PEER_MIN = 1 << 20      # spans below 4 MB stay on NCCL (latency bound either way, and they overlap nothing)
+
+
 class GradExchange:
     """Sum-all-reduce of spans of a flat gradient buffer, overlappable with the kernels that follow.
 
@@ -69,9 +162,10 @@ class GradExchange:
     stream (or the host) wait for all started reductions.  With world size 1 both are no-ops.
     """
 
-    def __init__(self, flat: torch.Tensor, group=None, side_stream: bool = False):
+    def __init__(self, flat: torch.Tensor, group=None, side_stream: bool = False, peer: Optional["PeerExchange"] = None):
         self.flat = flat
         self.group = group
+        self.peer = peer            # spans of >= PEER_MIN elements go through the copy engines instead of NCCL
         self.rank, self.world = world_info(group)
         self._pending: List = []
         # side_stream: keep the side stream even for one rank, for work the caller chains behind a span's reduction
@@ -98,7 +192,10 @@ class GradExchange:
             ev.record()
             with torch.cuda.stream(self._stream):
                 self._stream.wait_event(ev)
-                if self.world > 1:
+                if self.world > 1 and self.peer is not None and hi - lo >= PEER_MIN:
+                    self.bytes_reduced += buf.numel() * buf.element_size()
+                    self.peer.all_reduce_(lo, hi)             # stream-ordered on the side stream: nothing to wait for
+                elif self.world > 1:
                     self.bytes_reduced += buf.numel() * buf.element_size()
                     w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
                     if then is not None:

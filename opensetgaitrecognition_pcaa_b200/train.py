@@ -24,7 +24,7 @@ from ._lib import ACT_ELU, EW_ADD
 class _Flat:
     """Flat fp32 storage for a list of (name, tensor): parameters become views; same layout for grad / m / v."""
 
-    def __init__(self, named: List, device):
+    def __init__(self, named: List, device, group=None, exchanged: bool = False):
         self.names, self.slices = [], {}
         off = 0
         for name, t in named:
@@ -34,7 +34,8 @@ class _Flat:
             off += (n + 7) // 8 * 8                     # 16-byte alignment of every tensor, also in the bf16 shadow
         self.size = off
         self.p = torch.zeros(off, device=device, dtype=torch.float32)
-        self.g = torch.zeros(off, device=device, dtype=torch.float32)
+        # the gradient buffer of a data-parallel run may live in symmetric (peer-mapped) memory: dp.PeerExchange
+        self.g, self.peer = dp.alloc_exchange_buffer(off, device, group) if exchanged else (torch.zeros(off, device=device, dtype=torch.float32), None)
         self.m = torch.zeros(off, device=device, dtype=torch.float32)
         self.v = torch.zeros(off, device=device, dtype=torch.float32)
         for name, t in named:
@@ -108,7 +109,7 @@ class PCAATrainer:
             named += [("GPH." + k, p) for k, p in decoder_projection_head.named_parameters()]
         if decoder is not None:
             named += [("G." + k, p) for k, p in decoder.named_parameters() if k.startswith("dense")]
-        self.G = _Flat(named, dev)
+        self.G = _Flat(named, dev, process_group, exchanged=True)
         self.D = _Flat([("D." + k, p) for k, p in discriminator.named_parameters()], dev)
         dec_names = [n for n in self.G.names if n.startswith("G.") or n.startswith("GPH.")]
         self._dec_span = self.G.span(dec_names) if dec_names else None
@@ -116,7 +117,7 @@ class PCAATrainer:
         self.G.make_shadow()
         self._refresh_views()
         # gradient exchange (dp.py): decoder-side span first (overlaps the encoder backward), then the encoder span
-        self.xG = dp.GradExchange(self.G.g, process_group, side_stream=True)
+        self.xG = dp.GradExchange(self.G.g, process_group, side_stream=True, peer=self.G.peer)
         self.xD = dp.GradExchange(self.D.g, process_group)
         self._one = torch.ones((), device=dev, dtype=torch.float32)
         # PCAA_WGRAD_OVERLAP=1 runs the PointNet weight-gradient GEMMs on their own stream, concurrently with the
