@@ -230,16 +230,24 @@ def run_infer(args, world, rank, local, dev):
     # end to end: pinned host crops -> H2D (copy stream, one batch ahead: loader.DevicePrefetcher) -> encode + score +
     # vote -> D2H of the window labels, host waits for them every step
     from opensetgaitrecognition_pcaa_b200.loader import DevicePrefetcher
-    votes_host = torch.empty(B // k, dtype=torch.int32).pin_memory()
+    # the host reads every batch's window labels, one batch behind the device (two pinned buffers)
+    votes_host = [torch.empty(B // k, dtype=torch.int32).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
     for (x,) in DevicePrefetcher(((host[i % nb],) for i in range(2)), dev, depth=2):   # untimed: the loader's streams / device slots
         inference.sharded_stream_inference(enc, means, x, k, lthr, NCLS, encode_batch=B)
     barrier()
+    host_seen = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for (x,) in DevicePrefetcher(((host[i % nb],) for i in range(args.steps)), dev, depth=2):
+    for i, (x,) in enumerate(DevicePrefetcher(((host[i % nb],) for i in range(args.steps)), dev, depth=2)):
         ll, votes, pred = inference.sharded_stream_inference(enc, means, x, k, lthr, NCLS, encode_batch=B)
-        votes_host.copy_(votes, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        j = i & 1
+        votes_host[j].copy_(votes, non_blocking=True)
+        done[j].record()
+        if i > 0:
+            done[j ^ 1].synchronize()
+            host_seen += int(votes_host[j ^ 1][0])
+    done[(args.steps - 1) & 1].synchronize()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -260,7 +268,7 @@ def run_infer(args, world, rank, local, dev):
                    "parallelism": f"dp{world} (batch-sharded stream, no collective)",
                    "l2": "3 rotating input batches; per-step activations exceed the 126 MB L2"},
         "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": INFER_UNIT, "h2d_bytes_per_step": host[0].numel() * 4,
-                "d2h_bytes_per_step": votes_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": votes_host[0].numel() * 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("infer", B, nmax),
@@ -403,25 +411,36 @@ def run_b200(args):
     # ---- end-to-end through the public API with HOST buffers: pinned host batch -> H2D (copy stream, one batch ahead,
     # loader.DevicePrefetcher) -> train step -> D2H of the losses and predictions, host waits for them every step
     from opensetgaitrecognition_pcaa_b200.loader import DevicePrefetcher
-    res_host = torch.empty(5, dtype=torch.float32).pin_memory()
-    pred_host = torch.empty(B, dtype=torch.int32).pin_memory()
+    # The host reads every step's losses / predictions (the reference prints them each iteration, PCAA_ablation.py:1023-1030),
+    # one step behind the device: the D2H copies of step i are stream-ordered right behind it (before the next replay
+    # overwrites the graph-owned outputs) into one of two pinned buffers, and the host waits for them while step i+1 runs.
+    res_host = [torch.empty(5, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pred_host = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_steps = args.steps
     for d in DevicePrefetcher((host[i % nb] for i in range(2)), dev, depth=2):     # untimed: the loader's streams / device slots
         stepfn(*d)
     barrier()
+    host_seen = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     feed = DevicePrefetcher((host[i % nb] for i in range(e2e_steps)), dev, depth=2)
-    for d in feed:
+    for i, d in enumerate(feed):
         out = stepfn(*d)
-        res_host.copy_(torch.stack([out["rec_loss"], out["d_loss"], out["gp"], out["loss_g"], out["sup_loss"]]), non_blocking=True)
-        pred_host.copy_(out["pred"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the reference reads .item() every step (PCAA_ablation.py:1023-1030)
+        j = i & 1
+        res_host[j].copy_(torch.stack([out["rec_loss"], out["d_loss"], out["gp"], out["loss_g"], out["sup_loss"]]), non_blocking=True)
+        pred_host[j].copy_(out["pred"], non_blocking=True)
+        done[j].record()
+        if i > 0:
+            done[j ^ 1].synchronize()
+            host_seen += float(res_host[j ^ 1][0]) + int(pred_host[j ^ 1][0])
+    done[(e2e_steps - 1) & 1].synchronize()
+    host_seen += float(res_host[(e2e_steps - 1) & 1][0])
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     h2d = feed.h2d_bytes // e2e_steps
-    d2h = res_host.numel() * 4 + pred_host.numel() * 4
+    d2h = res_host[0].numel() * 4 + pred_host[0].numel() * 4
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)

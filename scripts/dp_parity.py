@@ -1,7 +1,6 @@
 """Data-parallel parity on real GPUs: run under torchrun with N ranks.
 
-Each rank runs ONE variant-4 step of the fused trainer on its shard of a global batch (local BatchNorm statistics, NCCL
-sum-all-reduce of the flat gradient, 1/N folded into Adam).  Reference for every rank: a single-process trainer (world 1)
+Each rank runs ONE variant-4 step of the fused trainer on its shard of a global batch (local BatchNorm statistics, sum-all-reduce of the flat gradient -- copy engines over NVLink peer memory by default, NCCL with PCAA_DP_EXCHANGE=nccl --, 1/N folded into Adam).  Reference for every rank: a single-process trainer (world 1)
 stepped on each shard separately from the same initial weights; the DP gradient must equal the MEAN of those per-shard
 gradients and the DP weights the Adam update of that mean.  Prints max relative deviations; exits non-zero on failure.
 
@@ -69,7 +68,8 @@ allp = [torch.empty_like(p_dp) for _ in range(world)]
 dist.all_gather(allp, p_dp)
 same = all(torch.equal(allp[0], t) for t in allp)
 if rank == 0:
-    print(f"dp_parity world={world}: ||g_dp - sum_shards g|| / ||.|| = {rel_g:.2e}, fraction of weights off Adam(mean grad) by > 2e-6 = {rel_p:.2e}, "
+    xch = "peer copies (copy engines, symmetric memory)" if tr.G.peer is not None else "NCCL all-reduce"
+    print(f"dp_parity world={world} [{xch}, {tr.xG.bytes_reduced / 1e6:.1f} MB reduced]: ||g_dp - sum_shards g|| / ||.|| = {rel_g:.2e}, fraction of weights off Adam(mean grad) by > 2e-6 = {rel_p:.2e}, "
           f"replicas identical after the step: {same} -> {'OK' if ok and same else 'FAIL'}")
 dist.destroy_process_group()
 sys.exit(0 if ok and same else 1)
