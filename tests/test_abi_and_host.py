@@ -212,3 +212,32 @@ def test_inference_host_logic_matches_sklearn():
     # `pdf > thr` in float64 <=> `log pdf > log_threshold(thr)`
     assert I.log_threshold(0.0) == I.LOG_MIN_POSITIVE and np.exp(I.LOG_MIN_POSITIVE - 1e-9) == 0.0 < np.exp(I.LOG_MIN_POSITIVE + 0.7)
     assert I.log_threshold(np.inf) == np.inf and abs(I.log_threshold(1e-30) - np.log(1e-30)) < 1e-12
+
+
+def test_peer_exchange_chunking_and_fallback():
+    """Host logic of the copy-engine gradient exchange (dp.PeerExchange): chunks tile the span, are 8-element aligned
+    and identical on every rank; without CUDA / a process group the gradient buffer is a plain tensor (NCCL / gloo path)."""
+    from opensetgaitrecognition_pcaa_b200 import dp
+
+    class H:                                    # stands in for the symmetric-memory handle
+        def __init__(self, rank, world):
+            self.rank, self.world_size = rank, world
+
+    class FakeFlat:
+        device = torch.device("cpu")
+
+    for world in (2, 3, 8):
+        for lo, hi in ((0, 217_000_008), (24, 1_000_000), (8, 16), (0, 8 * world), (16, 16 + 8 * (world - 1))):
+            per_rank = []
+            for rank in range(world):
+                px = dp.PeerExchange.__new__(dp.PeerExchange)
+                px.rank, px.world = rank, world
+                per_rank.append(px.chunks(lo, hi))
+            assert all(c == per_rank[0] for c in per_rank)
+            ch = per_rank[0]
+            assert len(ch) == world and ch[0][0] == lo and ch[-1][1] == hi
+            assert all(a[1] == b[0] for a, b in zip(ch, ch[1:])) and all(b <= e for b, e in ch)
+            assert all((b - lo) % 8 == 0 for b, _ in ch)
+    assert dp.exchange_mode() in ("peer", "nccl")
+    t, peer = dp.alloc_exchange_buffer(64, "cpu")
+    assert peer is None and t.shape == (64,) and float(t.abs().sum()) == 0
