@@ -587,22 +587,18 @@ bn_elu_meanpool_staged_kernel(const __nv_bfloat16* __restrict__ yT, const float*
     const int64_t tile = blockIdx.x;
     const int cb = blockIdx.y * MPS_CH;
     const int64_t tile_off = tile * (int64_t)C * 256;
-    // ---- stage: 64 rows x 32 chunks of 16 bytes, 8 per thread, all loads in flight before the first store
-    uint4 raw[8];
+    // ---- stage: 64 rows x 32 chunks of 16 bytes, 8 per thread, copied global -> shared asynchronously (cp.async: no
+    // staging registers, so more CTAs are resident per SM and one CTA's loads overlap another's arithmetic)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int id = threadIdx.x + 256 * i;
         const int r = id >> 5, ck = id & 31;
         const int c = min(cb + r, C - 1);
-        raw[i] = __ldg(reinterpret_cast<const uint4*>(yT + tile_off + (int64_t)c * 256 + ck * 8));
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(rows + r * MPS_PITCH + ck * 8);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(yT + tile_off + (int64_t)c * 256 + ck * 8) : "memory");
     }
     for (int i = threadIdx.x; i < kmax * NV * MPS_CH; i += 256) acc[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int id = threadIdx.x + 256 * i;
-        const int r = id >> 5, ck = id & 31;
-        *reinterpret_cast<uint4*>(rows + r * MPS_PITCH + ck * 8) = raw[i];
-    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     // ---- reduce: warp = (channel half, point quarter), lane = channel
     const int chl = (warp & 1) * 32 + lane;                     // channel within the block
