@@ -356,6 +356,53 @@ class PCAATrainer:
         return ops.chamfer_reduce(fl, True), ce, pred
 
 
+def _ckpt_paths(root: str, name: str):
+    d = os.path.join(root, "models", name)
+    return d, {k: os.path.join(d, f"{name}_{k}.pt") for k in ("E", "G", "D", "GPH", "OPT")}
+
+
+def save_checkpoint(trainer: PCAATrainer, model_name: str, root: str = ".") -> str:
+    """Write the files train_variant4 writes at a checkpoint (PCAA_ablation.py:1088-1112): models/<name>/<name>_E.pt,
+    _G.pt, _D.pt, _GPH.pt (state_dicts with the reference's keys: inference_PCAA.CGAAE_inference_setup loads them as they
+    are) and discriminator_means.pt; plus <name>_OPT.pt with both Adam states (the reference does not checkpoint its
+    optimizers; this is what makes a run resumable)."""
+    from . import utils
+    d, paths = _ckpt_paths(root, model_name)
+    os.makedirs(d, exist_ok=True)
+    utils.save_model(trainer.enc, paths["E"])
+    utils.save_model(trainer.dis, paths["D"])
+    if trainer.dec is not None:
+        utils.save_model(trainer.dec, paths["G"])
+    if trainer.gph is not None:
+        utils.save_model(trainer.gph, paths["GPH"])
+    torch.save(trainer.means.detach().cpu(), os.path.join(d, "discriminator_means.pt"))
+    torch.save({"G": {"m": trainer.G.m.cpu(), "v": trainer.G.v.cpu(), "step": trainer.G.step, "names": trainer.G.names},
+                "D": {"m": trainer.D.m.cpu(), "v": trainer.D.v.cpu(), "step": trainer.D.step, "names": trainer.D.names}},
+               paths["OPT"])
+    return d
+
+
+def load_checkpoint(trainer: PCAATrainer, model_name: str, root: str = ".", optimizer: bool = True) -> None:
+    """Load what save_checkpoint (or the reference's trainer) wrote into an already built trainer: weights into the flat
+    buffers (the parameters are views of them), bf16 operand copies refreshed, Adam states when present."""
+    d, paths = _ckpt_paths(root, model_name)
+    for key, mod in (("E", trainer.enc), ("D", trainer.dis), ("G", trainer.dec), ("GPH", trainer.gph)):
+        if mod is not None:
+            mod.load_state_dict(torch.load(paths[key], map_location=trainer.dev))
+    trainer.G.make_shadow()
+    trainer._refresh_views()
+    trainer._graphs.clear()                                   # captured graphs hold views of the old shadow
+    trainer._warm.clear()
+    if optimizer and os.path.exists(paths["OPT"]):
+        st = torch.load(paths["OPT"], map_location=trainer.dev)
+        for flat, key in ((trainer.G, "G"), (trainer.D, "D")):
+            if st[key]["names"] != flat.names:
+                raise ValueError(f"load_checkpoint: optimizer state of a different network layout ({key})")
+            flat.m.copy_(st[key]["m"])
+            flat.v.copy_(st[key]["v"])
+            flat.step = int(st[key]["step"])
+
+
 def build_variant(variant: int, n_classes: int, nmax: int, config: Optional[dict] = None, device="cuda",
                   seed: Optional[int] = None, process_group=None):
     """Construct the networks of ablation variant 2 (= train_CGAAE, train_AAE.py:36-46), 3 (PCAA_ablation.py:407-419) or

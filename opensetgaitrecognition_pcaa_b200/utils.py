@@ -61,7 +61,10 @@ def gradient_penalty(critic, z_noise, codes, latent_dim):
 
 
 def save_model(_model: torch.nn.Module, _path):
-    torch.save(_model.state_dict(), _path)
+    """utils.save_model of the reference (`torch.save(model.state_dict(), path)`, utils.py:254-256) -- same keys, shapes
+    and file format.  Tensors are cloned first: inside a PCAATrainer the parameters are views of one flat buffer, and
+    torch.save serialises the WHOLE storage behind a view (871 MB per file instead of the module's own bytes)."""
+    torch.save({k: v.detach().clone() for k, v in _model.state_dict().items()}, _path)
 
 
 def openness(n_train, n_total):

@@ -242,6 +242,45 @@ def test_graphed_step_is_the_eager_step(split):
     assert ins is not None and ins[0].shape == (B, 4, 30, nmax)
 
 
+def test_checkpoint_files_are_the_reference_format_and_resume(tmp_path):
+    """save_checkpoint writes the reference trainer's file set (PCAA_ablation.py:1088-1112) with plain state_dicts of
+    the reference's keys and the modules' own size; a fresh trainer resumed from it continues exactly like the original
+    (same weights, Adam moments and step count -> same next iteration)."""
+    from opensetgaitrecognition_pcaa_b200.train import PCAATrainer, load_checkpoint, save_checkpoint
+    B, nmax, C = 4, 50, 2
+    p = O.det_params(C, nmax, 1)
+    means = O.sample_distant_points(32, C, 10, 10).float()
+    mk = lambda: PCAATrainer(*build(p, C, nmax), means, CFG)
+    ta = mk()
+    rng = np.random.default_rng(9)
+    def draws():
+        return (torch.from_numpy(rng.normal(0, 1, (B, 32))).float().cuda(), torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32)).cuda())
+    for s in range(2):
+        pcs, gt = O.synth_batch(B, nmax, C, seed=50 + s)
+        ta.step(pcs.cuda(), gt.cuda(), *draws())
+    d = save_checkpoint(ta, "PCAA_t", root=str(tmp_path))
+    files = sorted(os.listdir(d))
+    assert files == ["PCAA_t_D.pt", "PCAA_t_E.pt", "PCAA_t_G.pt", "PCAA_t_GPH.pt", "PCAA_t_OPT.pt", "discriminator_means.pt"]
+    sd = torch.load(os.path.join(d, "PCAA_t_E.pt"), map_location="cpu")                 # weights_only default: plain tensors
+    want = {k[2:]: v for k, v in p.items() if k.startswith("E.")}
+    assert list(sd.keys()) == list(want.keys()) and all(sd[k].shape == want[k].shape for k in want)
+    assert os.path.getsize(os.path.join(d, "PCAA_t_E.pt")) < 2 * sum(v.numel() * v.element_size() for v in want.values()) + (1 << 16)
+    assert torch.equal(torch.load(os.path.join(d, "discriminator_means.pt")), means)
+    tb = mk()
+    load_checkpoint(tb, "PCAA_t", root=str(tmp_path))
+    assert torch.equal(tb.G.p, ta.G.p) and torch.equal(tb.G.m, ta.G.m) and torch.equal(tb.G.v, ta.G.v) and tb.G.step == 2
+    assert torch.equal(tb.G.shadow, ta.G.shadow) and int(tb.G.step_dev) == 2 and int(tb.D.step_dev) == 2
+    for (k, va), (_, vb) in zip(ta.enc.state_dict().items(), tb.enc.state_dict().items()):
+        assert torch.equal(va, vb), k
+    pcs, gt = O.synth_batch(B, nmax, C, seed=60)
+    z0, al = draws()
+    oa, ob = ta.step(pcs.cuda(), gt.cuda(), z0, al), tb.step(pcs.cuda(), gt.cuda(), z0, al)
+    for k in ("rec_loss", "d_loss", "sup_loss", "loss_g"):
+        assert abs(float(oa[k]) - float(ob[k])) <= 1e-4 * max(1.0, abs(float(oa[k]))), k
+    dmax = float((ta.G.p - tb.G.p).abs().max())
+    assert dmax <= 2 * CFG["LR"] * 1.01
+
+
 def test_module_autograd_path_matches_oracle():
     """The nn.Module surface driven the way the reference trainer drives it (stock autograd, torch.optim.Adam,
     autograd.grad(create_graph=True) through the critic)."""
