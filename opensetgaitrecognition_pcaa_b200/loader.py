@@ -129,7 +129,8 @@ class PackedCrops:
                 generator: Optional[torch.Generator] = None) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         """Host batches in DataLoader order (sequential, or a torch.randperm drawn from `generator`).  Unshuffled
         batches are views of the pinned store; shuffled ones are gathered into two alternating pinned staging
-        buffers (a yielded batch stays valid until the next-but-one is requested)."""
+        buffers: a yielded batch stays valid until the next-but-one is requested (DevicePrefetcher waits for its
+        asynchronous copy of a batch before it asks for the batch two later)."""
         M = len(self)
         order = torch.randperm(M, generator=generator) if shuffle else None
         stage = None
@@ -207,16 +208,23 @@ class DevicePrefetcher:
         self._fill()
 
     def _issue(self) -> bool:
+        s = self.n_issued % self.depth
+        if self.n_issued >= self.depth:
+            # the producer may reuse a host staging buffer `depth` batches later (PackedCrops.batches alternates two):
+            # the asynchronous copy issued `depth` batches ago must have left the host buffer before the producer runs
+            self.ready[s].synchronize()
         try:
             host = next(self.it)
         except StopIteration:
             return False
-        s = self.n_issued % self.depth
         slot = self.slots[s]
-        if slot is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slot, host)):
-            slot = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.dev) for h in host)
-            self.slots[s] = slot
         with torch.cuda.stream(self.stream):
+            if slot is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slot, host)):
+                # allocated ON the copy stream: the caching allocator never hands a block to another stream than the one
+                # it was allocated on, so the copies below cannot land in memory that kernels still queued on the
+                # consumer stream are using (freed-but-in-flight temporaries of the previous step)
+                slot = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.dev) for h in host)
+                self.slots[s] = slot
             if self.free[s] is not None:
                 self.stream.wait_event(self.free[s])          # the consumer is done with this slot
             for d, h in zip(slot, host):
@@ -247,4 +255,6 @@ class DevicePrefetcher:
         self.free[nxt] = ev
         self._issue()
         cur.wait_event(self.ready[s])
+        for t in self.slots[s]:
+            t.record_stream(cur)          # used on the consumer stream: its block is not recycled before that work is done
         return self.slots[s]

@@ -403,6 +403,69 @@ def load_checkpoint(trainer: PCAATrainer, model_name: str, root: str = ".", opti
             flat.step = int(st[key]["step"])
 
 
+def fit(trainer: PCAATrainer, train, valid, config: dict, model_name: str, root: str = ".", np_rng=None, torch_gen=None,
+        shuffle_gen: Optional[torch.Generator] = None, log=None, graphed: bool = True) -> List[dict]:
+    """The epoch loop of the reference trainers (PCAA_ablation.py:866-1112, train_AAE.py:126-364) on the fused path.
+
+    `train` / `valid` are loader.PackedCrops (the reference's MSRadarDataset(SPLIT.TRAIN / VALID)).  Per epoch: the train
+    split in shuffled batches of config["BATCH_SIZE"] with drop_last (the DataLoader settings of PCAA_ablation.py:793-799),
+    one fused iteration per batch; the validation split unshuffled with drop_last in eval mode (reconstruction loss,
+    cross-entropy, accuracy); every CHECKPOINT_FREQUENCY epochs the model is saved when the validation accuracy improved
+    (strictly, starting from 0: PCAA_ablation.py:1087-1091).  Returns one dict per epoch with the quantities the reference
+    sends to wandb (:1073-1084); `log(epoch_dict)` is called with each.
+
+    Differences by construction: batches are prefetched to the device one ahead; losses and predictions stay on the device
+    during an epoch and are read once at its end (the reference reads five .item()s per iteration); data-parallel, every
+    rank takes its shard of each global batch and of the global RNG draws (dp.shard_range / dp.global_draws), metrics
+    are those of the local shard."""
+    from . import loader
+    B = int(config["BATCH_SIZE"])
+    rank, world = trainer.rank, trainer.world
+    os.makedirs(os.path.join(root, "models", model_name), exist_ok=True)
+    torch.save(trainer.means.detach().cpu(), os.path.join(root, "models", model_name, "discriminator_means.pt"))   # :859-863
+    stepfn = trainer.step_graphed if graphed else trainer.step
+    lo, hi = dp.shard_range(B, rank, world)
+    history: List[dict] = []
+    best_valid_accuracy = 0.0
+    latent = trainer.means.shape[1]
+    for epoch in range(int(config["EPOCHS"])):
+        sums = torch.zeros(4, device=trainer.dev, dtype=torch.float64)
+        correct = torch.zeros((), device=trainer.dev, dtype=torch.int64)
+        n_it = 0
+        batches = ((x[lo:hi], y[lo:hi]) for x, y in train.batches(B, shuffle=True, drop_last=True, generator=shuffle_gen))
+        for pcs, gt in loader.DevicePrefetcher(batches, trainer.dev):
+            z0, alphas = dp.global_draws(B, latent, rank, world, np_rng, torch_gen)
+            out = stepfn(pcs, gt, z0.to(trainer.dev, non_blocking=True), alphas.to(trainer.dev, non_blocking=True))
+            sums += torch.stack([out["rec_loss"], out["sup_loss"], out["d_loss"],
+                                 out["rec_loss"] + out["loss_g"] + out["sup_loss"]]).double()
+            correct += (out["pred"].long() == gt).sum()
+            n_it += 1
+        vs = torch.zeros(2, device=trainer.dev, dtype=torch.float64)
+        vcorrect = torch.zeros((), device=trainer.dev, dtype=torch.int64)
+        n_v = 0
+        vbatches = ((x[lo:hi], y[lo:hi]) for x, y in valid.batches(B, shuffle=False, drop_last=True))
+        for pcs, gt in loader.DevicePrefetcher(vbatches, trainer.dev):
+            rec, ce, pred = trainer.evaluate(pcs, gt)
+            vs += torch.stack([rec, ce]).double()
+            vcorrect += (pred.long() == gt).sum()
+            n_v += 1
+        s, v = (sums / max(n_it, 1)).tolist(), (vs / max(n_v, 1)).tolist()          # the epoch's only host reads
+        rec_e = {"epoch": epoch, "iterations": n_it,
+                 "Reconstruction Loss Train": s[0], "Reconstruction Loss Valid": v[0], "Cross Entropy Loss Train": s[1],
+                 "Cross Entropy Loss Valid": v[1], "Discriminator Loss": s[2], "Total Loss Train": s[3],
+                 "Train Accuracy": int(correct) / max(n_it * (hi - lo), 1), "Valid Accuracy": int(vcorrect) / max(n_v * (hi - lo), 1),
+                 "saved": False}
+        if epoch % int(config.get("CHECKPOINT_FREQUENCY", 1)) == 0 and rec_e["Valid Accuracy"] > best_valid_accuracy:
+            best_valid_accuracy = rec_e["Valid Accuracy"]
+            if rank == 0:
+                save_checkpoint(trainer, model_name, root)
+            rec_e["saved"] = True
+        history.append(rec_e)
+        if log is not None:
+            log(rec_e)
+    return history
+
+
 def build_variant(variant: int, n_classes: int, nmax: int, config: Optional[dict] = None, device="cuda",
                   seed: Optional[int] = None, process_group=None):
     """Construct the networks of ablation variant 2 (= train_CGAAE, train_AAE.py:36-46), 3 (PCAA_ablation.py:407-419) or

@@ -281,6 +281,39 @@ def test_checkpoint_files_are_the_reference_format_and_resume(tmp_path):
     assert dmax <= 2 * CFG["LR"] * 1.01
 
 
+def test_fit_epoch_loop_on_a_synthetic_split(tmp_path):
+    """train.fit = the reference's epoch loop (PCAA_ablation.py:866-1112) on the fused path: shuffled drop_last train
+    batches, eval-mode validation, best-validation checkpoint in the reference's file set."""
+    from opensetgaitrecognition_pcaa_b200 import loader, synth
+    from opensetgaitrecognition_pcaa_b200.train import build_variant4, fit
+    root = str(tmp_path / "data")
+    synth.write_dataset(root, 50, train_subjects=[0, 3], unseen_subjects=[5], crops_per_track=6, tracks_per_subject=3, seed=1)
+    train = loader.PackedCrops.from_directory(os.path.join(root, "train"))
+    valid = loader.PackedCrops.from_directory(os.path.join(root, "valid"))
+    tr = build_variant4(2, 50, seed=0)
+    cfg = dict(EPOCHS=3, BATCH_SIZE=8, CHECKPOINT_FREQUENCY=1)
+    seen = []
+    hist = fit(tr, train, valid, cfg, "PCAA_fit", root=str(tmp_path), np_rng=np.random.default_rng(0),
+               torch_gen=torch.Generator().manual_seed(0), shuffle_gen=torch.Generator().manual_seed(0), log=seen.append)
+    assert len(hist) == 3 and seen == hist
+    assert all(h["iterations"] == len(train) // 8 for h in hist) and tr.G.step == 3 * (len(train) // 8)
+    for h in hist:
+        for k in ("Reconstruction Loss Train", "Reconstruction Loss Valid", "Cross Entropy Loss Train", "Cross Entropy Loss Valid",
+                  "Discriminator Loss", "Total Loss Train"):
+            assert np.isfinite(h[k]), (k, h)
+        assert 0.0 <= h["Train Accuracy"] <= 1.0 and 0.0 <= h["Valid Accuracy"] <= 1.0
+    assert hist[-1]["Reconstruction Loss Train"] < hist[0]["Reconstruction Loss Train"]
+    d = os.path.join(str(tmp_path), "models", "PCAA_fit")
+    assert os.path.exists(os.path.join(d, "discriminator_means.pt"))
+    if any(h["saved"] for h in hist):
+        assert os.path.exists(os.path.join(d, "PCAA_fit_E.pt")) and os.path.exists(os.path.join(d, "PCAA_fit_GPH.pt"))
+    # the saved flags follow the reference's rule: strictly better validation accuracy than the best so far (from 0)
+    best = 0.0
+    for h in hist:
+        assert h["saved"] == (h["Valid Accuracy"] > best)
+        best = max(best, h["Valid Accuracy"])
+
+
 def test_module_autograd_path_matches_oracle():
     """The nn.Module surface driven the way the reference trainer drives it (stock autograd, torch.optim.Adam,
     autograd.grad(create_graph=True) through the critic)."""
