@@ -184,6 +184,18 @@ class DeviceCrops:
             yield self.batch(order[b * batch_size:(b + 1) * batch_size])
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
+    """One copy stream per device, shared by all prefetchers: the caching allocator pools blocks per stream, so the
+    device slots a finished prefetcher frees are reused by the next one instead of being cudaMalloc'ed again."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
 class DevicePrefetcher:
     """Iterate device copies of pinned host batches, copying one batch ahead on a dedicated stream.
 
@@ -198,7 +210,7 @@ class DevicePrefetcher:
         if self.dev.type != "cuda":
             raise RuntimeError("DevicePrefetcher copies to a CUDA device (no CPU fallback)")
         self.depth = max(2, depth)
-        self.stream = torch.cuda.Stream(device=self.dev)
+        self.stream = _copy_stream(self.dev)
         self.slots: List[Optional[Tuple[torch.Tensor, ...]]] = [None] * self.depth
         self.ready = [torch.cuda.Event() for _ in range(self.depth)]
         self.free = [None] * self.depth
