@@ -327,12 +327,14 @@ class _MeanLearnerFn(torch.autograd.Function):
                                        engine.BN_MOMENTUM, engine.BN_EPS)
                 bn.num_batches_tracked.add_(1)
             else:
-                coef = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, engine.BN_EPS)
+                c2 = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, engine.BN_EPS)
+                # (scale, shift, mean, invstd) as bn_finalize returns them, from the running statistics (16..64 floats)
+                coef = torch.stack([c2[0], c2[1], bn.running_mean.float(), torch.rsqrt(bn.running_var.float() + engine.BN_EPS)])
             a = ops.bn_elu_apply(y, coef[0], coef[1])
             sv.append((h, y, coef))
             h = a
         out = ops.gemm(h, m[9].weight, trans_b=True, bias=m[9].bias)
-        ctx.sv, ctx.h_last, ctx.module = sv, h, module
+        ctx.sv, ctx.h_last, ctx.module, ctx.training = sv, h, module, training
         return out
 
     @staticmethod
@@ -346,7 +348,13 @@ class _MeanLearnerFn(torch.autograd.Function):
         for idx, i in reversed(list(enumerate((0, 3, 6)))):
             h_in, y, coef = ctx.sv[idx]
             dz, st2 = ops.elu_bwd_colstats(d, y, coef)
-            c, dgam, dbet = ops.bn_bwd_finalize(st2, y.shape[0], coef)
+            if ctx.training:
+                c, dgam, dbet = ops.bn_bwd_finalize(st2, y.shape[0], coef)
+            else:
+                # running statistics are constants: dy = scale * dz, d gamma = sum dz * xhat, d beta = sum dz
+                Cc = y.shape[1]
+                c = torch.stack([coef[0], torch.zeros_like(coef[0]), torch.zeros_like(coef[0])])
+                dgam, dbet = st2[Cc:].float(), st2[:Cc].float()
             dy = ops.bn_bwd_apply(dz, y, c, out=dz)
             grads[f"{i + 1}.weight"], grads[f"{i + 1}.bias"] = dgam, dbet
             grads[f"{i}.weight"] = ops.gemm(dy, h_in, trans_a=True)

@@ -314,6 +314,47 @@ def test_fit_epoch_loop_on_a_synthetic_split(tmp_path):
         best = max(best, h["Valid Accuracy"])
 
 
+@pytest.mark.parametrize("train_mode", [True, False])
+def test_gaussian_mean_learner_matches_the_torch_module(train_mode):
+    """models.GaussianMeanLearner (variant 1's learned prototypes, models.py:424-443) against the same torch.nn
+    architecture on the CPU: output, gradients w.r.t. every parameter and the input, BatchNorm buffers."""
+    from opensetgaitrecognition_pcaa_b200 import models
+    torch.manual_seed(3)
+    C, Bn = 4, 16
+    ref = torch.nn.Sequential(
+        torch.nn.Linear(C, 16), torch.nn.BatchNorm1d(16), torch.nn.ELU(), torch.nn.Linear(16, 32), torch.nn.BatchNorm1d(32),
+        torch.nn.ELU(), torch.nn.Linear(32, 64), torch.nn.BatchNorm1d(64), torch.nn.ELU(), torch.nn.Linear(64, 32)).float()
+    with torch.no_grad():
+        for m in ref:
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.8, 1.2), m.bias.uniform_(-0.1, 0.1)
+                m.running_mean.uniform_(-0.1, 0.1), m.running_var.uniform_(0.8, 1.2)
+    ml = models.GaussianMeanLearner(C)
+    ml.model.load_state_dict(ref.state_dict())
+    ml.cuda().float()
+    ref.train(train_mode), ml.train(train_mode)
+    gt = torch.randint(0, C, (Bn,))
+    oh = torch.nn.functional.one_hot(gt, C).float() + 0.05 * torch.randn(Bn, C)       # near one-hot, every row distinct
+    xr = oh.clone().requires_grad_(True)
+    xg = oh.clone().cuda().requires_grad_(True)
+    w = torch.randn(Bn, 32)
+    yr = ref(xr)
+    (yr * w).sum().backward()
+    out = ml(xg)
+    (out * w.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert relmax(out, yr) < 1e-4
+    assert relmax(xg.grad, xr.grad) < 1e-3
+    for (k, pr), (_, pg) in zip(ref.named_parameters(), ml.model.named_parameters()):
+        # a Linear bias in front of a train-mode BatchNorm has an identically-zero gradient (fp noise on both sides)
+        if train_mode and k in ("0.bias", "3.bias", "6.bias"):
+            assert float(pg.grad.abs().max()) < 1e-4, k
+            continue
+        assert relmax(pg.grad, pr.grad) < 1e-3, (k, relmax(pg.grad, pr.grad))
+    for (k, br), (_, bg) in zip(ref.named_buffers(), ml.model.named_buffers()):
+        assert relmax(bg.float(), br.float()) < 1e-4, k
+
+
 def test_module_autograd_path_matches_oracle():
     """The nn.Module surface driven the way the reference trainer drives it (stock autograd, torch.optim.Adam,
     autograd.grad(create_graph=True) through the critic)."""
