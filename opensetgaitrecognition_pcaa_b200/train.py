@@ -85,14 +85,20 @@ class PCAATrainer:
         32->64 `decoder_projection_head`;
       * variant 2 = train_CGAAE (train_AAE.py:25-364): `decoder_projection_head=None`, the decoder reads sup_fv;
       * variant 3 (PCAA_ablation.py:392-743): `decoder=None`, no reconstruction term.
-    (Variant 1's learned prototypes, PCAA_ablation.py:28-378, run through the nn.Module surface: models.GaussianMeanLearner.)
+      * variant 1 (PCAA_ablation.py:28-378): variant 4 plus `mean_learner` = models.GaussianMeanLearner, whose output
+        for the batch's labels replaces the fixed prototypes (forward only: the reference's Variable() detaches it).
     """
 
     def __init__(self, encoder, decoder, discriminator, decoder_projection_head, means: torch.Tensor, config: dict,
-                 process_group=None):
+                 process_group=None, mean_learner=None):
         if decoder is None and decoder_projection_head is not None:
             raise ValueError("PCAATrainer: a decoder projection head needs a decoder")
         self.enc, self.dec, self.dis, self.gph = encoder, decoder, discriminator, decoder_projection_head
+        # variant 1 (PCAA_ablation.py:28-378): the class prototypes are the GaussianMeanLearner's output for the batch's
+        # one-hot labels (train-mode BatchNorm1d, so they depend on the batch composition).  In the reference
+        # `z = Variable(z0 + mus)` (:186) detaches, so the learner never receives a gradient although optimizer_D lists
+        # its parameters: it is a forward-only module here, its BatchNorm running statistics still move
+        self.ml = mean_learner
         dev = next(encoder.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("PCAATrainer needs CUDA modules (no CPU fallback)")
@@ -120,6 +126,7 @@ class PCAATrainer:
         self.xG = dp.GradExchange(self.G.g, process_group, side_stream=True, peer=self.G.peer)
         self.xD = dp.GradExchange(self.D.g, process_group)
         self._one = torch.ones((), device=dev, dtype=torch.float32)
+        self._zero_means = torch.zeros_like(self.means)
         # PCAA_WGRAD_OVERLAP=1 runs the PointNet weight-gradient GEMMs on their own stream, concurrently with the
         # BatchNorm-backward passes (engine.pointnet_backward).  Off by default: measured on B200 the step is power
         # capped (sw_power_cap, ~1.6-1.7 GHz under load) and the overlap buys nothing (21.99 vs 22.07 ms at B=256).
@@ -195,7 +202,13 @@ class PCAATrainer:
             torch._foreach_add_(self._nbt, 1)
             # critic step (PCAA_ablation.py:900-980): one fused kernel forms d_loss and its parameter gradients
             self.D.g.zero_()
-            st["d_losses"] = ops.wgangp_dstep(st["fv"], z0, self.means, gt, alphas.reshape(-1), *self.Dw, cfg["GP_WEIGHT"], self.Dg)
+            z0_eff, means_eff = z0, self.means
+            if self.ml is not None:
+                with torch.no_grad():
+                    self.ml.train()
+                    mus = self.ml(torch.nn.functional.one_hot(gt, self.C).float())
+                z0_eff, means_eff = z0 + mus, self._zero_means        # z = z0 + mus enters the kernel as its noise input
+            st["d_losses"] = ops.wgangp_dstep(st["fv"], z0_eff, means_eff, gt, alphas.reshape(-1), *self.Dw, cfg["GP_WEIGHT"], self.Dg)
 
         def exchange_critic():
             self.xD.start(0, self.D.size)
@@ -468,13 +481,17 @@ def fit(trainer: PCAATrainer, train, valid, config: dict, model_name: str, root:
 
 def build_variant(variant: int, n_classes: int, nmax: int, config: Optional[dict] = None, device="cuda",
                   seed: Optional[int] = None, process_group=None):
-    """Construct the networks of ablation variant 2 (= train_CGAAE, train_AAE.py:36-46), 3 (PCAA_ablation.py:407-419) or
-    4 (PCAA_ablation.py:764-786) as the reference does and wrap them in a PCAATrainer."""
+    """Construct the networks of ablation variant 1 (PCAA_ablation.py:40-64), 2 (= train_CGAAE, train_AAE.py:36-46),
+    3 (PCAA_ablation.py:407-419) or 4 (PCAA_ablation.py:764-786) as the reference does and wrap them in a PCAATrainer."""
     from . import models, utils
     if variant == 4:
         return build_variant4(n_classes, nmax, config, device, seed, process_group)
+    if variant == 1:        # PCAA_ablation.py:40-64: variant 4's networks + the mean learner
+        tr = build_variant4(n_classes, nmax, config, device, seed, process_group)
+        tr.ml = models.GaussianMeanLearner(n_classes).to(device).float()
+        return tr
     if variant not in (2, 3):
-        raise ValueError("build_variant: the fused trainer covers variants 2, 3 and 4 (variant 1: nn.Module surface)")
+        raise ValueError("build_variant: ablation variants are 1, 2, 3 and 4")
     if seed is not None:
         torch.manual_seed(seed)
     cfg = dict(LR=1e-4, B1=0.9, B2=0.99, GP_WEIGHT=15, ADV_WEIGHT=1, SUP_LATENT_DIM=32)

@@ -42,7 +42,7 @@ def split_state(p, prefix):
 def build_reference_models(models, p, C, nmax, variant=4):
     """variant 4: PCAA_ablation.py:764-786; variants 2 / 3: train_AAE.py:36-46, PCAA_ablation.py:407-419 (encoder
     without projection head, decoder fed by sup_fv; the unused heads are still built here and never stepped)."""
-    head = variant == 4
+    head = variant in (1, 4)
     enc = models.CGEncoder(n_out_labels=C, use_projection_head=head, nmax_points=nmax).float()
     dec = models.CGDecoder(input_dim=64 if head else 32, nmax_points=nmax).float()
     dis = models.CGDiscriminator(C).float()
@@ -53,12 +53,16 @@ def build_reference_models(models, p, C, nmax, variant=4):
     dis.load_state_dict(split_state(p, "D."))
     gph.load_state_dict(split_state(p, "GPH."))
     dph.load_state_dict(split_state(p, "DPH."))
+    if variant == 1:        # PCAA_ablation.py:61-64: the learned prototypes
+        ml = models.GaussianMeanLearner(C).float()
+        ml.load_state_dict(split_state(p, "ML."))
+        return enc, dec, dis, gph, dph, ml
     return enc, dec, dis, gph, dph
 
 
-def gather_state(enc, dec, dis, gph, dph):
+def gather_state(enc, dec, dis, gph, dph, ml=None):
     out = {}
-    for pre, m in (("E.", enc), ("GPH.", gph), ("G.", dec), ("DPH.", dph), ("D.", dis)):
+    for pre, m in (("E.", enc), ("GPH.", gph), ("G.", dec), ("DPH.", dph), ("D.", dis)) + ((("ML.", ml),) if ml is not None else ()):
         for k, v in m.state_dict().items():
             out[pre + k] = v.detach().clone()
     return out
@@ -167,7 +171,8 @@ def reference_step(constants, mods, opts, pcs, gt, z0, alphas, means, C, variant
     """One iteration with the reference's own modules, in the order of PCAA_ablation.py:882-1021 (variant 4),
     train_AAE.py:126-290 (variant 2) or PCAA_ablation.py:500-660 (variant 3) (driver written for this generator;
     arithmetic is the reference's)."""
-    enc, dec, dis, gph, dph = mods
+    enc, dec, dis, gph, dph = mods[:5]
+    ml = mods[5] if variant == 1 else None
     optG, optD = opts
     out = {}
     enc.train(); dec.train(); dis.train()
@@ -175,8 +180,14 @@ def reference_step(constants, mods, opts, pcs, gt, z0, alphas, means, C, variant
     out["logits"], out["fv"] = logits.detach().clone(), fv.detach().clone()
     optD.zero_grad(); dis.zero_grad(); dph.zero_grad()
     oh = torch.nn.functional.one_hot(gt, num_classes=C).float()
-    mus = torch.matmul(oh.unsqueeze(1), means.unsqueeze(0)).squeeze()
-    z = (z0 + mus).detach().requires_grad_(True)
+    if variant == 1:        # PCAA_ablation.py:170-190: z stays attached to the mean learner
+        ml.train()
+        mus = ml(oh)
+        z = torch.autograd.Variable(z0 + mus)
+        z.requires_grad = True
+    else:
+        mus = torch.matmul(oh.unsqueeze(1), means.unsqueeze(0)).squeeze()
+        z = (z0 + mus).detach().requires_grad_(True)
     real = dis(z, oh)
     fake = dis(fv.detach(), oh)
     diff = fv.detach() - z
@@ -189,6 +200,9 @@ def reference_step(constants, mods, opts, pcs, gt, z0, alphas, means, C, variant
     d_loss = torch.mean(fake) - torch.mean(real) + CFG["GP_WEIGHT"] * gp
     d_loss.backward()
     out["d_grads"] = {"D." + k: v.grad.detach().clone() for k, v in dis.named_parameters()}
+    if variant == 1:
+        # Variable(z0 + mus) detaches (PCAA_ablation.py:186): the learner's grads are None in the reference
+        out["d_grads"].update({"ML." + k: (None if v.grad is None else v.grad.detach().clone()) for k, v in ml.named_parameters()})
     optD.step()
     optD.zero_grad(); dis.zero_grad()
     optG.zero_grad(); enc.zero_grad(); dec.zero_grad(); gph.zero_grad()
@@ -198,12 +212,13 @@ def reference_step(constants, mods, opts, pcs, gt, z0, alphas, means, C, variant
         rec, rec_loss = torch.zeros(()), torch.zeros(())
         tot = loss_g + sup
     else:
-        rec = dec(gph(fv)) if variant == 4 else dec(fv)
+        rec = dec(gph(fv)) if variant in (1, 4) else dec(fv)
         rec_loss = utils_mod.SeqChamferLoss()(rec, pcs)
         tot = rec_loss + loss_g + sup
     tot.backward()
     gg = {}
-    for pre, m in {4: (("E.", enc), ("GPH.", gph), ("G.", dec)), 2: (("E.", enc), ("G.", dec)), 3: (("E.", enc),)}[variant]:
+    for pre, m in {4: (("E.", enc), ("GPH.", gph), ("G.", dec)), 1: (("E.", enc), ("GPH.", gph), ("G.", dec)),
+                   2: (("E.", enc), ("G.", dec)), 3: (("E.", enc),)}[variant]:
         for k, v in m.named_parameters():
             gg[pre + k] = None if v.grad is None else v.grad.detach().clone()
     out["g_grads"] = gg
@@ -215,10 +230,15 @@ def reference_step(constants, mods, opts, pcs, gt, z0, alphas, means, C, variant
 
 def step_case(constants, models, utils, name, B, nmax, C, seed, nsteps=2, variant=4):
     import itertools
-    p0 = O.det_params(C, nmax, seed) if variant == 4 else O.det_params(C, nmax, seed, use_projection_head=False, dec_in=32)
+    p0 = {4: lambda: O.det_params(C, nmax, seed), 1: lambda: O.det_params(C, nmax, seed, mean_learner=True)}.get(
+        variant, lambda: O.det_params(C, nmax, seed, use_projection_head=False, dec_in=32))()
     mods = build_reference_models(models, p0, C, nmax, variant)
-    enc, dec, dis, gph, dph = mods
-    if variant == 4:        # PCAA_ablation.py:821-833
+    enc, dec, dis, gph, dph = mods[:5]
+    if variant == 1:        # PCAA_ablation.py:102-112: optimizer_D steps the mean learner and the critic
+        optG = torch.optim.Adam(itertools.chain(enc.parameters(), gph.parameters(), dec.parameters()),
+                                lr=CFG["LR"], betas=(CFG["B1"], CFG["B2"]))
+        optD = torch.optim.Adam(itertools.chain(mods[5].parameters(), dis.parameters()), lr=CFG["LR"], betas=(CFG["B1"], CFG["B2"]))
+    elif variant == 4:      # PCAA_ablation.py:821-833
         optG = torch.optim.Adam(itertools.chain(enc.parameters(), gph.parameters(), dec.parameters()),
                                 lr=CFG["LR"], betas=(CFG["B1"], CFG["B2"]))
         optD = torch.optim.Adam(itertools.chain(dph.parameters(), dis.parameters()), lr=CFG["LR"],
@@ -534,7 +554,11 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     constants, models, utils_mod = load_reference()
-    if "--variants-only" in sys.argv:          # just the variant-2 / variant-3 step vectors
+    if "--variant1-only" in sys.argv:
+        step_case(constants, models, utils_mod, "v1_n50_c4_b8", 8, 50, 4, seed=7, variant=1)
+        sys.exit(0)
+    if "--variants-only" in sys.argv:          # just the variant-1 / -2 / -3 step vectors
+        step_case(constants, models, utils_mod, "v1_n50_c4_b8", 8, 50, 4, seed=7, variant=1)
         step_case(constants, models, utils_mod, "v2_n50_c2_b4", 4, 50, 2, seed=5, variant=2)
         step_case(constants, models, utils_mod, "v3_n50_c4_b4", 4, 50, 4, seed=6, variant=3)
         sys.exit(0)
@@ -542,6 +566,7 @@ if __name__ == "__main__":
     module_case(constants, models, utils_mod, "n70_c4_b3", 3, 70, 4, seed=1)
     step_case(constants, models, utils_mod, "n50_c2_b4", 4, 50, 2, seed=0)
     step_case(constants, models, utils_mod, "n150_c4_b2", 2, 150, 4, seed=2, nsteps=1)
+    step_case(constants, models, utils_mod, "v1_n50_c4_b8", 8, 50, 4, seed=7, variant=1)
     step_case(constants, models, utils_mod, "v2_n50_c2_b4", 4, 50, 2, seed=5, variant=2)
     step_case(constants, models, utils_mod, "v3_n50_c4_b4", 4, 50, 4, seed=6, variant=3)
     scoring_case()

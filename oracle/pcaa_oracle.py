@@ -161,6 +161,19 @@ def proj_head_forward(p: Params, fv: torch.Tensor, pre: str = "GPH.") -> torch.T
     return elu(fv @ p[pre + "0.weight"].t() + p[pre + "0.bias"])
 
 
+def mean_learner_forward(p: Params, onehot: torch.Tensor, training: bool, update: Optional[dict] = None,
+                         pre: str = "ML.") -> torch.Tensor:
+    """GaussianMeanLearner.forward, models.py:424-443: 3 x (Linear, BatchNorm1d, ELU) + Linear(64, 32)."""
+    h = onehot
+    for i in (0, 3, 6):
+        k = f"{pre}model.{i}."
+        kb = f"{pre}model.{i + 1}."
+        y = h @ p[k + "weight"].t() + p[k + "bias"]
+        h = elu(batchnorm_rows(y, p[kb + "weight"], p[kb + "bias"], p[kb + "running_mean"], p[kb + "running_var"],
+                               training, update, kb))
+    return h @ p[f"{pre}model.9.weight"].t() + p[f"{pre}model.9.bias"]
+
+
 def disc_forward(p: Params, x: torch.Tensor, onehot: torch.Tensor, pre: str = "D.") -> torch.Tensor:
     """CGDiscriminator.forward, models.py:418-421."""
     h = torch.cat([x, onehot], dim=-1)
@@ -291,16 +304,23 @@ def train_step(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict
     * variant 2 -- the base ``train_CGAAE`` loop, ``train_AAE.py:126-290`` (= ``train_variant2``,
       ``PCAA_ablation.py:381-389``): encoder without projection head, ``CGDecoder()`` fed by ``sup_fv`` directly;
     * variant 3 -- no decoder, ``PCAA_ablation.py:500-660``: ``tot = loss_g + sup``, and optimizer_G uses
-      ``betas=(B1, B1)`` (``PCAA_ablation.py:452-456``).
+      ``betas=(B1, B1)`` (``PCAA_ablation.py:452-456``, SURVEY 9.2);
+    * variant 1 -- variant 4's networks with the GaussianMeanLearner's prototypes, ``PCAA_ablation.py:130-330``: ``mus``
+      is the learner's output (train-mode BatchNorm1d over the batch of one-hot labels, so it depends on the batch
+      composition), ``means`` is only used for its class count.  Reference quirk (verified by running it): ``z =
+      Variable(z0 + mus)`` (``:186``) DETACHES, so although optimizer_D is built over ``chain(mean_learner,
+      discriminator)`` (``:108-112``) the learner's parameters never receive a gradient (``grad is None``, Adam skips
+      them); only its BatchNorm running statistics move.
 
     cfg: LR, B1, B2, GP_WEIGHT, ADV_WEIGHT, NMAX.  ``z0`` (B,32) and ``alphas`` (B,1) are the host RNG draws of
     PCAA_ablation.py:915-931 / 944-948.  Returns losses, the class predictions and every gradient (by name).
     """
-    assert variant in (2, 3, 4)
+    assert variant in (1, 2, 3, 4)
     C = means.shape[0]
     nmax = cfg["NMAX"]
-    head = variant == 4
-    g_prefixes = {4: G_PREFIXES, 2: ("E.", "G."), 3: ("E.",)}[variant]
+    head = variant in (1, 4)
+    g_prefixes = {4: G_PREFIXES, 1: G_PREFIXES, 2: ("E.", "G."), 3: ("E.",)}[variant]
+    d_prefixes = ("ML.", "D.") if variant == 1 else D_PREFIXES
     b2_g = cfg["B1"] if variant == 3 else cfg["B2"]
     out: dict = {}
     # leaf copies that require grad (clone_leaves=False: differentiate the stored tensors in place -- what the
@@ -316,12 +336,12 @@ def train_step(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict
     out["logits"], out["fv"] = logits.detach(), fv.detach()
     out["pred"] = torch.argmax(torch.softmax(logits.detach(), dim=1), dim=1)
     onehot = torch.nn.functional.one_hot(gt, C).float()
-    mus = onehot @ means
+    mus = mean_learner_forward(q, onehot, True, upd).detach() if variant == 1 else onehot @ means
     z = z0 + mus
 
     # ---- discriminator step
     dl, gp = d_loss_fn(q, fv.detach(), z, onehot, alphas, cfg["GP_WEIGHT"])
-    d_names = trainable_names(p, D_PREFIXES)
+    d_names = trainable_names(p, d_prefixes)
     d_grads = torch.autograd.grad(dl, [q[n] for n in d_names], allow_unused=True)
     out["d_loss"], out["gp"] = dl.detach(), gp.detach()
     out["d_grads"] = {n: (None if g is None else g.detach()) for n, g in zip(d_names, d_grads)}
@@ -340,7 +360,7 @@ def train_step(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict
         rec_loss = torch.zeros(())
         tot = loss_g + sup
     else:
-        rec = decoder_forward(q, proj_head_forward(q, fv) if variant == 4 else fv, nmax)
+        rec = decoder_forward(q, proj_head_forward(q, fv) if head else fv, nmax)
         rec_loss, i1, i2 = chamfer(rec, pcs)
         tot = rec_loss + loss_g + sup
         out.update(rec=rec.detach(), idx_gt_for_pred=i1, idx_pred_for_gt=i2)
@@ -354,7 +374,7 @@ def train_step(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict
         for k, v in upd.items():
             p[k] = v
         for k in p:
-            if k.endswith("num_batches_tracked") and k.startswith("E."):
+            if k.endswith("num_batches_tracked") and (k.startswith("E.") or (variant == 1 and k.startswith("ML."))):
                 p[k] = p[k] + 1
     return out
 
@@ -494,9 +514,18 @@ def naive_sequential_procedure(k: int, test_emb, test_pred, test_labels, unseen_
 # deterministic parameters / inputs shared by the golden generator and the tests
 # --------------------------------------------------------------------------- #
 def param_shapes(n_classes: int, nmax: int, use_projection_head: bool = True,
-                 dec_in: int = 64) -> Dict[str, Tuple[int, ...]]:
-    """state_dict names and shapes of CGEncoder / proj-head / CGDecoder / CGDiscriminator."""
+                 dec_in: int = 64, mean_learner: bool = False) -> Dict[str, Tuple[int, ...]]:
+    """state_dict names and shapes of CGEncoder / proj-head / CGDecoder / CGDiscriminator (/ GaussianMeanLearner)."""
     s: Dict[str, Tuple[int, ...]] = {}
+    if mean_learner:
+        dims = [n_classes, 16, 32, 64, SUP_LATENT_DIM]
+        for j, i in enumerate((0, 3, 6, 9)):
+            s[f"ML.model.{i}.weight"] = (dims[j + 1], dims[j])
+            s[f"ML.model.{i}.bias"] = (dims[j + 1],)
+            if i < 9:
+                for nm in ("weight", "bias", "running_mean", "running_var"):
+                    s[f"ML.model.{i + 1}.{nm}"] = (dims[j + 1],)
+                s[f"ML.model.{i + 1}.num_batches_tracked"] = ()
     for l in range(1, 5):
         ci, co = POINTNET_DIMS[l - 1], POINTNET_DIMS[l]
         k = f"E.pc_block.pointnet{l}.module."
@@ -549,12 +578,14 @@ def param_shapes(n_classes: int, nmax: int, use_projection_head: bool = True,
 
 
 def det_params(n_classes: int, nmax: int, seed: int = 0, use_projection_head: bool = True,
-               dec_in: int = 64) -> Params:
+               dec_in: int = 64, mean_learner: bool = False) -> Params:
     """Deterministic (numpy PCG64) parameters with torch-default-like scales and
     non-trivial BatchNorm affine / running statistics."""
     rng = np.random.default_rng(seed)
     p: Params = {}
-    for name, shp in param_shapes(n_classes, nmax, use_projection_head, dec_in).items():
+    shapes = param_shapes(n_classes, nmax, use_projection_head, dec_in, mean_learner)
+    ml_bn = tuple(f"ML.model.{i}." for i in (1, 4, 7))
+    for name, shp in shapes.items():
         if name.endswith("num_batches_tracked"):
             p[name] = torch.tensor(0, dtype=torch.int64)
             continue
@@ -562,13 +593,17 @@ def det_params(n_classes: int, nmax: int, seed: int = 0, use_projection_head: bo
             a = 0.1 * rng.standard_normal(shp)
         elif name.endswith("running_var"):
             a = rng.uniform(0.5, 1.5, shp)
+        elif name.startswith(ml_bn) and name.endswith("weight"):
+            a = 1.0 + 0.1 * rng.standard_normal(shp)
+        elif name.startswith(ml_bn) and name.endswith("bias"):
+            a = 0.1 * rng.standard_normal(shp)
         elif (".1.weight" in name or "batch_norm.weight" in name or (".bn" in name and name.endswith("weight"))):
             a = 1.0 + 0.1 * rng.standard_normal(shp)
         elif (".1.bias" in name or "batch_norm.bias" in name or (".bn" in name and name.endswith("bias"))):
             a = 0.1 * rng.standard_normal(shp)
         else:
             wname = name.rsplit(".", 1)[0] + ".weight"
-            wshape = param_shapes(n_classes, nmax, use_projection_head, dec_in)[wname]
+            wshape = shapes[wname]
             fan_in = int(np.prod(wshape[1:]))
             bound = 1.0 / math.sqrt(fan_in)
             a = rng.uniform(-bound, bound, shp)

@@ -114,7 +114,7 @@ def _oracle_step(p, ost, pcs, gt, z0, alphas, means, nmax, variant=4):
     return O.train_step(p, ost, pcs, gt, z0, alphas, means, dict(CFG, NMAX=nmax), variant)
 
 
-@pytest.mark.parametrize("name", ["n50_c2_b4", "n150_c4_b2", "v2_n50_c2_b4", "v3_n50_c4_b4"])
+@pytest.mark.parametrize("name", ["n50_c2_b4", "n150_c4_b2", "v2_n50_c2_b4", "v3_n50_c4_b4", "v1_n50_c4_b8"])
 def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
     """The fused trainer against the oracle and the reference's golden values: variant 4 (the paper's PCAA), variant 2
     (= train_CGAAE, the decoder reads sup_fv) and variant 3 (no decoder, optimizer_G betas (B1, B1))."""
@@ -122,13 +122,20 @@ def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
     gd = np.load(os.path.join(golden_dir, f"step_{name}.npz"))
     B, nmax, C, seed, nsteps = (int(gd[k]) for k in ("B", "nmax", "C", "seed", "nsteps"))
     variant = int(gd["variant"]) if "variant" in gd.files else 4
-    p = O.det_params(C, nmax, seed) if variant == 4 else O.det_params(C, nmax, seed, use_projection_head=False, dec_in=32)
-    if variant != 4:
+    p = {4: lambda: O.det_params(C, nmax, seed), 1: lambda: O.det_params(C, nmax, seed, mean_learner=True)}.get(
+        variant, lambda: O.det_params(C, nmax, seed, use_projection_head=False, dec_in=32))()
+    if variant in (2, 3):
         p = {k: v for k, v in p.items() if not k.startswith(("GPH.", "DPH.")) and not (variant == 3 and k.startswith("G."))}
     po = {k: v.clone() for k, v in p.items()}
-    enc, dec, dis, gph = build(p, C, nmax, variant)
+    enc, dec, dis, gph = build(p, C, nmax, 4 if variant == 1 else variant)
+    ml = None
+    if variant == 1:        # the mean learner's prototypes replace the fixed ones (forward only, as in the reference)
+        from opensetgaitrecognition_pcaa_b200 import models
+        ml = models.GaussianMeanLearner(C)
+        ml.load_state_dict({k[3:]: v.clone() for k, v in p.items() if k.startswith("ML.")})
+        ml.cuda().float()
     means = torch.from_numpy(gd["means"])
-    tr = PCAATrainer(enc, dec, dis, gph, means, dict(CFG, B2_G=CFG["B1"]) if variant == 3 else CFG)
+    tr = PCAATrainer(enc, dec, dis, gph, means, dict(CFG, B2_G=CFG["B1"]) if variant == 3 else CFG, mean_learner=ml)
     ost = {}
     rng = np.random.default_rng(999 + seed)
     for s in range(nsteps):
@@ -168,7 +175,7 @@ def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
     # weights after the Adam updates
     lr = CFG["LR"]
     nbad = ntot = 0
-    for pre, m in (("E.", enc), ("G.", dec), ("D.", dis), ("GPH.", gph)):
+    for pre, m in (("E.", enc), ("G.", dec), ("D.", dis), ("GPH.", gph), ("ML.", ml)):
         for k, v in (m.state_dict().items() if m is not None else ()):
             if not v.dtype.is_floating_point:
                 assert int(v) == int(po[pre + k]), k

@@ -83,14 +83,15 @@ def test_modules_oracle_vs_reference_golden(golden_dir, name):
             assert int(gd[k]) == 0, k
 
 
-@pytest.mark.parametrize("name", ["n50_c2_b4", "v2_n50_c2_b4", "v3_n50_c4_b4"])
+@pytest.mark.parametrize("name", ["n50_c2_b4", "v1_n50_c4_b8", "v2_n50_c2_b4", "v3_n50_c4_b4"])
 def test_train_step_oracle_vs_reference_golden(golden_dir, name):
     """Two iterations of the variant-4 (PCAA_ablation.py:882-1021), variant-2 (train_AAE.py:126-290) and variant-3
     (PCAA_ablation.py:500-660) loops at B=4, N=50: losses, embeddings, gradient digests."""
     gd = np.load(os.path.join(golden_dir, f"step_{name}.npz"))
     variant = int(gd["variant"]) if "variant" in gd.files else 4
     B, nmax, C, seed, nsteps = (int(gd[k]) for k in ("B", "nmax", "C", "seed", "nsteps"))
-    p = O.det_params(C, nmax, seed) if variant == 4 else O.det_params(C, nmax, seed, use_projection_head=False, dec_in=32)
+    p = {4: lambda: O.det_params(C, nmax, seed), 1: lambda: O.det_params(C, nmax, seed, mean_learner=True)}.get(
+        variant, lambda: O.det_params(C, nmax, seed, use_projection_head=False, dec_in=32))()
     means = torch.from_numpy(gd["means"])
     assert maxdiff(O.sample_distant_points(32, C, 10, 10).float(), means) == 0.0
     ost = {}
