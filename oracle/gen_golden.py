@@ -575,4 +575,7 @@ if __name__ == "__main__":
     with open(os.path.join(GOLD, "PIN.txt"), "w") as f:
         f.write("oracle pinned against the reference run in the build container (oracle/gen_golden.py)\n"
                 f"unmodified PCAA_ablation.train_variant4, 2 iterations, max |param diff| vs oracle replay = {w:.3e} "
-                f"(bound 2*lr*steps: Adam sign steps on fp-noise gradients), fraction of weights off by > 2e-6 = {frac:.2e}\n")
+                f"(bound 2*lr*steps: Adam sign steps on fp-noise gradients), fraction of weights off by > 2e-6 = {frac:.2e}\n"
+                "ablation variants 1 / 2 / 3: two iterations each through the reference's own modules + torch.optim.Adam "
+                "(step_v1_*, step_v2_*, step_v3_*.npz; per-quantity |oracle - reference| stored as pin_* inside each file; "
+                "variant 1: the reference's Variable(z0 + mus) detaches, the mean learner's grads are None there and here)\n")
