@@ -116,6 +116,19 @@ int pcaa_pointnet_l1_wgrad(const float* x, const void* dy, float* dW, int64_t B,
  * with scale/shift (eval mode, BatchNorm folded) the stored value is ELU(scale[c]*y + shift[c]) instead. */
 int pcaa_pointnet_l1_fwd_t(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
                            void* yT, double* stats, int64_t B, int64_t TN, int Cout, pcaa_stream stream);
+/* train mode with the BatchNorm coefficients known up front (pcaa_bn_from_input_moments): ONE pass writes both the
+ * pre-BatchNorm y (yT, kept for the backward) and a = ELU(scale[c]*y + shift[c]) (aT) -- models.py:21-34 for the K = 4 layer. */
+int pcaa_pointnet_l1_fwd_bn_t(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
+                              void* yT, void* aT, int64_t B, int64_t TN, int Cout, pcaa_stream stream);
+/* mom[14] (double, overwritten) = { sum_p x_f (f = 0..3), sum_p x_f x_g (f <= g, row-major upper triangle) } over the B*TN
+ * points of x (B,4,TN): all that BatchNorm 1's batch statistics depend on, because y1 = W1 x + b1 is linear in x. */
+int pcaa_input_moments(const float* x, int64_t B, int64_t TN, double* mom, pcaa_stream stream);
+/* BatchNorm2d batch statistics + running-statistics update (models.py:29; momentum, unbiased variance) of the layer
+ * y = w x + bias, w [C,4], from the input moments of R points: mean_c = w_c.mu + bias_c, var_c = w_c^T Cov(x) w_c.
+ * Outputs as pcaa_bn_finalize: scale = gamma*invstd, shift = beta - mean*scale, mean, invstd (each [C], mean/invstd nullable). */
+int pcaa_bn_from_input_moments(const double* mom, int64_t R, int C, const float* w, const float* bias, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                               float* scale, float* shift, float* mean, float* invstd, pcaa_stream stream);
 /* dW[Cout,4] (overwritten) = sum_p dy(c,p) x[f,p], dy = c1[c]*dzT + c2[c]*yT + c3[c] (BatchNorm backward fused; yT and
  * the coefficients null: dy = dzT) */
 int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, const float* c1, const float* c2,
@@ -187,6 +200,27 @@ int pcaa_ew(int op, const float* a, const float* b, float* out, int64_t n, int n
  * col is fp32 or bf16 (col_dtype: the tensor-core GEMM operand) */
 int pcaa_tcn_im2col(const float* x, void* col, int col_dtype, int64_t B, int T, int Cin, int dil, pcaa_stream stream);
 int pcaa_tcn_col2im(const float* dcol, float* dx, int64_t B, int T, int Cin, int dil, pcaa_stream stream);
+/* ---- fused steps of one DilTempConv1d layer (models.py:37-79; the [B*T, C] tensors are tiny, the fusion removes launches)
+ * forward, after the layer's GEMM y[B*T, C] (+ column statistics from its epilogue): BatchNorm1d + ELU (models.py:72-78).
+ *   training: stats[2*C] = [sum_r y, sum_r y^2]; coef_out[4*C] receives scale | shift | mean | invstd, the running
+ *   statistics are updated (momentum, unbiased variance);  eval: stats null, scale / shift given.
+ *   Outputs (either may be null): col = bf16 im2col operand of the NEXT layer (dilation dil_next), col[(b,t), c*3+k] =
+ *   a[b, t-(2-k)*dil_next, c] (0 for negative time); act = fp32 activation a[B*T, C]. */
+int pcaa_tcn_bn_elu_next(const float* y, const double* stats, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float momentum, float eps, const float* scale,
+                         const float* shift, float* coef_out, int64_t B, int T, int C, int dil_next, void* col, float* act,
+                         pcaa_stream stream);
+/* backward pass 1: dz[B*T, C] = d * ELU'(scale*y + shift), stats2[2*C] += [sum dz, sum dz*xhat]; d comes from
+ *   src_mode 0: src[B*T, C];  1: the col2im of the layer above's d-im2col src[B*T, C*3] (its dilation dil_up);
+ *   2: src[B, C] / T broadcast over the T frames (backward of AvgPool1d(NSTEPS), models.py:249, 284). */
+int pcaa_tcn_elu_bwd_stats(const float* src, int src_mode, int dil_up, const float* y, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, float* dz, double* stats2,
+                           int64_t B, int T, int C, pcaa_stream stream);
+/* backward pass 2: BatchNorm1d backward from the completed sums, dy (bf16 [R, C]) = c1*dz + c2*y + c3; d gamma = sum dz*xhat,
+ *   d beta = sum dz (nullable) */
+int pcaa_tcn_bn_bwd_apply(const float* dz, const float* y, const double* stats2, const float* scale, const float* mean,
+                          const float* invstd, float* dgamma, float* dbeta, void* dy, int64_t R, int C,
+                          pcaa_stream stream);
 /* out[g,c] = mean_i x[g,i,c] (AvgPool1d(NSTEPS), models.py:249,284) and its backward */
 int pcaa_mean_rows(const float* x, float* out, int64_t G, int n, int C, pcaa_stream stream);
 int pcaa_mean_rows_bwd(const float* g, float* dx, int64_t G, int n, int C, pcaa_stream stream);

@@ -29,6 +29,9 @@ SIGNATURES = {
     "pcaa_pointnet_l1_wgrad": [_p, _p, _p, _l, _l, _i, _p],
     "pcaa_pointnet_l1_fwd_t": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _p],
     "pcaa_pointnet_l1_wgrad_t": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _p],
+    "pcaa_pointnet_l1_fwd_bn_t": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _p],
+    "pcaa_input_moments": [_p, _l, _l, _p, _p],
+    "pcaa_bn_from_input_moments": [_p, _l, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p],
     "pcaa_bn_elu_apply_t": [_p, _p, _p, _p, _l, _i, _p],
     "pcaa_bn_bwd_apply_t": [_p, _p, _p, _p, _p, _p, _l, _i, _p],
     "pcaa_bn_elu_meanpool_t": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
@@ -49,6 +52,9 @@ SIGNATURES = {
     "pcaa_pack_bf16": [_p, _l, _l, _l, _p, _l, _i, _p],
     "pcaa_tcn_im2col": [_p, _p, _i, _l, _i, _i, _i, _p],
     "pcaa_tcn_col2im": [_p, _p, _l, _i, _i, _i, _p],
+    "pcaa_tcn_bn_elu_next": [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _l, _i, _i, _i, _p, _p, _p],
+    "pcaa_tcn_elu_bwd_stats": [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
+    "pcaa_tcn_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _p],
     "pcaa_mean_rows": [_p, _p, _l, _i, _i, _p],
     "pcaa_mean_rows_bwd": [_p, _p, _l, _i, _i, _p],
     "pcaa_softmax_ce": [_p, _p, _p, _p, _f, _p, _l, _i, _p],

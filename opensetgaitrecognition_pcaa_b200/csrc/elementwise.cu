@@ -264,6 +264,161 @@ elu_bwd_colstats_kernel(const TD* __restrict__ dout, const float* __restrict__ d
     block_col_reduce(s1, s2, cg, lane, cgs, lanes, cgg, ncg, stats2, C);
 }
 
+// ------------------------------------------------------------------------------------------------ fused TCN layer steps
+// The six causal-conv layers (models.py:37-79, 108-160) work on [B*30, C <= 1024] matrices: every step is a few
+// microseconds, so the layer pipeline is fused to cut launches (and the round trips of intermediates), not bytes.
+
+// forward, after the layer's GEMM (whose epilogue accumulated the column statistics): BatchNorm1d coefficients (batch
+// statistics in training -- then block 0 also publishes them and updates the running statistics --, given scale / shift
+// in eval) + ELU, written as the NEXT layer's bf16 im2col operand ([R, C*3], tap k of channel c at column c*3 + k holds
+// the activation dil_next*(2-k) steps earlier, zero before the sequence start) and / or as the fp32 activation.
+__global__ void __launch_bounds__(256)
+tcn_bn_elu_next_kernel(const float* __restrict__ y, const double* __restrict__ stats, double invR, double unbias,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float* rmean, float* rvar,
+                       float momentum, float eps, const float* __restrict__ scale_in, const float* __restrict__ shift_in,
+                       float* __restrict__ coef_out, int64_t R, int T, int C, int dil_next,
+                       __nv_bfloat16* __restrict__ col, float* __restrict__ act) {
+    extern __shared__ float sm[];
+    float* sc = sm;
+    float* sh = sm + C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        if (stats != nullptr) {
+            const double mean = stats[c] * invR;
+            double var = stats[C + c] * invR - mean * mean;
+            if (var < 0) var = 0;
+            const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+            const float s = gamma[c] * invstd;
+            sc[c] = s;
+            sh[c] = beta[c] - (float)mean * s;
+            if (blockIdx.x == 0) {
+                coef_out[c] = s;
+                coef_out[C + c] = sh[c];
+                coef_out[2 * C + c] = (float)mean;
+                coef_out[3 * C + c] = invstd;
+                if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+                if (rvar) rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)(var * unbias);
+            }
+        } else {
+            sc[c] = scale_in[c];
+            sh[c] = shift_in[c];
+        }
+    }
+    __syncthreads();
+    const int64_t total = R * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t r = i / C;
+        const float a = elu_f(fmaf(y[i], sc[c], sh[c]));
+        if (act) act[i] = a;
+        if (col) {
+            const int t = (int)(r % T);
+            __nv_bfloat16* o = col + i * 3;
+            o[2] = __float2bfloat16_rn(a);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int ts = t - (2 - k) * dil_next;
+                o[k] = __float2bfloat16_rn(ts >= 0 ? elu_f(fmaf(y[(r - t + ts) * C + c], sc[c], sh[c])) : 0.f);
+            }
+        }
+    }
+}
+
+// backward, first pass of a layer: the gradient d reaching its activation is formed on the fly --
+//   src_mode 0: d = src[R, C];
+//   src_mode 1: col2im of the layer above, d[(b,t), c] = sum_k src[(b, t + (2-k)*dil_up), c*3 + k] for t + (2-k)*dil_up < T
+//               (src = that layer's d im2col [R, C*3]);
+//   src_mode 2: the mean over the T frames broadcast back, d[(b,t), c] = src[b, c] / T (src [R/T, C]);
+// then dz = d * ELU'(scale*y + shift) is stored and stats2 += [sum dz, sum dz * xhat] (the BatchNorm-backward sums).
+__global__ void __launch_bounds__(256)
+tcn_elu_bwd_stats_kernel(const float* __restrict__ src, int src_mode, int dil_up, int T,
+                         const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dz,
+                         double* stats2, int64_t R, int C, int cgs, int lanes) {
+    int cg = threadIdx.x % cgs, lane = threadIdx.x / cgs;
+    int ncg = C / 8;
+    int cgg = blockIdx.x * cgs + cg;
+    float s1[8] = {0}, s2[8] = {0};
+    if (cgg < ncg) {
+        float sc[8], sh[8], mu[8], is[8];
+        load8f(scale + cgg * 8, sc);
+        load8f(shift + cgg * 8, sh);
+        load8f(mean + cgg * 8, mu);
+        load8f(invstd + cgg * 8, is);
+        const float invT = 1.f / (float)T;
+        for (int64_t r = (int64_t)blockIdx.y * lanes + lane; r < R; r += (int64_t)gridDim.y * lanes) {
+            float v[8], d[8];
+            V8<float>::load(y + r * C + cgg * 8, v);
+            if (src_mode == 0) {
+                V8<float>::load(src + r * C + cgg * 8, d);
+            } else if (src_mode == 2) {
+                load8f(src + (r / T) * C + cgg * 8, d);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] *= invT;
+            } else {
+                const int t = (int)(r % T);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int to = t + (2 - k) * dil_up;
+                    if (to < T) {
+                        const float* q = src + ((r - t + to) * C + cgg * 8) * 3 + k;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) d[i] += __ldg(q + 3 * i);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float z = fmaf(v[i], sc[i], sh[i]);
+                float g = d[i] * elu_grad_f(z);
+                float xh = (v[i] - mu[i]) * is[i];
+                d[i] = g;
+                s1[i] += g;
+                s2[i] += g * xh;
+            }
+            V8<float>::store(dz + r * C + cgg * 8, d);
+        }
+    }
+    block_col_reduce(s1, s2, cg, lane, cgs, lanes, cgg, ncg, stats2, C);
+}
+
+// backward, second pass: BatchNorm-backward coefficients from the completed sums (every block derives them for all C
+// channels; block 0 also writes d gamma / d beta), dy = c1*dz + c2*y + c3 stored as the bf16 operand of the two GEMMs
+__global__ void __launch_bounds__(256)
+tcn_bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, const double* __restrict__ stats2,
+                        double invR, const float* __restrict__ scale, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                        __nv_bfloat16* __restrict__ dy, int64_t R, int C) {
+    extern __shared__ float sm[];
+    float* c1 = sm;
+    float* c2 = sm + C;
+    float* c3 = sm + 2 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double t1 = stats2[c], t2 = stats2[C + c];
+        const double s = scale[c], is = invstd[c], mu = mean[c];
+        c1[c] = (float)s;
+        c2[c] = (float)(-s * is * t2 * invR);
+        c3[c] = (float)(-s * t1 * invR + s * is * mu * t2 * invR);
+        if (blockIdx.x == 0) {
+            if (dgamma) dgamma[c] = (float)t2;
+            if (dbeta) dbeta[c] = (float)t1;
+        }
+    }
+    __syncthreads();
+    const int ncg = C / 8;
+    const int64_t nchunks = R * ncg;
+    for (int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(ch % ncg) * 8;
+        float z[8], v[8];
+        V8<float>::load(dz + ch * 8, z);
+        V8<float>::load(y + ch * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = fmaf(c1[c0 + i], z[i], fmaf(c2[c0 + i], v[i], c3[c0 + i]));
+        V8<__nv_bfloat16>::store(dy + ch * 8, z);
+    }
+}
+
 __global__ void bn_bwd_finalize_kernel(const double* stats2, double invR, int C, const float* scale,
                                        const float* mean, const float* invstd, float* c1, float* c2, float* c3,
                                        float* dgamma, float* dbeta) {
@@ -450,9 +605,12 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_
     se = warp_sum(se);
     float lse = mx + logf(se);
     int t = (int)gt[warp];
+    // a label outside [0, C) (the reference raises on it) must not index the logits: its loss term is NaN instead, so the
+    // batch loss and every gradient downstream turn NaN -- loud, without a host synchronisation
+    const bool t_ok = t >= 0 && t < C;
     if (lane == 0) {
         if (pred) pred[warp] = am;
-        if (loss) atomicAdd(loss, (lse - l[t]) / (float)B);
+        if (loss) atomicAdd(loss, t_ok ? (lse - l[t]) / (float)B : NAN);
     }
     if (dlogits) {
         float s = gscale / (float)B;
@@ -854,6 +1012,50 @@ int pcaa_tcn_col2im(const float* dcol, float* dx, int64_t B, int T, int Cin, int
     int64_t total = B * T * Cin;
     tcn_col2im_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(dcol, dx, B * T, T, Cin, dil);
     return check_launch("tcn_col2im");
+}
+
+int pcaa_tcn_bn_elu_next(const float* y, const double* stats, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float momentum, float eps, const float* scale,
+                         const float* shift, float* coef_out, int64_t B, int T, int C, int dil_next, void* col, float* act,
+                         pcaa_stream stream) {
+    const int64_t R = B * T;
+    if (R == 0) return PCAA_OK;
+    PCAA_REQUIRE(C > 0 && C <= 4096, PCAA_ERR_SHAPE, "tcn_bn_elu_next: C=%d out of range", C);
+    PCAA_REQUIRE((stats != nullptr) != (scale != nullptr && shift != nullptr), PCAA_ERR_SHAPE,
+                 "tcn_bn_elu_next: give either the batch statistics (training) or scale / shift (eval)");
+    PCAA_REQUIRE(stats == nullptr || (gamma && beta && coef_out), PCAA_ERR_SHAPE, "tcn_bn_elu_next: training needs gamma, beta, coef_out");
+    PCAA_REQUIRE(col != nullptr || act != nullptr, PCAA_ERR_SHAPE, "tcn_bn_elu_next: no output requested");
+    PCAA_REQUIRE(col == nullptr || dil_next > 0, PCAA_ERR_SHAPE, "tcn_bn_elu_next: the im2col output needs the next layer's dilation");
+    const double unbias = R > 1 ? (double)R / (double)(R - 1) : 1.0;
+    int grid = ew_grid((R * C + 3) / 4);
+    tcn_bn_elu_next_kernel<<<grid, 256, 2 * C * sizeof(float), ST(stream)>>>(y, stats, 1.0 / (double)R, unbias, gamma, beta,
+                                                                           running_mean, running_var, momentum, eps, scale,
+                                                                           shift, coef_out, R, T, C, dil_next,
+                                                                           (__nv_bfloat16*)col, act);
+    return check_launch("tcn_bn_elu_next");
+}
+
+int pcaa_tcn_elu_bwd_stats(const float* src, int src_mode, int dil_up, const float* y, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, float* dz, double* stats2,
+                           int64_t B, int T, int C, pcaa_stream stream) {
+    const int64_t R = B * T;
+    PCAA_REQUIRE(C % 8 == 0 && C > 0 && R > 0, PCAA_ERR_SHAPE, "tcn_elu_bwd_stats: C=%d must be a multiple of 8", C);
+    PCAA_REQUIRE(src_mode >= 0 && src_mode <= 2 && (src_mode != 1 || dil_up > 0), PCAA_ERR_SHAPE, "tcn_elu_bwd_stats: bad source mode");
+    ColGeom g = col_geom(R, C);
+    size_t smem = 256 * 16 * sizeof(float);
+    tcn_elu_bwd_stats_kernel<<<g.grid, g.block, smem, ST(stream)>>>(src, src_mode, dil_up, T, y, scale, shift, mean, invstd, dz,
+                                                                  stats2, R, C, g.cgs, g.lanes);
+    return check_launch("tcn_elu_bwd_stats");
+}
+
+int pcaa_tcn_bn_bwd_apply(const float* dz, const float* y, const double* stats2, const float* scale, const float* mean,
+                          const float* invstd, float* dgamma, float* dbeta, void* dy, int64_t R, int C,
+                          pcaa_stream stream) {
+    PCAA_REQUIRE(C % 8 == 0 && C > 0 && C <= 4096 && R > 0, PCAA_ERR_SHAPE, "tcn_bn_bwd_apply: C=%d must be a multiple of 8", C);
+    int grid = ew_grid(R * (C / 8));
+    tcn_bn_bwd_apply_kernel<<<grid, 256, 3 * C * sizeof(float), ST(stream)>>>(dz, y, stats2, 1.0 / (double)R, scale, mean, invstd,
+                                                                            dgamma, dbeta, (__nv_bfloat16*)dy, R, C);
+    return check_launch("tcn_bn_bwd_apply");
 }
 
 int pcaa_mean_rows(const float* x, float* out, int64_t G, int n, int C, pcaa_stream stream) {

@@ -90,7 +90,11 @@ struct L1Coef { float w[4]; float bias, scale, shift, scale_l2, shift_l2, pad0, 
 __global__ void __launch_bounds__(256, 3)
 pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                          const float* __restrict__ scale, const float* __restrict__ shift,
-                         __nv_bfloat16* __restrict__ yT, double* __restrict__ stats, int64_t P, int64_t TN, int Cout) {
+                         __nv_bfloat16* __restrict__ yT, __nv_bfloat16* __restrict__ aT, double* __restrict__ stats,
+                         int64_t P, int64_t TN, int Cout) {
+    // aT == nullptr: one output -- yT receives y = W x + b, or ELU(scale*y + shift) when scale is given (eval mode).
+    // aT != nullptr (train mode with BatchNorm coefficients known up front, pcaa_bn_from_input_moments): yT receives y
+    // AND aT receives ELU(scale*y + shift) in the same pass -- y is never re-read to form the activation.
     __shared__ L1Coef coef[8 * L1_CH_PER_WARP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 8 * L1_CH_PER_WARP) {
@@ -140,11 +144,12 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
                 s2[k] = fmaf(v, v, s2[k]);
                 y[j] = v;
             }
+            if (aT != nullptr && c0 + k < Cout) *reinterpret_cast<uint4*>(yT + t256(p0, c0 + k, Cout)) = pack8(y);
             if (act) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) y[j] = j < vcnt ? elu_l2(fmaf(y[j], bk.y, bk.z), fmaf(y[j], bk.w, shl)) : 0.f;
             }
-            if (c0 + k < Cout) *reinterpret_cast<uint4*>(yT + t256(p0, c0 + k, Cout)) = pack8(y);
+            if (c0 + k < Cout) *reinterpret_cast<uint4*>((aT != nullptr ? aT : yT) + t256(p0, c0 + k, Cout)) = pack8(y);
         }
     }
     if (stats) {
@@ -157,6 +162,98 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ layer 1 BatchNorm statistics
+// y1 = W1 x + b1 is LINEAR in the 4 input features, so the batch statistics of BatchNorm 1 follow from the first and second
+// moments of x alone:  mean_c = W1[c].mu + b_c,  var_c = W1[c]^T (E[x x^T] - mu mu^T) W1[c]  -- 14 numbers instead of a pass
+// over the [512, P] tensor.  mom = { sum_p x_f (4), sum_p x_f x_g for f <= g (10) } in double.
+__global__ void __launch_bounds__(256)
+input_moments_kernel(const float* __restrict__ x, int64_t P, int64_t TN, double* __restrict__ mom) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) q[i] = 0.f;
+    double ds[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) ds[i] = 0.0;
+    int flush = 0;
+    for (int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8; p0 < P; p0 += (int64_t)gridDim.x * 256 * 8) {
+        float xv[4][8];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);          // out-of-range points read as 0
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int i = 0;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                s[f] += xv[f][j];
+#pragma unroll
+                for (int g = f; g < 4; ++g) {
+                    q[i] = fmaf(xv[f][j], xv[g][j], q[i]);
+                    ++i;
+                }
+            }
+        }
+        if (++flush == 16) {       // fp32 partial sums of at most 128 points, then double
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ds[i] += (double)s[i]; s[i] = 0.f; }
+#pragma unroll
+            for (int i = 0; i < 10; ++i) { ds[4 + i] += (double)q[i]; q[i] = 0.f; }
+            flush = 0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ds[i] += (double)s[i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) ds[4 + i] += (double)q[i];
+    __shared__ double red[8][14];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+        const double t = warp_sum_d(ds[i]);
+        if (lane == 0) red[warp][i] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 14) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        atomicAdd(mom + threadIdx.x, t);
+    }
+}
+
+// BatchNorm coefficients (scale, shift, mean, invstd as pcaa_bn_finalize gives them) + running-statistics update of a
+// BatchNorm that follows a K = 4 linear layer, from the input moments
+__global__ void bn_from_input_moments_kernel(const double* __restrict__ mom, double invR, double unbias, int C,
+                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                             const float* gamma, const float* beta, float* rmean, float* rvar,
+                                             float momentum, float eps, float* scale, float* shift, float* mean_o,
+                                             float* invstd_o) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double mu[4], cov[4][4];
+    int i = 0;
+    for (int f = 0; f < 4; ++f) mu[f] = mom[f] * invR;
+    for (int f = 0; f < 4; ++f)
+        for (int g = f; g < 4; ++g) {
+            cov[f][g] = cov[g][f] = mom[4 + i] * invR - mu[f] * mu[g];
+            ++i;
+        }
+    double wv[4];
+    for (int f = 0; f < 4; ++f) wv[f] = (double)w[c * 4 + f];
+    double mean = bias ? (double)bias[c] : 0.0, var = 0.0;
+    for (int f = 0; f < 4; ++f) {
+        mean += wv[f] * mu[f];
+        for (int g = 0; g < 4; ++g) var += wv[f] * cov[f][g] * wv[g];
+    }
+    if (var < 0) var = 0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    if (mean_o) mean_o[c] = (float)mean;
+    if (invstd_o) invstd_o[c] = invstd;
+    if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+    if (rvar) rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)(var * unbias);
 }
 
 // ------------------------------------------------------------------------------------------------ layer 1 weight gradient
@@ -815,8 +912,42 @@ int pcaa_pointnet_l1_fwd_t(const float* x, const float* w, const float* bias, co
     PCAA_REQUIRE(((uintptr_t)yT & 15) == 0 && ((uintptr_t)w & 15) == 0 && Cout > 0, PCAA_ERR_ALIGN, "pointnet_l1_fwd_t: alignment / Cout");
     PCAA_REQUIRE((scale == nullptr) == (shift == nullptr), PCAA_ERR_SHAPE, "pointnet_l1_fwd_t: scale and shift go together");
     dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
-    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, stats, P, TN, Cout);
+    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, nullptr, stats, P, TN, Cout);
     return check_launch("pointnet_l1_fwd_t");
+}
+
+int pcaa_pointnet_l1_fwd_bn_t(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
+                              void* yT, void* aT, int64_t B, int64_t TN, int Cout, pcaa_stream stream) {
+    if (B == 0) return PCAA_OK;
+    const int64_t P = B * TN;
+    PCAA_REQUIRE(((uintptr_t)yT & 15) == 0 && ((uintptr_t)aT & 15) == 0 && ((uintptr_t)w & 15) == 0 && Cout > 0, PCAA_ERR_ALIGN,
+                 "pointnet_l1_fwd_bn_t: alignment / Cout");
+    PCAA_REQUIRE(yT && aT && scale && shift, PCAA_ERR_SHAPE, "pointnet_l1_fwd_bn_t: needs both outputs and the BatchNorm coefficients");
+    dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
+    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, (__nv_bfloat16*)aT, nullptr, P, TN, Cout);
+    return check_launch("pointnet_l1_fwd_bn_t");
+}
+
+int pcaa_input_moments(const float* x, int64_t B, int64_t TN, double* mom, pcaa_stream stream) {
+    if (cudaMemsetAsync(mom, 0, sizeof(double) * 14, ST(stream)) != cudaSuccess) return check_launch("input_moments memset");
+    if (B == 0) return PCAA_OK;
+    const int64_t P = B * TN;
+    int grid = (int)ceil_div(P, 256 * 8 * 4);
+    if (grid > 148 * 4) grid = 148 * 4;
+    if (grid < 1) grid = 1;
+    input_moments_kernel<<<grid, 256, 0, ST(stream)>>>(x, P, TN, mom);
+    return check_launch("input_moments");
+}
+
+int pcaa_bn_from_input_moments(const double* mom, int64_t R, int C, const float* w, const float* bias, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                               float* scale, float* shift, float* mean, float* invstd, pcaa_stream stream) {
+    PCAA_REQUIRE(R > 0 && C > 0, PCAA_ERR_SHAPE, "bn_from_input_moments: empty");
+    const double unbias = R > 1 ? (double)R / (double)(R - 1) : 1.0;
+    bn_from_input_moments_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(mom, 1.0 / (double)R, unbias, C, w, bias, gamma, beta,
+                                                                         running_mean, running_var, momentum, eps, scale,
+                                                                         shift, mean, invstd);
+    return check_launch("bn_from_input_moments");
 }
 
 int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, const float* c1, const float* c2,

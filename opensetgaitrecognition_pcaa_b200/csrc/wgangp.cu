@@ -123,12 +123,17 @@ wgangp_dstep_kernel(const float* __restrict__ fv, const float* __restrict__ z0, 
     float acc_loss = 0.f, acc_gp = 0.f, acc_fake = 0.f, acc_real = 0.f, acc_gb3 = 0.f;
     int s0 = blockIdx.x * spb, s1 = min(B, s0 + spb);
     for (int s = s0; s < s1; ++s) {
-        const int lab = (int)labels[s];
+        const int lab_raw = (int)labels[s];
+        // a label outside [0, C) (the reference's one_hot raises on it) must not index the prototypes: the sample's noise
+        // input becomes NaN instead, so d_loss and the critic gradients turn NaN -- loud, without a host synchronisation
+        const bool lab_ok = lab_raw >= 0 && lab_raw < C;
+        const int lab = lab_ok ? lab_raw : 0;
+        const float lab_nan = lab_ok ? 0.f : NAN;
         // ---- real (pass 0, dout = -1/B, input z) and fake (pass 1, dout = +1/B, input fv)
         for (int pass = 0; pass < 2; ++pass) {
             if (t < D) {
                 float v;
-                if (t < XD) v = pass == 0 ? z0[s * XD + t] + means[lab * XD + t] : fv[s * XD + t];
+                if (t < XD) v = pass == 0 ? z0[s * XD + t] + means[lab * XD + t] + lab_nan : fv[s * XD + t];
                 else v = (t - XD == lab) ? 1.f : 0.f;
                 m.u[t] = v;
             }
@@ -159,7 +164,7 @@ wgangp_dstep_kernel(const float* __restrict__ fv, const float* __restrict__ z0, 
         if (t < D) {
             float v;
             if (t < XD) {
-                float zz = z0[s * XD + t] + means[lab * XD + t];
+                float zz = z0[s * XD + t] + means[lab * XD + t] + lab_nan;
                 v = zz + alphas[s] * (fv[s * XD + t] - zz);
             } else v = (t - XD == lab) ? 1.f : 0.f;
             m.u[t] = v;

@@ -31,8 +31,13 @@ import torch
 import torch.distributed as dist
 
 
+SINGLE = "single"      # process_group sentinel: behave as one rank even inside an initialised multi-rank job (parity checks)
+
+
 def world_info(group=None) -> Tuple[int, int]:
-    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised or group is dp.SINGLE."""
+    if isinstance(group, str) and group == SINGLE:
+        return 0, 1
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
@@ -248,3 +253,89 @@ def gather_scores(local: torch.Tensor, counts: Sequence[int], group=None) -> Opt
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad, group=group)
     return torch.cat([o[:c] for o, c in zip(outs, counts)])
+
+
+def _checksum(t: torch.Tensor) -> torch.Tensor:
+    """Two int64 checksums of the bit pattern of an fp32 tensor (plain and position-weighted sums of its int32 view)."""
+    v = t.view(torch.int32).to(torch.int64)
+    w = (torch.arange(v.numel(), device=t.device, dtype=torch.int64) % 65521) + 1
+    return torch.stack([v.sum(), (v * w).sum()])
+
+
+@torch.no_grad()
+def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
+    """Data-parallel parity of ONE iteration run the way the benchmark runs it (`trainer.step_graphed`: split CUDA graphs
+    + the gradient exchange actually selected), checked on every rank against a single-device emulation of the same
+    global iteration.  Collective: call on all ranks with this rank's `inputs` = (pcs, gt, z0, alphas).
+
+    Emulation (trainer built by `make_single()` with process_group=dp.SINGLE, stepped phase by phase from a snapshot of
+    this trainer's state): pass A runs encoder forward + critic gradients on every rank's shard and sums the critic
+    gradients; pass B repeats the forward per shard, installs the MEAN critic gradient (what the exchange + Adam give every
+    rank), runs the generator forward / backward and sums the generator gradients.  Expected:
+      rel_g, rel_d   ||g_dp - sum_shards g|| / ||sum_shards g||  (generator / critic flat gradients) ~ reduction-order noise
+      frac_p_off     fraction of generator weights that differ by > 2e-6 from Adam(snapshot, mean gradient)
+      replicas_identical   every rank holds bit-identical generator and critic weights after the iteration
+    Returns the dict (same on all ranks); `ok` is the verdict."""
+    rank, world = world_info(group)
+    dev = trainer.dev
+    snap = trainer.snapshot()
+    trainer.step_graphed(*inputs)
+    torch.cuda.synchronize(dev)
+    g_dp, d_dp = trainer.G.g.clone(), trainer.D.g.clone()
+    gathered = []
+    for t in inputs:
+        outs = [torch.empty_like(t) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(outs, t.contiguous(), group=group)
+        else:
+            outs = [t]
+        gathered.append(outs)
+    ref = make_single()
+    if ref.world != 1:
+        raise RuntimeError("graphed_step_parity: make_single() must build the trainer with process_group=dp.SINGLE")
+    dsum = torch.zeros_like(d_dp)
+    for r in range(world):                                             # pass A: critic gradients of every shard
+        ref.restore(snap)
+        phases, _ = ref._phases(*[g[r] for g in gathered])
+        phases[0][1]()
+        dsum += ref.D.g
+    gsum = torch.zeros_like(g_dp)
+    for r in range(world):                                             # pass B: generator gradients under the mean critic step
+        ref.restore(snap)
+        phases, _ = ref._phases(*[g[r] for g in gathered])
+        phases[0][1]()
+        ref.D.g.copy_(dsum / world)
+        for _, fn in phases[2:]:
+            fn()
+        gsum += ref.G.g
+    torch.cuda.synchronize(dev)
+    rel_g = float((g_dp - gsum).norm() / gsum.norm())
+    rel_d = float((d_dp - dsum).norm() / dsum.norm())
+    # weights: Adam of the mean gradient from the snapshot, through the same fused kernel
+    ref.restore(snap)
+    ref.G.g.copy_(gsum / world)
+    from . import ops
+    cfg = ref.cfg
+    b2_g = cfg.get("B2_G", cfg["B2"])
+    ops.adam_advance(ref.G.step_dev, ref.G.coef_dev, cfg["LR"], cfg["B1"], b2_g)
+    ops.adam_flat_dev(ref.G.p, ref.G.g, ref.G.m, ref.G.v, cfg["B1"], b2_g, 1e-8, ref.G.coef_dev, 1.0, ref.G.shadow)
+    frac_p_off = float(((trainer.G.p - ref.G.p).abs() > 2e-6).float().mean())
+    cs = torch.cat([_checksum(trainer.G.p), _checksum(trainer.D.p)])
+    allcs = [torch.empty_like(cs) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allcs, cs, group=group)
+    else:
+        allcs = [cs]
+    same = all(torch.equal(allcs[0], c) for c in allcs)
+    res = torch.tensor([rel_g, rel_d, frac_p_off], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(res, op=dist.ReduceOp.MAX, group=group)
+    rel_g, rel_d, frac_p_off = (float(x) for x in res)
+    peer = getattr(trainer.G, "peer", None)
+    out = {"rel_g": rel_g, "rel_d": rel_d, "frac_p_off": frac_p_off, "replicas_identical": bool(same),
+           "exchange": "peer" if peer is not None else ("nccl" if world > 1 else "none"), "world": world,
+           "path": "step_graphed (split graphs)" if trainer.split_graphs else "step_graphed (one graph)",
+           "ok": bool(rel_g < 2e-3 and rel_d < 2e-3 and frac_p_off < 1e-2 and same)}
+    del ref
+    torch.cuda.empty_cache()
+    return out

@@ -9,6 +9,7 @@ head / decoder activations are fp32 ``[rows, C]``.  Reference: models.py:82-160,
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -17,6 +18,9 @@ from . import ops
 from ._lib import (ACT_ELU, ACT_NONE, OP_MN, OP_T256_K, OP_T256_MN, TC_BIAS_ELU, TC_BIAS_STATS, TC_DGRAD_ELUBN, TC_DGRAD_ELUOUT, TC_PLAIN,
                    TC_T_AFFINE_ELU, TC_T_BIAS_STATS, TC_T_DGRAD_ELUBN, TC_WGRAD_ACC, TC_WGRAD_STORE)
 
+# PCAA_TCN_FUSED=0 selects the unfused TCN layer pipeline (im2col, GEMM, colstats, finalize, apply as separate launches):
+# kept for A/B timing of the fused one
+TCN_FUSED = os.environ.get("PCAA_TCN_FUSED", "1") == "1"
 T_STEPS = 30
 DTC_DILATIONS = (1, 2, 4, 1, 2, 4)
 BN_MOMENTUM = 0.1
@@ -31,11 +35,24 @@ def _out(gradbuf: Optional[Grads], name: str):
 
 
 def _zeros_like_param(gradbuf, name, ref):
+    """A zeroed gradient tensor for `name`.  A gradient buffer that sets "__zeroed__" (the fused trainer: ONE fill of its
+    flat encoder span per iteration) hands its slot out as it is."""
     t = _out(gradbuf, name)
     if t is None:
         return torch.zeros_like(ref)
-    t.zero_()
+    if not gradbuf.get("__zeroed__", False):
+        t.zero_()
     return t
+
+
+def _stats_arena(sizes, device):
+    """One zero-filled double buffer for several [2*C] BatchNorm statistics accumulators (one fill instead of one each)."""
+    buf = torch.zeros(2 * sum(sizes), device=device, dtype=torch.float64)
+    out, o = [], 0
+    for c in sizes:
+        out.append(buf[o:o + 2 * c])
+        o += 2 * c
+    return out
 
 
 # ====================================================================================================== PointNet
@@ -64,10 +81,15 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
 
     b1 = P[f"{pre}pointnet1.module.0.bias"]
     if training:
-        y, st = ops.pointnet_l1_fwd_t(x, _conv_w(P, pre, 1), b1)
-        coef = bn_coef(1, st)
-        a = ops.bn_elu_apply_t(y, coef, R)
+        # y1 = W1 x + b1 is linear in the 4 input features: BatchNorm 1's batch statistics follow from the input moments
+        # (14 numbers), so the coefficients exist BEFORE y1 does and one pass writes y1 and a1 = ELU(BN(y1)) -- y1 is not
+        # re-read for the activation (-2.4 GB of HBM traffic at B = 256)
+        k1 = f"{pre}pointnet1.module.1."
+        coef = ops.bn_from_input_moments(ops.input_moments(x), R, _conv_w(P, pre, 1), b1, P[k1 + "weight"], P[k1 + "bias"],
+                                         P[k1 + "running_mean"], P[k1 + "running_var"], BN_MOMENTUM, BN_EPS)
+        y, a = ops.pointnet_l1_fwd_bn_t(x, _conv_w(P, pre, 1), b1, coef)
         sv["y"][1], sv["coef"][1], sv["a"][1] = y, coef, a
+        arena = dict(zip((2, 3, 4), _stats_arena([_conv_w(P, pre, l).shape[0] for l in (2, 3, 4)], x.device)))
     else:
         a, _ = ops.pointnet_l1_fwd_t(x, _conv_w(P, pre, 1), b1, coef=bn_coef(1, None))
     for l in (2, 3, 4):
@@ -76,7 +98,7 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
         wb = wb16[l] if wb16 is not None else ops.pack_bf16(W)
         bias = P[f"{pre}pointnet{l}.module.0.bias"]
         if training:
-            st = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64)
+            st = arena[l]
             y = ops.gemm_tc(wb, a, TC_T_BIAS_STATS, Cout, R, Cin, b_mn=OP_T256_MN, bias=bias, stats=st)
             coef = bn_coef(l, st)
             sv["y"][l], sv["coef"][l], sv["wb"][l] = y, coef, wb
@@ -115,6 +137,7 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
     c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][4], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
     G[kb + "weight"], G[kb + "bias"] = dgam, dbet
     dy = ops.pool_bwd_apply_t(gpool, sv["y"][4], sv["coef"][4], c, N)
+    arena = dict(zip((4, 3, 2), _stats_arena([P[f"{pre}pointnet{l}.module.0.weight"].shape[1] for l in (4, 3, 2)], gpool.device)))
     for l in (4, 3, 2):
         kc = f"{pre}pointnet{l}.module.0."
         W = P[kc + "weight"]
@@ -135,7 +158,7 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
         # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero
         G[kc + "bias"] = _zeros_like_param(gradbuf, kc + "bias", P[kc + "bias"])
         # dz_{l-1}T [Cin, P] = (W^T dyT) * ELU'(BN(y_{l-1})) with the statistics of BatchNorm l-1's backward
-        st2 = torch.zeros(2 * Cin, device=gpool.device, dtype=torch.float64)
+        st2 = arena[l]
         dz = ops.gemm_tc(sv["wb"][l], dy, TC_T_DGRAD_ELUBN, Cin, R, Cout, a_mn=OP_MN, b_mn=OP_T256_MN, stats=st2,
                          yprev=sv["y"][l - 1], coef=sv["coef"][l - 1])
         kb = f"{pre}pointnet{l - 1}.module.1."
@@ -158,13 +181,52 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
 
 
 # ====================================================================================================== TCN
+def _tcn_bn(P: Params, k: str):
+    return (P[k + "batch_norm.weight"], P[k + "batch_norm.bias"], P[k + "batch_norm.running_mean"], P[k + "batch_norm.running_var"])
+
+
 def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block.", wb16: Optional[dict] = None):
-    """h [B, T, 1024] fp32 -> [B, T, 512]; causal dilated conv (im2col + tcgen05 GEMM, bf16 operands, fp32 accumulate /
+    """h [B, T, 1024] fp32 -> [B, T, 512]; causal dilated conv (bf16 im2col operand + tcgen05 GEMM, fp32 accumulate /
     output) + BatchNorm1d + ELU, six times.  ``wb16`` optionally maps the layer number to a ready bf16 copy of the
-    [Cout, Cin*3] weight (the trainer's Adam-maintained shadow)."""
+    [Cout, Cin*3] weight (the trainer's Adam-maintained shadow).
+
+    Per layer two launches: the GEMM, whose epilogue also accumulates the BatchNorm column statistics (training), and one
+    kernel that turns those into coefficients, applies BatchNorm + ELU and writes the result directly as the NEXT layer's
+    im2col operand (the last layer writes the fp32 activation)."""
     B, T, _ = h.shape
     R = B * T
     sv = {"B": B, "T": T, "col": [], "y": [], "coef": [], "cin": [], "wb": []}
+    if not TCN_FUSED:
+        return _tcn_forward_unfused(h, P, training, pre, wb16, sv)
+    chans = [P[f"{pre}dtc{l}.conv1d.weight"].shape[0] for l in range(1, 7)]
+    arena = _stats_arena(chans, h.device) if training else [None] * 6
+    col = ops.tcn_im2col(h, DTC_DILATIONS[0], torch.bfloat16)
+    act = None
+    for l in range(1, 7):
+        k = f"{pre}dtc{l}."
+        W = P[k + "conv1d.weight"]
+        Cout, Cin, _ = W.shape
+        wb = wb16[l] if wb16 is not None else ops.pack_bf16(W.view(Cout, Cin * 3))
+        gamma, beta, rmean, rvar = _tcn_bn(P, k)
+        dil_next = DTC_DILATIONS[l] if l < 6 else 0
+        if training:
+            y = ops.gemm_tc(col, wb, TC_BIAS_STATS, R, Cout, Cin * 3, bias=P[k + "conv1d.bias"], stats=arena[l - 1],
+                            out_dtype=torch.float32)
+            nxt, act, coef = ops.tcn_bn_elu_next(y, B, T, stats=arena[l - 1], gamma=gamma, beta=beta, running_mean=rmean,
+                                                 running_var=rvar, momentum=BN_MOMENTUM, eps=BN_EPS, dil_next=dil_next,
+                                                 want_act=(l == 6))
+        else:
+            y = ops.gemm_tc(col, wb, TC_PLAIN, R, Cout, Cin * 3, bias=P[k + "conv1d.bias"], out_dtype=torch.float32)
+            coef = ops.bn_eval_coeffs(gamma, beta, rmean, rvar, BN_EPS)
+            nxt, act, _ = ops.tcn_bn_elu_next(y, B, T, scale=coef[0], shift=coef[1], dil_next=dil_next, want_act=(l == 6))
+        sv["col"].append(col), sv["y"].append(y), sv["coef"].append(coef), sv["cin"].append(Cin), sv["wb"].append(wb)
+        col = nxt
+    return act.view(B, T, -1), sv
+
+
+def _tcn_forward_unfused(h, P, training, pre, wb16, sv):
+    B, T, _ = h.shape
+    R = B * T
     for l in range(1, 7):
         k = f"{pre}dtc{l}."
         W = P[k + "conv1d.weight"]
@@ -174,19 +236,57 @@ def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block
         y = ops.gemm_tc(col, wb, TC_PLAIN, R, Cout, Cin * 3, bias=P[k + "conv1d.bias"], out_dtype=torch.float32)
         if training:
             st = ops.colstats(y)
-            coef = ops.bn_finalize(st, R, P[k + "batch_norm.weight"], P[k + "batch_norm.bias"],
-                                   P[k + "batch_norm.running_mean"], P[k + "batch_norm.running_var"], BN_MOMENTUM, BN_EPS)
+            coef = ops.bn_finalize(st, R, *_tcn_bn(P, k), BN_MOMENTUM, BN_EPS)
         else:
-            coef = ops.bn_eval_coeffs(P[k + "batch_norm.weight"], P[k + "batch_norm.bias"],
-                                      P[k + "batch_norm.running_mean"], P[k + "batch_norm.running_var"], BN_EPS)
+            coef = ops.bn_eval_coeffs(*_tcn_bn(P, k), BN_EPS)
         a = ops.bn_elu_apply(y, coef[0], coef[1])
         sv["col"].append(col), sv["y"].append(y), sv["coef"].append(coef), sv["cin"].append(Cin), sv["wb"].append(wb)
         h = a.view(B, T, Cout)
     return h, sv
 
 
-def tcn_backward(dout: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = None, pre: str = "tc_block."):
-    """dout [B, T, 512] -> (d input [B, T, 1024], parameter gradients)."""
+def tcn_backward(dout: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = None, pre: str = "tc_block.",
+                 dout_is_frame_mean: bool = False):
+    """dout [B, T, 512] (or, with dout_is_frame_mean, the gradient [B, 512] of the mean over the T frames, whose broadcast
+    is then formed inside the first kernel) -> (d input [B, T, 1024], parameter gradients).
+
+    Per layer four launches: ELU' * d + BatchNorm-backward sums (d read straight from the layer above's d-im2col: the
+    col2im is folded in), BatchNorm backward -> bf16 dy (coefficients and d gamma / d beta derived in the same kernel),
+    weight-gradient GEMM, data-gradient GEMM."""
+    G: Grads = {}
+    B, T = sv["B"], sv["T"]
+    R = B * T
+    if not TCN_FUSED:
+        if dout_is_frame_mean:
+            dout = ops.mean_rows_bwd(dout, T)
+        return _tcn_backward_unfused(dout, sv, P, gradbuf, pre)
+    chans = [P[f"{pre}dtc{l}.conv1d.weight"].shape[0] for l in range(1, 7)]
+    arena = _stats_arena(chans, dout.device)
+    src, mode, dil_up = dout.reshape(-1, dout.shape[-1]).contiguous(), (2 if dout_is_frame_mean else 0), 0
+    for l in range(6, 0, -1):
+        k = f"{pre}dtc{l}."
+        W = P[k + "conv1d.weight"]
+        Cout, Cin, _ = W.shape
+        y, coef, col, wb = sv["y"][l - 1], sv["coef"][l - 1], sv["col"][l - 1], sv["wb"][l - 1]
+        if len(coef) < 4:
+            raise RuntimeError("tcn_backward: the forward ran in eval mode (no batch statistics were saved)")
+        dz = ops.tcn_elu_bwd_stats(src, mode, dil_up, y, coef, arena[l - 1], B, T)
+        dy, dgam, dbet = ops.tcn_bn_bwd_apply(dz, y, arena[l - 1], coef, _out(gradbuf, k + "batch_norm.weight"),
+                                              _out(gradbuf, k + "batch_norm.bias"))
+        G[k + "batch_norm.weight"], G[k + "batch_norm.bias"] = dgam, dbet
+        # dW [Cout, Cin*3] += dy^T col (k = the B*T rows, split over the SMs), dcol = dy W
+        dW = _zeros_like_param(gradbuf, k + "conv1d.weight", W)
+        ops.gemm_tc(dy, col, TC_WGRAD_ACC, Cout, Cin * 3, R, a_mn=OP_MN, b_mn=OP_MN, out=dW.view(Cout, Cin * 3))
+        G[k + "conv1d.weight"] = dW
+        # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero (sum_rows dy = 0)
+        G[k + "conv1d.bias"] = _zeros_like_param(gradbuf, k + "conv1d.bias", P[k + "conv1d.bias"])
+        src = ops.gemm_tc(dy, wb, TC_PLAIN, R, Cin * 3, Cout, b_mn=OP_MN, out_dtype=torch.float32)
+        mode, dil_up = 1, DTC_DILATIONS[l - 1]
+    d = ops.tcn_col2im(src, B, T, sv["cin"][0], DTC_DILATIONS[0])
+    return d.view(B, T, -1), G
+
+
+def _tcn_backward_unfused(dout, sv, P, gradbuf, pre):
     G: Grads = {}
     B, T = sv["B"], sv["T"]
     R = B * T
@@ -201,11 +301,9 @@ def tcn_backward(dout: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = N
                                             _out(gradbuf, k + "batch_norm.bias"))
         G[k + "batch_norm.weight"], G[k + "batch_norm.bias"] = dgam, dbet
         dy = ops.bn_bwd_apply(dz, y, c, out_dtype=torch.bfloat16)
-        # dW [Cout, Cin*3] += dy^T col (k = the B*T rows, split over the SMs), dcol = dy W
         dW = _zeros_like_param(gradbuf, k + "conv1d.weight", W)
         ops.gemm_tc(dy, col, TC_WGRAD_ACC, Cout, Cin * 3, R, a_mn=OP_MN, b_mn=OP_MN, out=dW.view(Cout, Cin * 3))
         G[k + "conv1d.weight"] = dW
-        # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero (sum_rows dy = 0)
         G[k + "conv1d.bias"] = _zeros_like_param(gradbuf, k + "conv1d.bias", P[k + "conv1d.bias"])
         dcol = ops.gemm_tc(dy, wb, TC_PLAIN, R, Cin * 3, Cout, b_mn=OP_MN, out_dtype=torch.float32)
         d = ops.tcn_col2im(dcol, B, T, Cin, DTC_DILATIONS[l - 1]).view(R, Cin)
@@ -240,7 +338,8 @@ def heads_forward(h6: torch.Tensor, P: Params, use_projection_head: bool):
 
 def heads_backward(dlogits: Optional[torch.Tensor], dfv_ext: Optional[torch.Tensor], sv, P: Params,
                    gradbuf: Optional[Grads] = None):
-    """Returns (d h6 [B,T,512], grads).  dfv_ext is the gradient reaching sup_fv from outside the encoder."""
+    """Returns (d g [B,512] = gradient of the frame mean of h6, grads).  dfv_ext is the gradient reaching sup_fv from
+    outside the encoder."""
     G: Grads = {}
     fv = sv["fv"]
     dfv = None if dfv_ext is None else dfv_ext.clone()
@@ -257,7 +356,7 @@ def heads_backward(dlogits: Optional[torch.Tensor], dfv_ext: Optional[torch.Tens
         for n in ("MLP_sup2.0.weight", "MLP_sup2.0.bias") + (("MLP_head.0.weight", "MLP_head.0.bias") if sv["head"] else ()):
             G[n] = _zeros_like_param(gradbuf, n, P[n])
     dg = linear_backward(dfv, sv["g"], fv, P["MLP_sup1.0.weight"], "MLP_sup1.0.weight", "MLP_sup1.0.bias", G, gradbuf)
-    return ops.mean_rows_bwd(dg, sv["T"]), G
+    return dg, G        # [B, 512]: the gradient of the mean over frames; tcn_backward broadcasts it (/ T) in its first kernel
 
 
 # ====================================================================================================== encoder
@@ -273,8 +372,8 @@ def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_h
 def encoder_backward(dlogits, dfv, saved, P: Params, gradbuf: Optional[Grads] = None,
                      side: Optional[torch.cuda.Stream] = None) -> Grads:
     sv_p, sv_t, sv_h = saved
-    dh6, G = heads_backward(dlogits, dfv, sv_h, P, gradbuf)
-    dpool, Gt = tcn_backward(dh6, sv_t, P, gradbuf)
+    dg, G = heads_backward(dlogits, dfv, sv_h, P, gradbuf)
+    dpool, Gt = tcn_backward(dg, sv_t, P, gradbuf, dout_is_frame_mean=True)
     G.update(Gt)
     G.update(pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf, side=side))
     return G

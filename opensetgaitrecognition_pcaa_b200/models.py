@@ -32,33 +32,139 @@ def _named_tensors(module: torch.nn.Module):
     return d
 
 
-# ------------------------------------------------------------------------------------------------ containers
+# ------------------------------------------------------------------------------------------------ stand-alone blocks
+# CGEncoder never calls the layer objects below: its fused path (engine.encoder_forward) reads their parameters.  Their own
+# forward()s exist for code that composes the blocks itself -- the reference's ORCEDEncoder does (models.py:446-495:
+# pc_block -> AvgPool2d -> tc_block -> AvgPool1d) -- and run one shared autograd.Function: y = x W^T + b on the tensor cores
+# (tcgen05, bf16 operands, fp32 accumulation; the CUDA-core GEMM when the inner dimension is not a multiple of 8, i.e. the
+# K = 4 first layer), BatchNorm over the rows (batch statistics in training, running statistics in eval), ELU.
+class _LinearBnEluFn(torch.autograd.Function):
+    """a = ELU(BN(x W^T + b)) over rows: x [R, K] fp32, W [Cout, K] (a view of the conv weight), BatchNorm `bn`."""
+
+    @staticmethod
+    def forward(ctx, x, w2d, bias, gamma, beta, bn, training):
+        from ._lib import TC_PLAIN
+        x = x.contiguous()
+        R, K = x.shape
+        Cout = w2d.shape[0]
+        tc = K % 8 == 0
+        if tc:
+            xb = ops.convert(x, torch.bfloat16)
+            wb = ops.pack_bf16(w2d.contiguous())
+            y = ops.gemm_tc(xb, wb, TC_PLAIN, R, Cout, K, bias=bias, out_dtype=torch.float32)
+        else:
+            xb, wb = x, None
+            y = ops.gemm(x, w2d, trans_b=True, bias=bias)
+        if training:
+            coef = ops.bn_finalize(ops.colstats(y), R, gamma, beta, bn.running_mean, bn.running_var, engine.BN_MOMENTUM, engine.BN_EPS)
+            bn.num_batches_tracked.add_(1)
+        else:
+            c2 = ops.bn_eval_coeffs(gamma, beta, bn.running_mean, bn.running_var, engine.BN_EPS)
+            coef = torch.stack([c2[0], c2[1], bn.running_mean.float(), torch.rsqrt(bn.running_var.float() + engine.BN_EPS)])
+        ctx.sv = (xb, wb, y, coef, w2d, tc, training)
+        return ops.bn_elu_apply(y, coef[0], coef[1])
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ._lib import OP_MN, TC_PLAIN, TC_WGRAD_ACC
+        xb, wb, y, coef, w2d, tc, training = ctx.sv
+        R, Cout = y.shape
+        K = w2d.shape[1]
+        dz, st2 = ops.elu_bwd_colstats(dout.contiguous().float(), y, coef)
+        if training:
+            c, dgam, dbet = ops.bn_bwd_finalize(st2, R, coef)
+        else:      # running statistics are constants: dy = scale * dz, d gamma = sum dz * xhat, d beta = sum dz
+            c = torch.stack([coef[0], torch.zeros_like(coef[0]), torch.zeros_like(coef[0])])
+            dgam, dbet = st2[Cout:].float(), st2[:Cout].float()
+        if tc:
+            dy = ops.bn_bwd_apply(dz, y, c, out_dtype=torch.bfloat16)
+            dW = torch.zeros((Cout, K), device=y.device, dtype=torch.float32)
+            ops.gemm_tc(dy, xb, TC_WGRAD_ACC, Cout, K, R, a_mn=OP_MN, b_mn=OP_MN, out=dW)
+            dx = ops.gemm_tc(dy, wb, TC_PLAIN, R, K, Cout, b_mn=OP_MN, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
+            dbias = ops.colsum_ld(dy, Cout)
+        else:
+            dy = ops.bn_bwd_apply(dz, y, c)
+            dW = ops.gemm(dy, xb, trans_a=True)
+            dx = ops.gemm(dy, w2d) if ctx.needs_input_grad[0] else None
+            dbias = ops.colsum(dy)
+        return dx, dW, dbias, dgam, dbet, None, None
+
+
+def _only_elu(act, who):
+    if not isinstance(act, torch.nn.ELU) or act.alpha != 1.0:
+        raise NotImplementedError(f"{who}: the B200 kernels implement the reference's ELU(alpha=1) activation only")
+
+
 class PointNetModule(torch.nn.Module):
-    """Parameter container with the reference layout: module.0 = Conv2d(1x1), module.1 = BatchNorm2d, module.2 = act."""
+    """Reference layout (models.py:6-34): module.0 = Conv2d(1x1), module.1 = BatchNorm2d, module.2 = activation."""
 
     def __init__(self, in_chs, out_chs, activation=torch.nn.ELU()):
         super().__init__()
+        _only_elu(activation, "PointNetModule")
         self.module = torch.nn.Sequential(
             torch.nn.Conv2d(in_chs, out_chs, (1, 1), stride=1, padding="valid", dilation=1),
             torch.nn.BatchNorm2d(num_features=out_chs),
             activation,
         )
 
+    def forward_rows(self, rows):
+        """rows [R, Cin] fp32 (one row per point) -> [R, Cout]."""
+        conv, bn = self.module[0], self.module[1]
+        return _LinearBnEluFn.apply(rows, conv.weight.view(conv.weight.shape[0], -1), conv.bias, bn.weight, bn.bias, bn,
+                                    self.training)
+
     def forward(self, x):
-        raise NotImplementedError("PointNetModule is computed inside CGEncoder's fused path; call the encoder")
+        """x (B, Cin, T, N) -> (B, Cout, T, N), as models.py:33-34."""
+        _require_cuda(x, "PointNetModule")
+        B, C, T, N = x.shape
+        out = self.forward_rows(x.float().permute(0, 2, 3, 1).reshape(B * T * N, C))      # data movement only
+        return out.view(B, T, N, -1).permute(0, 3, 1, 2)
+
+
+class _Im2ColFn(torch.autograd.Function):
+    """[B, T, Cin] -> [B*T, Cin*3]: the three causally shifted taps of a dilated k=3 convolution side by side."""
+
+    @staticmethod
+    def forward(ctx, h, dil):
+        ctx.shape, ctx.dil = h.shape, dil
+        return ops.tcn_im2col(h.contiguous(), dil, torch.float32)
+
+    @staticmethod
+    def backward(ctx, dcol):
+        B, T, Cin = ctx.shape
+        return ops.tcn_col2im(dcol.contiguous(), B, T, Cin, ctx.dil), None
 
 
 class DilTempConv1d(torch.nn.Module):
+    """Reference layout (models.py:37-79): conv1d (k=3, dilation d, padding 2d, last 2d outputs dropped), batch_norm, ELU."""
+
     def __init__(self, in_chs, out_chs, dilation, kernel_size=3, stride=1, use_bias=True, activation=torch.nn.ELU()):
         super().__init__()
+        _only_elu(activation, "DilTempConv1d")
+        if kernel_size != 3 or stride != 1:
+            raise NotImplementedError("DilTempConv1d: the B200 kernels implement kernel_size=3, stride=1 (the reference's only use)")
         self.padding = int(np.floor((kernel_size - 1) * dilation))
         self.conv1d = torch.nn.Conv1d(in_chs, out_chs, kernel_size=kernel_size, stride=stride, padding=self.padding,
                                       dilation=dilation, bias=True)
         self.activation = activation
         self.batch_norm = torch.nn.BatchNorm1d(out_chs)
 
+    def forward_btc(self, h):
+        """h [B, T, Cin] fp32 (channels last) -> [B, T, Cout]."""
+        B, T, _ = h.shape
+        W = self.conv1d.weight                                           # (Cout, Cin, 3)
+        # pcaa_tcn_im2col lays a row out as [Cin][3] (channel-major, tap inner) -- the memory order of Conv1d's (Cout, Cin, 3)
+        # weight, so W.view(Cout, Cin*3) is the matching matrix (engine.tcn_forward relies on the same fact)
+        w2d = W.view(W.shape[0], -1)
+        col = _Im2ColFn.apply(h, int(self.conv1d.dilation[0]))
+        a = _LinearBnEluFn.apply(col, w2d, self.conv1d.bias, self.batch_norm.weight, self.batch_norm.bias, self.batch_norm,
+                                 self.training)
+        return a.view(B, T, -1)
+
     def forward(self, x):
-        raise NotImplementedError("DilTempConv1d is computed inside CGEncoder's fused path; call the encoder")
+        """x (B, Cin, T) -> (B, Cout, T), as models.py:73-79."""
+        _require_cuda(x, "DilTempConv1d")
+        return self.forward_btc(x.float().permute(0, 2, 1)).permute(0, 2, 1)
 
 
 class PointNetBlock(torch.nn.Module):
@@ -71,7 +177,14 @@ class PointNetBlock(torch.nn.Module):
         self.pointnet4 = PointNetModule(in_chs=d, out_chs=d)
 
     def forward(self, x):
-        raise NotImplementedError("PointNetBlock is computed inside CGEncoder's fused path; call the encoder")
+        """x (B, 4, T, N) -> (B, 1024, T, N), as models.py:100-105 (the un-pooled activation: stand-alone use only; CGEncoder's
+        fused path never materialises it)."""
+        _require_cuda(x, "PointNetBlock")
+        B, C, T, N = x.shape
+        rows = x.float().permute(0, 2, 3, 1).reshape(B * T * N, C)
+        for m in (self.pointnet1, self.pointnet2, self.pointnet3, self.pointnet4):
+            rows = m.forward_rows(rows)
+        return rows.view(B, T, N, -1).permute(0, 3, 1, 2)
 
 
 class TemporalConvolutionBlock(torch.nn.Module):
@@ -83,7 +196,12 @@ class TemporalConvolutionBlock(torch.nn.Module):
             setattr(self, f"dtc{l}", DilTempConv1d(in_chs=chans[l - 1], out_chs=chans[l], dilation=dil, kernel_size=3))
 
     def forward(self, x):
-        raise NotImplementedError("TemporalConvolutionBlock is computed inside CGEncoder's fused path")
+        """x (B, 1024, T) -> (B, 512, T), as models.py:153-160."""
+        _require_cuda(x, "TemporalConvolutionBlock")
+        h = x.float().permute(0, 2, 1)
+        for l in range(1, 7):
+            h = getattr(self, f"dtc{l}").forward_btc(h)
+        return h.permute(0, 2, 1)
 
 
 # ------------------------------------------------------------------------------------------------ encoder
@@ -97,7 +215,7 @@ class _EncoderFn(torch.autograd.Function):
             for k, v in P.items():
                 if k.endswith("num_batches_tracked"):
                     v.add_(1)
-        ctx.saved, ctx.module, ctx.names = saved, module, names
+        ctx.saved, ctx.module, ctx.names, ctx.eval_mode = saved, module, names, not training
         ctx.set_materialize_grads(False)
         return logits, fv
 
@@ -106,6 +224,15 @@ class _EncoderFn(torch.autograd.Function):
         P = _named_tensors(ctx.module)
         dlogits = None if dlogits is None else dlogits.contiguous()
         dfv = None if dfv is None else dfv.contiguous()
+        if ctx.eval_mode:
+            # the eval-mode forward folds BatchNorm into the GEMM epilogues and keeps no activations: there is nothing to
+            # differentiate through (the reference's scripts only call the eval-mode encoder under no_grad():
+            # PCAA_ablation.py:1045-1048, inference_PCAA.py:195-208, 239-251)
+            raise RuntimeError("CGEncoder (B200): the eval-mode forward is inference-only and cannot be differentiated; "
+                               "use .train(), or run it under torch.no_grad()")
+        if ctx.saved is None:
+            raise RuntimeError("CGEncoder (B200): backward through the same forward twice is not supported "
+                               "(the saved activations are released after the first backward)")
         G = engine.encoder_backward(dlogits, dfv, ctx.saved, P)
         ctx.saved = None
         return (None, None, None) + tuple(G[n] for n in ctx.names)

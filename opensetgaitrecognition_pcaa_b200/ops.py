@@ -153,9 +153,21 @@ def convert(x, dtype):
     return out
 
 
+def convert_into(x, out):
+    """out[:] = x converted to out's dtype (same number of elements; in place, so views of `out` stay valid)."""
+    _chk(x), _chk(out)
+    if x.numel() != out.numel():
+        raise ValueError("convert_into: element counts differ")
+    call("pcaa_convert", _p(x), _DT[x.dtype], _p(out), _DT[out.dtype], x.numel(), _s())
+    return out
+
+
 def pack_bf16(w: torch.Tensor, ld_out: Optional[int] = None, transpose=False, out: Optional[torch.Tensor] = None):
-    """bf16 copy of a 2-D fp32 matrix (optionally transposed) with the leading dimension padded to ld_out."""
-    _chk(w, torch.float32)
+    """bf16 copy of a 2-D fp32 matrix (optionally transposed) with the leading dimension padded to ld_out.  `w` may be a
+    row-strided view (unit inner stride)."""
+    _chk(w, torch.float32, contiguous=False)
+    if w.dim() != 2 or w.stride(1) != 1:
+        raise ValueError("pack_bf16: expected a 2-D matrix with unit inner stride")
     R, Cc = w.shape
     rows, cols = (Cc, R) if transpose else (R, Cc)
     if ld_out is None:
@@ -178,6 +190,45 @@ def tcn_col2im(dcol, B: int, T: int, Cin: int, dil: int):
     dx = torch.empty((B, T, Cin), device=dcol.device, dtype=torch.float32)
     call("pcaa_tcn_col2im", _p(dcol), _p(dx), B, T, Cin, dil, _s())
     return dx
+
+
+def tcn_bn_elu_next(y, B: int, T: int, *, stats=None, gamma=None, beta=None, running_mean=None, running_var=None,
+                    momentum=0.1, eps=1e-5, scale=None, shift=None, dil_next: int = 0, want_act: bool = False):
+    """BatchNorm1d + ELU of a TCN layer output y [B*T, C] fp32 (statistics from the GEMM epilogue in training, scale / shift
+    in eval).  Returns (col, act, coef): the next layer's bf16 im2col operand [B*T, C*3] (dil_next > 0), the fp32
+    activation (want_act) and, in training, coef [4, C] = scale, shift, mean, invstd."""
+    _chk(y, torch.float32)
+    Cc = y.shape[1]
+    col = torch.empty((B * T, Cc * 3), device=y.device, dtype=torch.bfloat16) if dil_next > 0 else None
+    act = torch.empty((B * T, Cc), device=y.device, dtype=torch.float32) if want_act else None
+    coef = torch.empty((4, Cc), device=y.device, dtype=torch.float32) if stats is not None else None
+    call("pcaa_tcn_bn_elu_next", _p(y), _p(stats), _p(gamma), _p(beta), _p(running_mean), _p(running_var), momentum, eps,
+         _p(scale), _p(shift), _p(coef), B, T, Cc, dil_next, _p(col), _p(act), _s())
+    return col, act, coef
+
+
+def tcn_elu_bwd_stats(src, src_mode: int, dil_up: int, y, coef, stats2, B: int, T: int):
+    """dz [B*T, C] fp32 = d * ELU'(BN(y)) with d formed from src (mode 0: as is, 1: col2im of the layer above, 2: frame-mean
+    broadcast); stats2 [2*C] double (pre-zeroed) += BatchNorm-backward sums."""
+    _chk(y, torch.float32), _chk(src, torch.float32)
+    Cc = y.shape[1]
+    dz = torch.empty_like(y)
+    call("pcaa_tcn_elu_bwd_stats", _p(src), src_mode, dil_up, _p(y), _p(coef[0]), _p(coef[1]), _p(coef[2]), _p(coef[3]), _p(dz),
+         _p(stats2), B, T, Cc, _s())
+    return dz
+
+
+def tcn_bn_bwd_apply(dz, y, stats2, coef, dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None):
+    """dy bf16 [R, C] = BatchNorm1d backward of dz (coefficients derived from the completed stats2 inside the kernel)."""
+    R, Cc = y.shape
+    dy = torch.empty((R, Cc), device=y.device, dtype=torch.bfloat16)
+    if dgamma is None:
+        dgamma = torch.empty(Cc, device=y.device, dtype=torch.float32)
+    if dbeta is None:
+        dbeta = torch.empty(Cc, device=y.device, dtype=torch.float32)
+    call("pcaa_tcn_bn_bwd_apply", _p(dz), _p(y), _p(stats2), _p(coef[0]), _p(coef[2]), _p(coef[3]), _p(dgamma), _p(dbeta), _p(dy),
+         R, Cc, _s())
+    return dy, dgamma, dbeta
 
 
 def mean_rows(x):
@@ -262,6 +313,38 @@ def pointnet_l1_fwd_t(x, w, bias, coef=None, want_stats=True):
     sc, sh = (None, None) if coef is None else (coef[0], coef[1])
     call("pcaa_pointnet_l1_fwd_t", _p(x), _p(w), _p(bias), _p(sc), _p(sh), _p(yT), _p(stats), B, T * N, Cout, _s())
     return yT, stats
+
+
+def input_moments(x):
+    """double[14] = first and second moments (sums over all B*T*N points) of the 4 input features of x (B,4,T,N)."""
+    _chk(x, torch.float32)
+    B, F, T, N = x.shape
+    if F != 4:
+        raise ValueError("input_moments: x must have 4 feature planes")
+    mom = torch.empty(14, device=x.device, dtype=torch.float64)
+    call("pcaa_input_moments", _p(x), B, T * N, _p(mom), _s())
+    return mom
+
+
+def bn_from_input_moments(mom, R, w, bias, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5):
+    """BatchNorm coefficients [4, C] (scale, shift, mean, invstd) of the K = 4 layer y = w x + bias from the input moments;
+    updates the running statistics like bn_finalize."""
+    Cc = gamma.numel()
+    coef = torch.empty((4, Cc), device=gamma.device, dtype=torch.float32)
+    call("pcaa_bn_from_input_moments", _p(mom), R, Cc, _p(w), _p(bias), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+         momentum, eps, _p(coef[0]), _p(coef[1]), _p(coef[2]), _p(coef[3]), _s())
+    return coef
+
+
+def pointnet_l1_fwd_bn_t(x, w, bias, coef):
+    """x (B,4,T,N) fp32 -> (yT, aT) T256 bf16: y = w x + bias and a = ELU(scale*y + shift) written in one pass."""
+    _chk(x, torch.float32), _chk(w, torch.float32)
+    B, F, T, N = x.shape
+    Cout = w.shape[0]
+    yT = t256_empty(Cout, B * T * N, x.device)
+    aT = torch.empty_like(yT)
+    call("pcaa_pointnet_l1_fwd_bn_t", _p(x), _p(w), _p(bias), _p(coef[0]), _p(coef[1]), _p(yT), _p(aT), B, T * N, Cout, _s())
+    return yT, aT
 
 
 def pointnet_l1_wgrad_t(x, dzT, yT=None, c=None, out: Optional[torch.Tensor] = None):

@@ -22,15 +22,24 @@ from ._lib import ACT_ELU, EW_ADD
 
 
 class _Flat:
-    """Flat fp32 storage for a list of (name, tensor): parameters become views; same layout for grad / m / v."""
+    """Flat fp32 storage for a list of (name, tensor): parameters become views; same layout for grad / m / v.
 
-    def __init__(self, named: List, device, group=None, exchanged: bool = False):
+    `pad_rows(name, tensor)` (optional) marks 2-D tensors whose rows are stored with a leading dimension rounded up to 8
+    elements: the decoder weights [out, in] with odd `in` (1125, 2250, 4500 ...).  Their bf16 shadow is then directly a
+    valid TMA / tensor-core operand (16-byte row stride) and their gradient a TMA-storable fp32 matrix -- no per-step
+    re-packing.  The parameter is the [out, in] strided view; the pad columns are zero and stay zero (their gradient is
+    never written, so Adam leaves them alone)."""
+
+    def __init__(self, named: List, device, group=None, exchanged: bool = False, pad_rows=None):
         self.names, self.slices = [], {}
         off = 0
         for name, t in named:
-            n = t.numel()
+            ld = None
+            if pad_rows is not None and t.dim() == 2 and t.shape[1] % 8 and pad_rows(name, t):
+                ld = (t.shape[1] + 7) // 8 * 8
+            n = t.numel() if ld is None else t.shape[0] * ld
             self.names.append(name)
-            self.slices[name] = (off, n, tuple(t.shape))
+            self.slices[name] = (off, n, tuple(t.shape), ld)
             off += (n + 7) // 8 * 8                     # 16-byte alignment of every tensor, also in the bf16 shadow
         self.size = off
         self.p = torch.zeros(off, device=device, dtype=torch.float32)
@@ -39,9 +48,9 @@ class _Flat:
         self.m = torch.zeros(off, device=device, dtype=torch.float32)
         self.v = torch.zeros(off, device=device, dtype=torch.float32)
         for name, t in named:
-            o, n, shp = self.slices[name]
-            self.p[o:o + n].copy_(t.detach().reshape(-1))
-            t.data = self.p[o:o + n].view(shp)          # the module parameter now aliases the flat buffer
+            dst = self.view(self.p, name)
+            dst.copy_(t.detach())
+            t.data = dst                                # the module parameter now aliases the flat buffer
         # Adam step count: authoritative copy on the device (advanced by pcaa_adam_advance inside the step, so a replayed
         # CUDA graph keeps counting), host mirror for bookkeeping; assigning .step sets both
         self.step_dev = torch.zeros(1, device=device, dtype=torch.int32)
@@ -64,8 +73,11 @@ class _Flat:
         return self.shadow
 
     def view(self, buf, name):
-        o, n, shp = self.slices[name]
-        return buf[o:o + n].view(shp)
+        """The tensor `name` inside a buffer of this layout (a strided [rows, cols] view for row-padded matrices)."""
+        o, n, shp, ld = self.slices[name]
+        if ld is None:
+            return buf[o:o + n].view(shp)
+        return buf[o:o + n].view(shp[0], ld)[:, :shp[1]]
 
     def span(self, names):
         """[start, end) of the flat range covered by `names` (must be contiguous in registration order)."""
@@ -90,10 +102,13 @@ class PCAATrainer:
     """
 
     def __init__(self, encoder, decoder, discriminator, decoder_projection_head, means: torch.Tensor, config: dict,
-                 process_group=None, mean_learner=None):
+                 process_group=None, mean_learner=None, discriminator_projection_head=None):
         if decoder is None and decoder_projection_head is not None:
             raise ValueError("PCAATrainer: a decoder projection head needs a decoder")
         self.enc, self.dec, self.dis, self.gph = encoder, decoder, discriminator, decoder_projection_head
+        # train_variant4 builds, "optimises" and saves a 64->32 discriminator_projection_head that its default flag never
+        # applies (PCAA_ablation.py:783-786, 933-937): kept only so that checkpoints carry _DPH.pt
+        self.dph = discriminator_projection_head
         # variant 1 (PCAA_ablation.py:28-378): the class prototypes are the GaussianMeanLearner's output for the batch's
         # one-hot labels (train-mode BatchNorm1d, so they depend on the batch composition).  In the reference
         # `z = Variable(z0 + mus)` (:186) detaches, so the learner never receives a gradient although optimizer_D lists
@@ -115,11 +130,20 @@ class PCAATrainer:
             named += [("GPH." + k, p) for k, p in decoder_projection_head.named_parameters()]
         if decoder is not None:
             named += [("G." + k, p) for k, p in decoder.named_parameters() if k.startswith("dense")]
-        self.G = _Flat(named, dev, process_group, exchanged=True)
+        self.G = _Flat(named, dev, process_group, exchanged=True, pad_rows=lambda n, t: n.startswith("G.dense"))
         self.D = _Flat([("D." + k, p) for k, p in discriminator.named_parameters()], dev)
         dec_names = [n for n in self.G.names if n.startswith("G.") or n.startswith("GPH.")]
         self._dec_span = self.G.span(dec_names) if dec_names else None
         self._enc_span = self.G.span([n for n in self.G.names if n.startswith("E.")])
+        # the classifier layers (MLP_head, MLP_sup2: the last encoder parameters) only receive a gradient on supervised
+        # iterations; torch.optim.Adam skips parameters without one, moments and per-parameter step count included
+        # (PCAA_ablation.py:1005-1021 with SUPERVISION_FREQUENCY > 1), so they carry their own Adam step counter
+        self._cls_span = self.G.span([n for n in self.G.names if n.startswith("E.MLP_head.") or n.startswith("E.MLP_sup2.")])
+        assert self._cls_span[1] == self._enc_span[1], "classifier layers must close the encoder span"
+        self._cls_step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._cls_coef_dev = torch.zeros(2, device=dev, dtype=torch.float32)
+        self._cls_step = 0
+        self._cls_diverged = False          # set by the first unsupervised iteration; until then one Adam call covers both
         self.G.make_shadow()
         self._refresh_views()
         # gradient exchange (dp.py): decoder-side span first (overlaps the encoder backward), then the encoder span
@@ -133,6 +157,10 @@ class PCAATrainer:
         self._wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("PCAA_WGRAD_OVERLAP", "0") == "1" else None
         self._graphs: Dict = {}
         self._warm = set()
+        # phase_timing = True: step / step_graphed (split graphs) bracket every phase of `_phases` with CUDA events on the
+        # main stream; phase_ms() reads them (data-parallel diagnosis: where an N-rank step spends its time)
+        self.phase_timing = False
+        self._phase_events: List = []
         # data-parallel: never capture a collective (kernel phases -> graphs, exchanges eager in between);
         # PCAA_SPLIT_GRAPHS=1 forces that program structure on one rank (tests)
         self.split_graphs = self.world > 1 or os.environ.get("PCAA_SPLIT_GRAPHS", "0") == "1"
@@ -144,6 +172,7 @@ class PCAATrainer:
         self.P_G = {k: v for k, v in self.dec.named_parameters()} if self.dec is not None else {}
         self.P_GPH = {k: v for k, v in self.gph.named_parameters()} if self.gph is not None else {}
         self.gb_E = {k: self.G.view(self.G.g, "E." + k) for k, _ in self.enc.named_parameters()}
+        self.gb_E["__zeroed__"] = True      # the step zero-fills the whole encoder span of G.g once (engine._zeros_like_param)
         self.gb_G = {k: self.G.view(self.G.g, "G." + k) for k in self.P_G if k.startswith("dense")}
         self.gb_GPH = {k: self.G.view(self.G.g, "GPH." + k) for k in self.P_GPH}
         self.Dw = [self.D.view(self.D.p, f"D.model.{i}.{s}") for i in (0, 2, 4) for s in ("weight", "bias")]
@@ -159,22 +188,14 @@ class PCAATrainer:
         for l in range(1, 7):
             W = self.P_E[f"tc_block.dtc{l}.conv1d.weight"]
             self._tcn_wb16[l] = self.G.view(self.G.shadow, f"E.tc_block.dtc{l}.conv1d.weight").view(W.shape[0], W.shape[1] * 3)
-        self._dec_shadow = {}
-        for l in range(1, 6) if self.dec is not None else ():
-            W = self.P_G[f"dense{l}.weight"]
-            if W.shape[1] % 8 == 0:
-                self._dec_shadow[l] = self.G.view(self.G.shadow, f"G.dense{l}.weight")
+        # every decoder weight's slice of the bf16 shadow is a tensor-core operand as it is (rows padded to 16 bytes: _Flat)
+        self._dec_shadow = {l: self.G.view(self.G.shadow, f"G.dense{l}.weight") for l in (range(1, 6) if self.dec is not None else ())}
 
     def _decoder_weights_bf16(self):
-        wb = dict(self._dec_shadow)
-        for l in range(1, 6):
-            if l not in wb:
-                W = self.P_G[f"dense{l}.weight"]
-                wb[l] = ops.pack_bf16(W, ld_out=engine.pad8(W.shape[1]))
-        return wb
+        return self._dec_shadow
 
     # ------------------------------------------------------------------------------------------------------------
-    def _phases(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor):
+    def _phases(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor, supervised: bool = True):
         """One variant-4 iteration as an ordered list of (kind, fn): "kernels" phases only enqueue C-ABI kernels (and
         torch fills) on the current stream, "exchange" phases are the data-parallel gradient exchanges (NCCL all-reduce,
         on the side stream for the generator spans, each followed by the Adam update of its span).  Running them in
@@ -186,11 +207,15 @@ class PCAATrainer:
         gscale = 1.0 / self.world
         b2_g = cfg.get("B2_G", cfg["B2"])
         st: Dict = {}
+        if not supervised and not self._cls_diverged:
+            self._cls_diverged = True
+            self.set_cls_step(self.G._step)                      # from here on the classifier layers count their own steps
+        cls_split = self._cls_diverged
 
-        def adam_span(lo, hi):
+        def adam_span(lo, hi, coef=None):
             G = self.G
-            ops.adam_flat_dev(G.p[lo:hi], G.g[lo:hi], G.m[lo:hi], G.v[lo:hi], cfg["B1"], b2_g, 1e-8, G.coef_dev,
-                              gscale, G.shadow[lo:hi])
+            ops.adam_flat_dev(G.p[lo:hi], G.g[lo:hi], G.m[lo:hi], G.v[lo:hi], cfg["B1"], b2_g, 1e-8,
+                              G.coef_dev if coef is None else coef, gscale, G.shadow[lo:hi])
 
         def encoder_and_critic():
             self.enc.train(), self.dis.train()
@@ -222,7 +247,9 @@ class PCAATrainer:
             adv = -float(cfg["ADV_WEIGHT"]) / B
             _, st["dfv"], st["loss_g"] = ops.disc_fwd(fv, gt, *self.Dw, self.C, want_out=False, want_dx=True, dx_scale=adv,
                                                       want_sum=True, out_scale=adv)           # critic already updated (:996)
-            st["sup_loss"], st["dlogits"], st["pred"] = ops.softmax_ce(logits, gt, want_grad=True)
+            # cross-entropy term only on iterations with i % SUPERVISION_FREQUENCY == 0 (PCAA_ablation.py:1005-1018): on the
+            # others tot = rec + loss_g, the classifier head receives no gradient (sup_loss is still reported)
+            st["sup_loss"], st["dlogits"], st["pred"] = ops.softmax_ce(logits, gt, want_grad=supervised)
             if self.dec is None:                                 # variant 3: tot = loss_g + sup (PCAA_ablation.py:640)
                 st["rec_loss"] = torch.zeros((), device=self.dev, dtype=torch.float32)
             else:
@@ -242,6 +269,8 @@ class PCAATrainer:
                 else:                                            # train_CGAAE: the decoder reads sup_fv (train_AAE.py:243)
                     st["dfv"] = ops.ew(EW_ADD, st["dfv"], dh0)
             ops.adam_advance(self.G.step_dev, self.G.coef_dev, cfg["LR"], cfg["B1"], b2_g)
+            if supervised and cls_split:
+                ops.adam_advance(self._cls_step_dev, self._cls_coef_dev, cfg["LR"], cfg["B1"], b2_g)
 
         def exchange_decoder_span():
             # decoder-side gradients (99 % of the bytes) are final: reduce them AND apply their Adam update (HBM bound)
@@ -250,6 +279,7 @@ class PCAATrainer:
                 self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
 
         def encoder_backward():
+            self.G.g[self._enc_span[0]:self._enc_span[1]].zero_()     # one fill instead of one per accumulated gradient
             engine.encoder_backward(st["dlogits"], st["dfv"], st["saved"], self.P_E, self.gb_E, side=self._wgrad_stream)
 
         def exchange_encoder_span():
@@ -257,7 +287,12 @@ class PCAATrainer:
             self.xG.finish()
 
         def encoder_update():
-            adam_span(*self._enc_span)
+            if not cls_split:
+                adam_span(*self._enc_span)
+            else:
+                adam_span(self._enc_span[0], self._cls_span[0])
+                if supervised:
+                    adam_span(*self._cls_span, coef=self._cls_coef_dev)
             st["out"] = {"rec_loss": st["rec_loss"], "d_loss": st["d_losses"][0], "gp": st["d_losses"][1],
                          "loss_g": st["loss_g"], "sup_loss": st["sup_loss"], "pred": st["pred"], "logits": st["logits"],
                          "fv": st["fv"]}
@@ -267,18 +302,23 @@ class PCAATrainer:
                 ("kernels", generator_forward_and_decoder_backward), ("exchange", exchange_decoder_span),
                 ("kernels", encoder_backward), ("exchange", exchange_encoder_span), ("kernels", encoder_update)], st
 
-    def step(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """One variant-4 iteration.  pcs (B,4,30,N) fp32, gt (B,) int64, z0 (B,32) ~ N(0,1) and alphas (B,1) ~ U(0,1)
-        are the host RNG draws of PCAA_ablation.py:915-931, 944-948 (already on the device).  Returns device scalars."""
-        phases, st = self._phases(pcs, gt, z0, alphas)
+    def step(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor,
+             supervised: bool = True) -> Dict[str, torch.Tensor]:
+        """One variant-4 iteration.  pcs (B,4,30,N) fp32, gt (B,) int64 in [0, C), z0 (B,32) ~ N(0,1) and alphas (B,1) ~ U(0,1)
+        are the host RNG draws of PCAA_ablation.py:915-931, 944-948 (already on the device).  `supervised=False` leaves the
+        cross-entropy term out of the generator loss (iterations with i % SUPERVISION_FREQUENCY != 0).  Returns device
+        scalars.  A label outside [0, C) turns d_loss / sup_loss (and every gradient) NaN -- the reference raises there."""
+        phases, st = self._phases(pcs, gt, z0, alphas, supervised)
         for _, fn in phases:
-            fn()
+            self._timed(fn.__name__, fn)
         self.D._step += 1
         self.G._step += 1
+        self._cls_step += int(supervised and self._cls_diverged)
         return st["out"]
 
     # ------------------------------------------------------------------------------------------------------------
-    def step_graphed(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def step_graphed(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor,
+                     supervised: bool = True) -> Dict[str, torch.Tensor]:
         """`step` replayed from CUDA graphs (captured once per input shape).  The ~200 launches of an iteration become
         one graph launch: no per-kernel host cost, back-to-back kernel scheduling on the device -- what the launch-bound
         small-batch configurations need.  With one rank the whole iteration is ONE graph (the side-stream Adam update
@@ -289,24 +329,48 @@ class PCAATrainer:
         second one captures; every call performs exactly one training iteration.  Inputs are copied into the graphs'
         static buffers unless they already are those buffers (`static_inputs`).  The returned tensors are graph-owned:
         read them before the next call."""
-        key = (tuple(pcs.shape), tuple(z0.shape))
+        if not supervised and not self._cls_diverged:
+            self._cls_diverged = True
+            self.set_cls_step(self.G._step)
+        key = (tuple(pcs.shape), tuple(z0.shape)) + ((("cls-split",) if self._cls_diverged else ()) if supervised else ("unsupervised",))
         gs = self._graphs.get(key)
         if gs is None:
             if key not in self._warm:
                 self._warm.add(key)
-                return self.step(pcs, gt, z0, alphas)
-            gs = self._capture(key, (pcs, gt, z0, alphas))
+                return self.step(pcs, gt, z0, alphas, supervised)
+            gs = self._capture(key, (pcs, gt, z0, alphas), supervised)
         for dst, src in zip(gs["in"], (pcs, gt, z0, alphas)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        for kind, item in gs["program"]:
-            if kind == "graph":
-                item.replay()
-            else:
-                item()
+        for (kind, item), name in zip(gs["program"], gs["names"]):
+            self._timed(name, item.replay if kind == "graph" else item)
         self.G._step += 1
         self.D._step += 1
+        self._cls_step += int(supervised and self._cls_diverged)
         return gs["out"]
+
+    def _timed(self, name, fn):
+        if not self.phase_timing:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self._phase_events.append((name, e0, e1))
+        return r
+
+    def phase_ms(self, reset: bool = True) -> Dict[str, float]:
+        """Mean milliseconds per phase over the iterations run since the last reset with phase_timing on (synchronises).
+        Measured between events on the MAIN stream: a phase that forks work to the side stream (the decoder-span exchange +
+        its Adam update) shows only its enqueue cost; the wait for that work shows up in the phase that joins it
+        (exchange_encoder_span / the end of the step)."""
+        torch.cuda.synchronize(self.dev)
+        acc: Dict[str, List[float]] = {}
+        for name, e0, e1 in self._phase_events:
+            acc.setdefault(name, []).append(e0.elapsed_time(e1))
+        if reset:
+            self._phase_events = []
+        return {k: sum(v) / len(v) for k, v in acc.items()}
 
     def static_inputs(self, pcs_shape, z0_shape=None):
         """The captured graph's input buffers (pcs, gt, z0, alphas) for this shape, or None before capture: a loader can
@@ -315,15 +379,16 @@ class PCAATrainer:
         gs = self._graphs.get((tuple(pcs_shape), tuple(z0_shape or (B, self.means.shape[1]))))
         return None if gs is None else gs["in"]
 
-    def _capture(self, key, example):
+    def _capture(self, key, example, supervised: bool = True):
         from . import _lib
         static_in = tuple(torch.empty_like(t) for t in example)
         for d, s_ in zip(static_in, example):
             d.copy_(s_)
         torch.cuda.synchronize(self.dev)
         calls0 = _lib.CALLS
-        phases, st = self._phases(*static_in)
+        phases, st = self._phases(*static_in, supervised)
         program = []
+        names = [fn.__name__ for _, fn in phases] if self.split_graphs else ["whole_step_graph"]
         if not self.split_graphs:
             # the exchanges are no collectives here, only the fork / join of the side-stream Adam update: one graph
             g = torch.cuda.CUDAGraph()
@@ -341,7 +406,7 @@ class PCAATrainer:
                     program.append(("graph", g))
                 else:
                     program.append(("exchange", fn))          # issued eagerly between the replays
-        gs = {"program": program, "in": static_in, "out": st["out"], "launches": _lib.CALLS - calls0, "state": st}
+        gs = {"program": program, "names": names, "in": static_in, "out": st["out"], "launches": _lib.CALLS - calls0, "state": st}
         self._graphs[key] = gs
         return gs
 
@@ -351,6 +416,36 @@ class PCAATrainer:
             if k[0] == tuple(pcs_shape):
                 return gs["launches"]
         return 0
+
+    def set_cls_step(self, n: int) -> None:
+        self._cls_step = int(n)
+        self._cls_step_dev.fill_(int(n))
+
+    # ------------------------------------------------------------------------------------------------------------
+    def snapshot(self) -> Dict:
+        """Clone of everything one iteration changes: both optimizers' weights / moments / step counts and the encoder's
+        BatchNorm running statistics (+ the mean learner's).  `restore` puts it back (also into another trainer of the
+        same architecture: data-parallel parity checks, resumable probes)."""
+        snap = {"G": (self.G.p.clone(), self.G.m.clone(), self.G.v.clone(), self.G.step),
+                "D": (self.D.p.clone(), self.D.m.clone(), self.D.v.clone(), self.D.step),
+                "enc_buffers": [b.clone() for b in self.enc.buffers()],
+                "cls_step": self._cls_step if self._cls_diverged else None}
+        if self.ml is not None:
+            snap["ml"] = {k: v.clone() for k, v in self.ml.state_dict().items()}
+        return snap
+
+    def restore(self, snap: Dict) -> None:
+        for flat, key in ((self.G, "G"), (self.D, "D")):
+            p, m, v, step = snap[key]
+            flat.p.copy_(p), flat.m.copy_(m), flat.v.copy_(v)
+            flat.step = step
+        for b, b0 in zip(self.enc.buffers(), snap["enc_buffers"]):
+            b.copy_(b0)
+        self._cls_diverged = snap.get("cls_step") is not None
+        self.set_cls_step(snap["cls_step"] if self._cls_diverged else 0)
+        if self.ml is not None and "ml" in snap:
+            self.ml.load_state_dict(snap["ml"])
+        ops.convert_into(self.G.p, self.G.shadow)              # in place: captured graphs keep reading this buffer
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -371,25 +466,51 @@ class PCAATrainer:
 
 def _ckpt_paths(root: str, name: str):
     d = os.path.join(root, "models", name)
-    return d, {k: os.path.join(d, f"{name}_{k}.pt") for k in ("E", "G", "D", "GPH", "OPT")}
+    return d, {k: os.path.join(d, f"{name}_{k}.pt") for k in ("E", "G", "D", "GPH", "DPH", "OPT")}
 
 
-def save_checkpoint(trainer: PCAATrainer, model_name: str, root: str = ".") -> str:
-    """Write the files train_variant4 writes at a checkpoint (PCAA_ablation.py:1088-1112): models/<name>/<name>_E.pt,
-    _G.pt, _D.pt, _GPH.pt (state_dicts with the reference's keys: inference_PCAA.CGAAE_inference_setup loads them as they
-    are) and discriminator_means.pt; plus <name>_OPT.pt with both Adam states (the reference does not checkpoint its
-    optimizers; this is what makes a run resumable)."""
+def write_config(trainer: PCAATrainer, config: Optional[dict], model_name: str, root: str = ".") -> str:
+    """models/<name>/config.pkl, the first thing every reference trainer writes (train_AAE.py:27-30, PCAA_ablation.py:754-757)
+    and the first thing inference_PCAA.CGAAE_inference_setup reads (:63-65: NMAX, TRAIN_CLASSES, MODEL_NAME).  The caller's
+    config is pickled as it is, with those three keys filled in from the trainer when absent."""
+    import pickle
+    cfg = dict(config or {})
+    cfg["MODEL_NAME"] = model_name
+    cfg.setdefault("NMAX", int(trainer.enc.nmax_points))
+    if not cfg.get("TRAIN_CLASSES"):
+        cfg["TRAIN_CLASSES"] = list(range(trainer.C))
+    if len(cfg["TRAIN_CLASSES"]) != trainer.C:
+        raise ValueError(f"config['TRAIN_CLASSES'] has {len(cfg['TRAIN_CLASSES'])} classes, the networks were built for {trainer.C}")
+    d = os.path.join(root, "models", model_name)
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "config.pkl")
+    with open(path, "wb") as f:
+        pickle.dump(cfg, f)
+    return path
+
+
+def save_checkpoint(trainer: PCAATrainer, model_name: str, root: str = ".", config: Optional[dict] = None) -> str:
+    """Write the files train_variant4 writes (PCAA_ablation.py:754-757, 859-863, 1088-1112): models/<name>/config.pkl,
+    <name>_E.pt, _G.pt, _D.pt, _GPH.pt, _DPH.pt (state_dicts with the reference's keys) and discriminator_means.pt, so that
+    inference_PCAA.CGAAE_inference_setup loads the folder as it is; plus <name>_OPT.pt with both Adam states (the reference
+    does not checkpoint its optimizers; this is what makes a run resumable).  config.pkl is (re)written when `config` is
+    given or the file does not exist yet (the trainer's own hyper-parameters then)."""
     from . import utils
     d, paths = _ckpt_paths(root, model_name)
     os.makedirs(d, exist_ok=True)
+    if config is not None or not os.path.exists(os.path.join(d, "config.pkl")):
+        write_config(trainer, config if config is not None else trainer.cfg, model_name, root)
     utils.save_model(trainer.enc, paths["E"])
     utils.save_model(trainer.dis, paths["D"])
     if trainer.dec is not None:
         utils.save_model(trainer.dec, paths["G"])
     if trainer.gph is not None:
         utils.save_model(trainer.gph, paths["GPH"])
+    if trainer.dph is not None:
+        utils.save_model(trainer.dph, paths["DPH"])
     torch.save(trainer.means.detach().cpu(), os.path.join(d, "discriminator_means.pt"))
-    torch.save({"G": {"m": trainer.G.m.cpu(), "v": trainer.G.v.cpu(), "step": trainer.G.step, "names": trainer.G.names},
+    torch.save({"G": {"m": trainer.G.m.cpu(), "v": trainer.G.v.cpu(), "step": trainer.G.step, "names": trainer.G.names,
+                      "cls_step": trainer._cls_step if trainer._cls_diverged else None},
                 "D": {"m": trainer.D.m.cpu(), "v": trainer.D.v.cpu(), "step": trainer.D.step, "names": trainer.D.names}},
                paths["OPT"])
     return d
@@ -399,8 +520,8 @@ def load_checkpoint(trainer: PCAATrainer, model_name: str, root: str = ".", opti
     """Load what save_checkpoint (or the reference's trainer) wrote into an already built trainer: weights into the flat
     buffers (the parameters are views of them), bf16 operand copies refreshed, Adam states when present."""
     d, paths = _ckpt_paths(root, model_name)
-    for key, mod in (("E", trainer.enc), ("D", trainer.dis), ("G", trainer.dec), ("GPH", trainer.gph)):
-        if mod is not None:
+    for key, mod in (("E", trainer.enc), ("D", trainer.dis), ("G", trainer.dec), ("GPH", trainer.gph), ("DPH", trainer.dph)):
+        if mod is not None and (key != "DPH" or os.path.exists(paths[key])):
             mod.load_state_dict(torch.load(paths[key], map_location=trainer.dev))
     trainer.G.make_shadow()
     trainer._refresh_views()
@@ -414,6 +535,9 @@ def load_checkpoint(trainer: PCAATrainer, model_name: str, root: str = ".", opti
             flat.m.copy_(st[key]["m"])
             flat.v.copy_(st[key]["v"])
             flat.step = int(st[key]["step"])
+        cls = st["G"].get("cls_step")
+        trainer._cls_diverged = cls is not None
+        trainer.set_cls_step(cls if cls is not None else 0)
 
 
 def fit(trainer: PCAATrainer, train, valid, config: dict, model_name: str, root: str = ".", np_rng=None, torch_gen=None,
@@ -434,7 +558,29 @@ def fit(trainer: PCAATrainer, train, valid, config: dict, model_name: str, root:
     from . import loader
     B = int(config["BATCH_SIZE"])
     rank, world = trainer.rank, trainer.world
+    sup_freq = int(config.get("SUPERVISION_FREQUENCY", 1))
+    if sup_freq < 1:
+        raise ValueError("SUPERVISION_FREQUENCY must be >= 1")
+    if B % world:
+        # the exchanged gradient is the plain mean of the ranks' shard means (1/world inside Adam): unequal shards would
+        # weight samples unequally
+        raise ValueError(f"BATCH_SIZE {B} is not a multiple of the {world} data-parallel ranks")
+    for name, split in (("train", train), ("valid", valid)):
+        lab = split.labels
+        if len(lab) and (int(lab.min()) < 0 or int(lab.max()) >= trainer.C):
+            raise ValueError(f"{name} split: labels must lie in [0, {trainer.C}) (found {int(lab.min())}..{int(lab.max())})")
+    if world > 1:
+        # every rank must walk the same permutation (each takes its slice of the same global batch) and draw the same
+        # global z0 / alphas: take rank 0's generator states
+        if shuffle_gen is None:
+            shuffle_gen = torch.Generator()
+            shuffle_gen.manual_seed(int(config.get("SHUFFLE_SEED", 0)))
+        state = shuffle_gen.get_state().to(trainer.dev if trainer.dev.type == "cuda" and torch.distributed.get_backend(trainer.pg) == "nccl" else "cpu")
+        torch.distributed.broadcast(state, 0, group=trainer.pg)
+        shuffle_gen.set_state(state.cpu())
     os.makedirs(os.path.join(root, "models", model_name), exist_ok=True)
+    if rank == 0:
+        write_config(trainer, config, model_name, root)                                                            # :754-757
     torch.save(trainer.means.detach().cpu(), os.path.join(root, "models", model_name, "discriminator_means.pt"))   # :859-863
     stepfn = trainer.step_graphed if graphed else trainer.step
     lo, hi = dp.shard_range(B, rank, world)
@@ -448,7 +594,8 @@ def fit(trainer: PCAATrainer, train, valid, config: dict, model_name: str, root:
         batches = ((x[lo:hi], y[lo:hi]) for x, y in train.batches(B, shuffle=True, drop_last=True, generator=shuffle_gen))
         for pcs, gt in loader.DevicePrefetcher(batches, trainer.dev):
             z0, alphas = dp.global_draws(B, latent, rank, world, np_rng, torch_gen)
-            out = stepfn(pcs, gt, z0.to(trainer.dev, non_blocking=True), alphas.to(trainer.dev, non_blocking=True))
+            out = stepfn(pcs, gt, z0.to(trainer.dev, non_blocking=True), alphas.to(trainer.dev, non_blocking=True),
+                         supervised=(n_it % sup_freq == 0))                                                        # :1005
             sums += torch.stack([out["rec_loss"], out["sup_loss"], out["d_loss"],
                                  out["rec_loss"] + out["loss_g"] + out["sup_loss"]]).double()
             correct += (out["pred"].long() == gt).sum()
@@ -471,7 +618,7 @@ def fit(trainer: PCAATrainer, train, valid, config: dict, model_name: str, root:
         if epoch % int(config.get("CHECKPOINT_FREQUENCY", 1)) == 0 and rec_e["Valid Accuracy"] > best_valid_accuracy:
             best_valid_accuracy = rec_e["Valid Accuracy"]
             if rank == 0:
-                save_checkpoint(trainer, model_name, root)
+                save_checkpoint(trainer, model_name, root, config)
             rec_e["saved"] = True
         history.append(rec_e)
         if log is not None:
@@ -519,5 +666,6 @@ def build_variant4(n_classes: int, nmax: int, config: Optional[dict] = None, dev
     dec = models.CGDecoder(input_dim=cfg["SUP_LATENT_DIM"] * 2, nmax_points=nmax).to(device).float()
     dis = models.CGDiscriminator(n_classes).to(device).float()
     gph = torch.nn.Sequential(torch.nn.Linear(cfg["SUP_LATENT_DIM"], cfg["SUP_LATENT_DIM"] * 2), torch.nn.ELU()).to(device).float()
+    dph = torch.nn.Sequential(torch.nn.Linear(cfg["SUP_LATENT_DIM"] * 2, cfg["SUP_LATENT_DIM"]), torch.nn.ELU()).to(device).float()
     means = utils.sample_distant_points(cfg["SUP_LATENT_DIM"], n_classes, 10, 10).float()
-    return PCAATrainer(enc, dec, dis, gph, means, cfg, process_group)
+    return PCAATrainer(enc, dec, dis, gph, means, cfg, process_group, discriminator_projection_head=dph)

@@ -550,10 +550,65 @@ def procedure_case():
     np.savez_compressed(os.path.join(GOLD, "procedure.npz"), **g)
 
 
+def infer4096_case(models):
+    """Config 5 label parity at N = 150 on 4 096 crops: the REFERENCE's own CGEncoder (eval mode, fp32, CPU)
+    encodes an identity-ordered stream of 4 known + 6 unseen synthetic subjects; its embeddings / logits and the open-set
+    labels the oracle procedure derives from them (k = 1, 2, 4, 6) are the golden outputs.  The inputs are regenerated from
+    seeds by the test (oracle.synth_subject_stream), the weights are oracle.det_params(4, 150, seed=11) with BatchNorm
+    running statistics calibrated on the first 64 crops (stored), the prototypes are the known subjects' centroids."""
+    C, nmax, seed = 4, 150, 11
+    known, unseen = [0, 1, 2, 3], [10, 11, 12, 13, 14, 15]
+    per_known, per_unseen = 512, 342
+    p = O.det_params(C, nmax, seed)
+    # random-init embeddings of all subjects sit within ~1 unit of each other, where the identity-covariance mixture cannot
+    # separate anything; the embedding layer is scaled so that class centroids end up O(10) apart, the scale the reference's
+    # radius-10 prototypes work at (utils.py:216-251)
+    emb_scale = 6.0
+    p["E.MLP_sup1.0.weight"] = p["E.MLP_sup1.0.weight"] * emb_scale
+    p["E.MLP_sup1.0.bias"] = p["E.MLP_sup1.0.bias"] * emb_scale
+    t_pcs, t_sub = O.synth_subject_stream(known, per_known, nmax, seed=7000)
+    u_pcs, u_sub = O.synth_subject_stream(unseen, per_unseen, nmax, seed=9000)
+    u_pcs, u_sub = u_pcs[:2048], u_sub[:2048]
+    calib = torch.cat([t_pcs[i * per_known:i * per_known + 12] for i in range(4)] + [u_pcs[:16]])
+    bn = O.calibrate_bn(p, calib)
+    enc = models.CGEncoder(n_out_labels=C, use_projection_head=True, nmax_points=nmax).float().eval()
+    enc.load_state_dict(split_state(p, "E."))
+    fvs, lgs = [], []
+    with torch.no_grad():
+        for x in (t_pcs, u_pcs):
+            f, l = [], []
+            for s0 in range(0, x.shape[0], 64):
+                lg, fv = enc(x[s0:s0 + 64])
+                f.append(fv), l.append(lg)
+            fvs.append(torch.cat(f)), lgs.append(torch.cat(l))
+        lg_o, fv_o = O.encoder_forward(p, t_pcs[:32], False, True)
+    pin = max(maxdiff(fv_o, fvs[0][:32]), maxdiff(lg_o, lgs[0][:32]))
+    assert pin < 1e-4, pin
+    t_lab = np.searchsorted(np.array(known), t_sub)                 # labels 0..3 (datasets.py:455-462)
+    means = torch.stack([fvs[0][torch.from_numpy(t_lab == c)].mean(0) for c in range(C)])
+    g = {"C": C, "nmax": nmax, "seed": seed, "known": np.array(known), "unseen": np.array(unseen), "per_known": per_known,
+         "per_unseen": per_unseen, "means": means.numpy(), "t_fv": fvs[0].numpy(), "t_logits": lgs[0].numpy(),
+         "u_fv": fvs[1].numpy(), "u_logits": lgs[1].numpy(), "t_lab": t_lab, "u_lab": u_sub, "pin_encoder": pin,
+         "emb_scale": emb_scale}
+    for k_, v in bn.items():
+        g["bn:" + k_] = v.numpy()
+    for k in (1, 2, 4, 6):
+        o = O.naive_sequential_procedure(k, g["t_fv"], g["t_logits"].argmax(1), t_lab, g["u_fv"], g["u_logits"].argmax(1), u_sub,
+                                         g["means"], 0, 0.2)
+        g[f"preds_k{k}"], g[f"labels_k{k}"], g[f"threshold_k{k}"] = o["preds"], o["labels"], np.float64(o["threshold"])
+        print(f"[infer4096] k={k}: {len(o['preds'])} windows, accuracy {o['metrics']['accuracy']:.3f}, threshold {o['threshold']:.3e}")
+    d = torch.cdist(means, means)
+    print(f"[infer4096] centroid distances {float(d[d > 0].min()):.3f}..{float(d.max()):.3f}, |oracle - reference encoder| = {pin:.2e}")
+    np.savez_compressed(os.path.join(GOLD, "infer4096_n150.npz"), **g)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     constants, models, utils_mod = load_reference()
+    if "--infer4096-only" in sys.argv:
+        infer4096_case(models)
+        sys.exit(0)
     if "--variant1-only" in sys.argv:
         step_case(constants, models, utils_mod, "v1_n50_c4_b8", 8, 50, 4, seed=7, variant=1)
         sys.exit(0)
@@ -571,6 +626,7 @@ if __name__ == "__main__":
     step_case(constants, models, utils_mod, "v3_n50_c4_b4", 4, 50, 4, seed=6, variant=3)
     scoring_case()
     procedure_case()
+    infer4096_case(models)
     w, frac = trainer_pin(constants, models, utils_mod)
     with open(os.path.join(GOLD, "PIN.txt"), "w") as f:
         f.write("oracle pinned against the reference run in the build container (oracle/gen_golden.py)\n"

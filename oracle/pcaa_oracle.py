@@ -296,7 +296,7 @@ def trainable_names(p: Params, prefixes) -> List[str]:
 
 
 def train_step(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict, variant: int = 4,
-               clone_leaves: bool = True) -> dict:
+               clone_leaves: bool = True, supervised: bool = True) -> dict:
     """One training iteration of the reference's AAE loops (in place on ``p``):
 
     * variant 4 -- the paper's PCAA, ``PCAA_ablation.py:882-1021``: encoder with projection head, decoder fed by
@@ -311,6 +311,10 @@ def train_step(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict
       Variable(z0 + mus)`` (``:186``) DETACHES, so although optimizer_D is built over ``chain(mean_learner,
       discriminator)`` (``:108-112``) the learner's parameters never receive a gradient (``grad is None``, Adam skips
       them); only its BatchNorm running statistics move.
+
+    ``supervised=False`` is an iteration with ``i % SUPERVISION_FREQUENCY != 0`` (``PCAA_ablation.py:1005-1018``): the
+    cross-entropy term is left out of ``tot``, so the classifier layers (``MLP_head``, ``MLP_sup2``) have ``grad is None`` after
+    ``zero_grad()`` and ``torch.optim.Adam`` skips them entirely (their moments and per-parameter step counts do not move).
 
     cfg: LR, B1, B2, GP_WEIGHT, ADV_WEIGHT, NMAX.  ``z0`` (B,32) and ``alphas`` (B,1) are the host RNG draws of
     PCAA_ablation.py:915-931 / 944-948.  Returns losses, the class predictions and every gradient (by name).
@@ -358,11 +362,11 @@ def train_step(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, cfg: dict
     sup = cross_entropy(logits, gt)
     if variant == 3:
         rec_loss = torch.zeros(())
-        tot = loss_g + sup
+        tot = loss_g + sup if supervised else loss_g
     else:
         rec = decoder_forward(q, proj_head_forward(q, fv) if head else fv, nmax)
         rec_loss, i1, i2 = chamfer(rec, pcs)
-        tot = rec_loss + loss_g + sup
+        tot = rec_loss + loss_g + sup if supervised else rec_loss + loss_g
         out.update(rec=rec.detach(), idx_gt_for_pred=i1, idx_pred_for_gt=i2)
     g_names = trainable_names(p, g_prefixes)
     g_grads = torch.autograd.grad(tot, [q[n] for n in g_names], allow_unused=True)
@@ -388,6 +392,42 @@ def train_step_variant4(p: Params, opt_state: dict, pcs, gt, z0, alphas, means, 
 # --------------------------------------------------------------------------- #
 # open-set scoring, inference_PCAA.py:129-136, 225-231, 255-271
 # --------------------------------------------------------------------------- #
+def subject_sigma_scale(subject: int) -> np.ndarray:
+    """Deterministic per-subject spread factors for `synth_batch` (synthetic identities: body size / gait dynamics)."""
+    s = int(subject)
+    return np.array([0.6 + 0.13 * (s % 7), 0.6 + 0.11 * ((3 * s) % 7), 0.7 + 0.09 * ((5 * s) % 7), 0.5 + 0.17 * ((2 * s + 1) % 7)])
+
+
+def synth_subject_stream(subjects, crops_per_subject: int, nmax: int, seed: int):
+    """An identity-ordered crop stream as MSRadarDataset(sequential=True) serves it: for every subject,
+    `crops_per_subject` consecutive crops drawn with that subject's spread factors.  Returns (pcs, subject ids)."""
+    xs, ids = [], []
+    for i, s in enumerate(subjects):
+        x, _ = synth_batch(crops_per_subject, nmax, 1, seed=seed + 1009 * i, sigma_scale=subject_sigma_scale(s))
+        xs.append(x)
+        ids += [int(s)] * crops_per_subject
+    return torch.cat(xs), np.array(ids, dtype=np.int64)
+
+
+def calibrate_bn(p: Params, pcs: torch.Tensor, use_projection_head: bool = True) -> Dict[str, torch.Tensor]:
+    """Running statistics := the batch statistics of one training-mode forward over `pcs` (momentum undone), so that
+    the eval-mode encoder is well conditioned on this data.  Returns {buffer name: tensor} (also written into p)."""
+    upd: dict = {}
+    q = dict(p)
+    for k in list(q):
+        if k.startswith("E.") and k.endswith("running_mean"):
+            q[k] = torch.zeros_like(q[k])
+        elif k.startswith("E.") and k.endswith("running_var"):
+            q[k] = torch.zeros_like(q[k])
+    with torch.no_grad():
+        encoder_forward(q, pcs, True, use_projection_head, upd)
+    out = {}
+    for k, v in upd.items():
+        out[k] = (v / BN_MOMENTUM).float()
+        p[k] = out[k]
+    return out
+
+
 def joint_log_likelihood(x: np.ndarray, means: np.ndarray) -> np.ndarray:
     """log of the equal-weight mixture pdf (1/C) sum_c N(x; mu_c, I_d), float64.  x (M,d)."""
     x = np.asarray(x, dtype=np.float64).reshape(-1, means.shape[1])
@@ -611,13 +651,16 @@ def det_params(n_classes: int, nmax: int, seed: int = 0, use_projection_head: bo
     return p
 
 
-def synth_batch(B: int, nmax: int, n_classes: int, seed: int = 1234):
+def synth_batch(B: int, nmax: int, n_classes: int, seed: int = 1234, sigma_scale=None):
     """Synthetic mmGait10-shaped crops, SURVEY section 8(d) (mimics datasets.py:98-161,290-295):
     per-frame cardinality c~U{8..220}, points ~N(0,diag(.35,.35,.55,1.2)^2) around a drifting
     offset, pad by repeating random real points / subsample to nmax, subtract per-frame mean.
+    ``sigma_scale`` (4,) optionally scales the per-feature spread (a stand-in for subject-specific gait statistics).
     Returns (pcs (B,4,T,N) float32, labels (B,) int64)."""
     rng = np.random.default_rng(seed)
     sig = np.array([0.35, 0.35, 0.55, 1.2])
+    if sigma_scale is not None:
+        sig = sig * np.asarray(sigma_scale, dtype=np.float64)
     out = np.empty((B, NSTEPS, nmax, NFEATURES), dtype=np.float64)
     for b in range(B):
         off = rng.normal(0, 1.0, 4) * np.array([1.0, 1.0, 0.2, 0.5])

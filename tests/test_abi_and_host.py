@@ -139,8 +139,8 @@ def test_flat_parameter_layout_aliases_module_parameters():
     fl = _Flat(named, "cpu")
     off = 0
     for n, p in named:
-        o, cnt, shp = fl.slices[n]
-        assert o == off and o % 8 == 0 and cnt == p.numel() and shp == tuple(p.shape)
+        o, cnt, shp, ld = fl.slices[n]
+        assert o == off and o % 8 == 0 and cnt == p.numel() and shp == tuple(p.shape) and ld is None
         off += (cnt + 7) // 8 * 8
         assert torch.equal(p.detach(), before[n])
         assert p.data_ptr() == fl.p.data_ptr() + 4 * o            # aliasing, not a copy
@@ -150,6 +150,19 @@ def test_flat_parameter_layout_aliases_module_parameters():
     lo, hi = fl.span(["b.weight", "b.bias"])
     assert lo == fl.slices["b.weight"][0] and hi == fl.size
     assert fl.view(fl.g, "b.weight").shape == (7, 3)
+    # row-padded matrices (the decoder weights with an odd input width): leading dimension rounded up to 8 elements, the
+    # parameter is the strided [rows, cols] view, pad columns are zero
+    lin3 = torch.nn.Linear(13, 6)
+    w0 = lin3.weight.detach().clone()
+    fp = _Flat([("w", lin3.weight), ("b", lin3.bias)], "cpu", pad_rows=lambda n, t: n == "w")
+    o, cnt, shp, ld = fp.slices["w"]
+    assert (o, cnt, shp, ld) == (0, 6 * 16, (6, 13), 16) and fp.slices["b"][0] == 96
+    assert torch.equal(lin3.weight.detach(), w0) and lin3.weight.stride() == (16, 1) and lin3.weight.data_ptr() == fp.p.data_ptr()
+    assert float(fp.p[:96].view(6, 16)[:, 13:].abs().max()) == 0.0
+    assert fp.view(fp.g, "w").shape == (6, 13) and fp.view(fp.g, "w").stride() == (16, 1)
+    sd = lin3.state_dict()
+    lin3.load_state_dict({k: v.clone() + 1 for k, v in sd.items()})              # checkpoints load into the strided views
+    assert torch.equal(lin3.weight.detach(), w0 + 1) and float(fp.p[:96].view(6, 16)[:, 13:].abs().max()) == 0.0
 
 
 def test_synthetic_crops_follow_the_dataset_contract(tmp_path):

@@ -1,0 +1,247 @@
+"""Parity against the CPU oracle AT the sizes BASELINE.json names (B200 only): one full variant-4 iteration at batch 32 and
+64 with N = 150 points (configs 1-2), at N = 90 / 110 / 130 (config 4, the points-per-frame sweep), and open-set label parity
+on a 4 096-crop N = 150 stream (config 5) against golden outputs of the REFERENCE's own encoder (tests/golden/infer4096_n150.npz,
+oracle/gen_golden.py --infer4096-only).
+
+Tolerances (bf16 tensor-core operands and bf16 stored activations vs the fp32 reference; scripts/sim_bf16_rounding.py
+reproduces these magnitudes on the CPU from the storage roundings alone):
+  losses 2e-2 relative to max(1, |ref|); embeddings / logits 3e-2 of max |ref|;
+  gradients per tensor ||g - g_ref|| / ||g_ref||: encoder GRAD_TOL_ENC, decoder 4e-2, critic GRAD_TOL_ENC
+  (the critic's input is the bf16-path embedding);
+  gradient direction: sign agreement >= 99 % over the entries with |g_ref| > 10 % of the tensor's max |g_ref|;
+  Chamfer arg-mins of the oracle's reconstruction: bit-exact after canonicalising bit-equal distances to the lowest index;
+  class predictions exact except samples whose top-2 logit gap is inside the logit tolerance (listed).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pcaa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(LR=1e-4, B1=0.9, B2=0.99, GP_WEIGHT=15, ADV_WEIGHT=1)
+GRAD_TOL_ENC = 6e-2
+GRAD_TOL_DEC = 4e-2
+
+
+def relmax(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def relnorm(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bn_cancelled_bias(name):
+    return name.endswith("module.0.bias") or name.endswith("conv1d.bias")
+
+
+def build_trainer(p, C, nmax):
+    from opensetgaitrecognition_pcaa_b200 import models
+    from opensetgaitrecognition_pcaa_b200.train import PCAATrainer
+    enc = models.CGEncoder(n_out_labels=C, use_projection_head=True, nmax_points=nmax)
+    dec = models.CGDecoder(input_dim=64, nmax_points=nmax)
+    dis = models.CGDiscriminator(C)
+    gph = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ELU())
+    for pre, m in (("E.", enc), ("G.", dec), ("D.", dis), ("GPH.", gph)):
+        m.load_state_dict({k[len(pre):]: v.clone() for k, v in p.items() if k.startswith(pre)})
+        m.cuda().float()
+    means = O.sample_distant_points(32, C, 10, 10).float()
+    return PCAATrainer(enc, dec, dis, gph, means, CFG), means
+
+
+def one_step_vs_oracle(B, nmax, C, seed):
+    from opensetgaitrecognition_pcaa_b200 import ops
+    p = O.det_params(C, nmax, seed)
+    po = {k: v.clone() for k, v in p.items()}
+    tr, means = build_trainer(p, C, nmax)
+    pcs, gt = O.synth_batch(B, nmax, C, seed=4321 + seed)
+    rng = np.random.default_rng(999 + seed)
+    z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float()
+    alphas = torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32))
+    ref = O.train_step_variant4(po, {}, pcs, gt, z0, alphas, means, dict(CFG, NMAX=nmax))
+    out = tr.step(pcs.cuda(), gt.cuda(), z0.cuda(), alphas.cuda())
+    torch.cuda.synchronize()
+    tag = f"[B={B} N={nmax}]"
+    for k in ("rec_loss", "d_loss", "sup_loss", "loss_g"):
+        a, b = float(out[k]), float(ref[k])
+        print(f"{tag} {k}: {a:.6f} vs oracle {b:.6f}")
+        assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (k, a, b)
+    e_fv, e_lg = relmax(out["fv"], ref["fv"]), relmax(out["logits"], ref["logits"])
+    print(f"{tag} relmax fv {e_fv:.4f} logits {e_lg:.4f}")
+    assert e_fv < 3e-2 and e_lg < 3e-2
+    lg = ref["logits"]
+    top2 = lg.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 3e-2 * float(lg.abs().max())
+    mism = torch.nonzero(out["pred"].cpu().long() != ref["pred"]).flatten().tolist()
+    print(f"{tag} class predictions: {len(mism)} of {B} differ {mism}; undecided (top-2 gap inside tolerance): {(~decided).nonzero().flatten().tolist()}")
+    assert all(not bool(decided[i]) for i in mism)
+    worst = {"E.": (0.0, ""), "G.": (0.0, ""), "GPH.": (0.0, ""), "D.": (0.0, "")}
+    sign_worst = (1.0, "")
+    for kind, flat in (("g_grads", tr.G), ("d_grads", tr.D)):
+        for n, g_ref in ref[kind].items():
+            if g_ref is None or n not in flat.slices or bn_cancelled_bias(n):
+                continue
+            g = flat.view(flat.g, n)
+            e = relnorm(g, g_ref)
+            pre = n.split(".")[0] + "."
+            if e > worst[pre][0]:
+                worst[pre] = (e, n)
+            tol = GRAD_TOL_DEC if pre in ("G.", "GPH.") else GRAD_TOL_ENC
+            assert e < tol, (n, e)
+            if float(g_ref.abs().max()) == 0.0:
+                continue                                            # e.g. the critic's output bias: sum of +1/B and -1/B terms
+            big = g_ref.abs() > 0.1 * g_ref.abs().max()
+            agree = float((torch.sign(g.cpu())[big] == torch.sign(g_ref)[big]).float().mean())
+            if agree < sign_worst[0]:
+                sign_worst = (agree, n)
+            assert agree >= 0.99, (n, agree)
+    print(f"{tag} worst gradient relnorm per network: " + ", ".join(f"{k} {v[0]:.4f} ({v[1]})" for k, v in worst.items())
+          + f"; worst sign agreement on large entries {sign_worst[0]:.4f} ({sign_worst[1]})")
+    # Chamfer kernel on the ORACLE's reconstruction at this size: arg-mins bit-exact (ties canonicalised to the lowest index)
+    rec = ref["rec"].cuda().contiguous()
+    fl, i1, i2 = ops.chamfer_fwd(rec, pcs.cuda())
+    P = O.pairwise_dist(pcs, ref["rec"])                            # [B,T,N(gt),N(pred)]
+    for ours, want, dim in ((i1, ref["idx_gt_for_pred"], 2), (i2, ref["idx_pred_for_gt"], 3)):
+        ours = ours.cpu().long()
+        bad = ours != want
+        if bool(bad.any()):
+            # a mismatch is admissible only between bit-equal distances (padded duplicate points)
+            d_ours = torch.gather(P, dim, ours.unsqueeze(dim)).squeeze(dim)
+            d_want = torch.gather(P, dim, want.unsqueeze(dim)).squeeze(dim)
+            n_tie = int((bad & (d_ours == d_want)).sum())
+            n_near = int((bad & (d_ours != d_want)).sum())
+            rel = float(((d_ours - d_want).abs() / d_want.abs().clamp_min(1e-12))[bad].max())
+            print(f"{tag} Chamfer arg-min: {int(bad.sum())} of {bad.numel()} differ: {n_tie} exact ties, {n_near} near-ties (max relative distance gap {rel:.2e})")
+            assert rel < 1e-5
+    loss_ref = float(ref["rec_loss"])
+    assert abs(float(fl.mean()) - loss_ref) <= 1e-4 * abs(loss_ref)
+    return tr, po, ref
+
+
+@pytest.mark.parametrize("B", [32, 64])
+def test_step_vs_oracle_at_baseline_batch(B):
+    """BASELINE configs 1-2: batch 32 / 64, N = 150, C = 4 (PCAA_ablation.py:882-1021)."""
+    one_step_vs_oracle(B, 150, 4, seed=20 + B)
+
+
+@pytest.mark.parametrize("nmax", [90, 110, 130])
+def test_step_vs_oracle_point_sweep(nmax):
+    """BASELINE config 4 (train_pointsubsampling.py:52-56): N = 90 / 110 / 130, batch 16 (the reference's BATCH_SIZE)."""
+    one_step_vs_oracle(16, nmax, 4, seed=nmax)
+
+
+def test_unsupervised_iteration_matches_torch_adam_skip_semantics():
+    """SUPERVISION_FREQUENCY > 1 (PCAA_ablation.py:1005-1018): on an unsupervised iteration the classifier layers have no
+    gradient and torch.optim.Adam leaves them (weights, moments, step count) untouched; the next supervised iteration updates
+    them with THEIR step count (1), everything else with step 2."""
+    B, nmax, C, seed = 4, 50, 2, 3
+    p = O.det_params(C, nmax, seed)
+    po = {k: v.clone() for k, v in p.items()}
+    tr, means = build_trainer(p, C, nmax)
+    cls = [n for n in tr.G.names if n.startswith("E.MLP_head.") or n.startswith("E.MLP_sup2.")]
+    before = {n: tr.G.view(tr.G.p, n).clone() for n in cls}
+    ost = {}
+    rng = np.random.default_rng(1)
+    for s, sup in enumerate((False, True)):
+        pcs, gt = O.synth_batch(B, nmax, C, seed=50 + s)
+        z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float()
+        al = torch.from_numpy(rng.uniform(0, 1, (B, 1)).astype(np.float32))
+        ref = O.train_step(po, ost, pcs, gt, z0, al, means, dict(CFG, NMAX=nmax), 4, supervised=sup)
+        out = tr.step(pcs.cuda(), gt.cuda(), z0.cuda(), al.cuda(), supervised=sup)
+        torch.cuda.synchronize()
+        assert abs(float(out["sup_loss"]) - float(ref["sup_loss"])) <= 2e-2          # still reported
+        if not sup:
+            for n in cls:
+                assert ref["g_grads"][n] is None
+                assert torch.equal(tr.G.view(tr.G.p, n), before[n]), n                 # untouched, as torch's Adam leaves them
+                assert float(tr.G.view(tr.G.m, n).abs().max()) == 0.0
+        else:
+            # first update of the classifier layers: |step| = lr (bias correction of step 1), not lr * (1-b1)/(1-b1^2)
+            for n in cls:
+                d = (tr.G.view(tr.G.p, n) - before[n]).abs()
+                assert 0.9 * CFG["LR"] < float(d.max()) <= 1.01 * CFG["LR"], (n, float(d.max()))
+                e = (tr.G.view(tr.G.p, n).cpu() - po[n]).abs()
+                assert float(e.max()) <= 2.02 * CFG["LR"] and float((e > 5e-6).float().mean()) < 0.1, n
+    assert tr._cls_step == 1 and tr.G.step == 2 and int(tr._cls_step_dev) == 1
+
+
+def test_out_of_range_label_is_loud():
+    """The reference raises on a label outside [0, C) (one_hot / CrossEntropyLoss); here the losses turn NaN, no OOB read."""
+    B, nmax, C = 4, 50, 2
+    tr, means = build_trainer(O.det_params(C, nmax, 0), C, nmax)
+    pcs, gt = O.synth_batch(B, nmax, C, seed=1)
+    gt[1] = C + 3
+    out = tr.step(pcs.cuda(), gt.cuda(), torch.zeros(B, 32).cuda(), torch.full((B, 1), 0.5).cuda())
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(out["d_loss"])) and bool(torch.isnan(out["sup_loss"]))
+
+
+# ---------------------------------------------------------------------------------------------- config 5: label parity
+def test_openset_labels_on_4096_crops_match_the_reference_encoder(golden_dir):
+    """inference_PCAA.py:195-314 on 2 048 test + 2 048 unseen crops, N = 150, k = 1, 2, 4, 6.  Golden embeddings / logits come
+    from the reference's own CGEncoder on the CPU; the labels from the oracle procedure on them.  Exceptions are LISTED:
+    a window may differ only if one of its crops is (i) inside the score band around the threshold that the measured
+    embedding deviation spans, or (ii) has a top-2 logit gap inside the measured logit deviation."""
+    from opensetgaitrecognition_pcaa_b200 import inference as I, models
+    path = os.path.join(golden_dir, "infer4096_n150.npz")
+    g = np.load(path)
+    C, nmax, seed = int(g["C"]), int(g["nmax"]), int(g["seed"])
+    p = O.det_params(C, nmax, seed)
+    p["E.MLP_sup1.0.weight"] = p["E.MLP_sup1.0.weight"] * float(g["emb_scale"])     # see oracle/gen_golden.py infer4096_case
+    p["E.MLP_sup1.0.bias"] = p["E.MLP_sup1.0.bias"] * float(g["emb_scale"])
+    for k in g.files:
+        if k.startswith("bn:"):
+            p[k[3:]] = torch.from_numpy(g[k])
+    enc = models.CGEncoder(n_out_labels=C, use_projection_head=True, nmax_points=nmax)
+    enc.load_state_dict({k[2:]: v.clone() for k, v in p.items() if k.startswith("E.")})
+    enc = enc.cuda().float().eval()
+    t_pcs, t_sub = O.synth_subject_stream(g["known"].tolist(), int(g["per_known"]), nmax, seed=7000)
+    u_pcs, u_sub = O.synth_subject_stream(g["unseen"].tolist(), int(g["per_unseen"]), nmax, seed=9000)
+    u_pcs, u_sub = u_pcs[:2048], u_sub[:2048]
+    t_lab = np.searchsorted(g["known"], t_sub)
+    assert np.array_equal(t_lab, g["t_lab"]) and np.array_equal(u_sub, g["u_lab"])
+    means = torch.from_numpy(g["means"]).cuda()
+    emb = {"test": I.encode(enc, t_pcs.cuda(), 512), "unseen": I.encode(enc, u_pcs.cuda(), 512)}
+    fv = torch.cat([emb["test"][0], emb["unseen"][0]]).cpu()
+    fv_ref = torch.from_numpy(np.concatenate([g["t_fv"], g["u_fv"]]))
+    lg_ref = torch.from_numpy(np.concatenate([g["t_logits"], g["u_logits"]]))
+    e_fv = float((fv - fv_ref).abs().max() / fv_ref.abs().max())
+    print(f"[infer4096] embeddings: relmax {e_fv:.4f} over 4096 crops")
+    assert e_fv < 3e-2
+    pred = torch.cat([emb["test"][1], emb["unseen"][1]]).cpu().long()
+    top2 = lg_ref.topk(2, dim=1).values
+    undecided = (top2[:, 0] - top2[:, 1]) <= 3e-2 * float(lg_ref.abs().max())
+    pm = torch.nonzero(pred != lg_ref.argmax(1)).flatten()
+    print(f"[infer4096] class predictions: {len(pm)} of 4096 differ, all inside the logit tolerance: "
+          f"{bool(undecided[pm].all())}; undecided crops: {int(undecided.sum())}")
+    assert bool(undecided[pm].all())
+    ll_ref = O.joint_log_likelihood(fv_ref.numpy(), g["means"])
+    ll = O.joint_log_likelihood(fv.numpy(), g["means"])
+    band = float(np.abs(ll - ll_ref).max())
+    print(f"[infer4096] log-likelihood deviation caused by the embedding tolerance: max {band:.4f} (scores span {ll_ref.min():.1f}..{ll_ref.max():.1f})")
+    total = differ = 0
+    for k in (1, 2, 4, 6):
+        out = I.naive_sequential_procedure(k, enc, means, None, t_lab, None, u_sub, seed=0, unseen_valid_ratio=0.2, embeddings=emb)
+        assert np.array_equal(out["labels"], g[f"labels_k{k}"]), k                     # skip rules, validation subjects
+        lthr = np.log(float(g[f"threshold_k{k}"]))
+        border = (np.abs(ll_ref - lthr) <= 2 * band + abs(out["log_threshold"] - lthr)) | undecided.numpy()
+        # window -> crops: windows of the TEST stream first, then the kept UNSEEN windows (inference.py / :239-314)
+        nw_t = 2048 // k
+        keep_t = I._uniform_windows(t_lab, k)
+        keep_u = I._uniform_windows(u_sub, k) & ~np.isin(u_sub[: (2048 // k) * k].reshape(-1, k)[:, 0], out["val_subjects"])
+        first = np.concatenate([np.nonzero(keep_t)[0] * k, 2048 + np.nonzero(keep_u)[0] * k])
+        mism = np.nonzero(out["preds"] != g[f"preds_k{k}"])[0]
+        unexplained = [int(w) for w in mism if not border[first[w]:first[w] + k].any()]
+        total += len(out["preds"])
+        differ += len(mism)
+        print(f"[infer4096] k={k}: {len(out['preds'])} windows, {len(mism)} labels differ from the reference "
+              f"(windows {mism.tolist()[:20]}{'...' if len(mism) > 20 else ''}), unexplained: {unexplained}; "
+              f"threshold {out['threshold']:.6e} vs {float(g[f'threshold_k{k}']):.6e}")
+        assert not unexplained, (k, unexplained)
+    assert differ <= 0.02 * total, (differ, total)

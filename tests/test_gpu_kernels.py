@@ -216,6 +216,41 @@ def test_tcn_conv_as_gemm(ops, dil):
     assert rel_err(dW.reshape(Cout, Cin, 3), ww.grad) < 1e-5
 
 
+@pytest.mark.parametrize("dil", [1, 2, 4])
+@pytest.mark.parametrize("B,Cin,Cout", [(5, 1024, 16), (3, 16, 32), (7, 256, 512), (64, 64, 128)])
+def test_tcn_conv_on_tensor_cores(ops, dil, B, Cin, Cout):
+    """The path engine.tcn_forward / tcn_backward actually run (models.py:59-76): bf16 im2col + tcgen05 GEMM (TC_PLAIN, fp32
+    output) forward; weight gradient TC_WGRAD_ACC (k = the B*T rows) and data gradient TC_PLAIN + col2im backward; against
+    autograd through oracle.causal_dilated_conv on bf16-rounded operands (so the comparison isolates the kernels: fp32
+    accumulation order only -> 1e-4) and against the unrounded fp32 result (bf16 operand tolerance 1e-2)."""
+    L = ops._lib
+    g = torch.Generator().manual_seed(17 * dil + B + Cin)
+    T = 30
+    x = torch.randn(B, T, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, generator=g) / math.sqrt(3 * Cin)
+    b = torch.randn(Cout, generator=g)
+    xr, wr = bf16_round(x).requires_grad_(True), bf16_round(w).requires_grad_(True)
+    ref = O.causal_dilated_conv(xr, wr, b, dil)
+    R, K = B * T, Cin * 3
+    col = ops.tcn_im2col(cuda(x), dil, torch.bfloat16)
+    wb = ops.pack_bf16(cuda(w).reshape(Cout, K))
+    y = ops.gemm_tc(col, wb, L.TC_PLAIN, R, Cout, K, bias=cuda(b), out_dtype=torch.float32)
+    assert y.dtype == torch.float32 and tuple(y.shape) == (R, Cout)
+    assert rel_err(y, ref.detach().reshape(R, Cout)) < 1e-4
+    assert rel_err(y, O.causal_dilated_conv(x, w, b, dil).reshape(R, Cout)) < 1e-2
+    dy = bf16_round(torch.randn(B, T, Cout, generator=g))
+    ref.backward(dy)
+    dyb = cuda(dy).reshape(R, Cout).bfloat16()
+    dW = torch.zeros(Cout, K, device="cuda")
+    ops.gemm_tc(dyb, col, L.TC_WGRAD_ACC, Cout, K, R, a_mn=L.OP_MN, b_mn=L.OP_MN, out=dW)
+    assert rel_err(dW.reshape(Cout, Cin, 3), wr.grad) < 1e-4
+    ops.gemm_tc(dyb, col, L.TC_WGRAD_ACC, Cout, K, R, a_mn=L.OP_MN, b_mn=L.OP_MN, out=dW)          # accumulates
+    assert rel_err(dW.reshape(Cout, Cin, 3), 2 * wr.grad) < 1e-4
+    dcol = ops.gemm_tc(dyb, wb, L.TC_PLAIN, R, K, Cout, b_mn=L.OP_MN, out_dtype=torch.float32)
+    dx = ops.tcn_col2im(dcol, B, T, Cin, dil)
+    assert rel_err(dx, xr.grad) < 1e-4
+
+
 def test_small_helpers(ops):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(11, 30, 40, generator=g)
@@ -517,6 +552,25 @@ def test_pointnet_t_kernels(ops, B, N, C):
     # eval-mode layer 1: activation directly
     aT, none = ops.pointnet_l1_fwd_t(cuda(x), cuda(w), cuda(b), coef=cuda(coef[:2]))
     assert none is None and rel_err(_un(ops, aT, P), O.elu(y_ref * sc + sh)) < 1e-2 and _pad_is_zero(ops, aT, P)
+    # train-mode layer 1 with the BatchNorm statistics taken from the INPUT moments (y is linear in x): same coefficients as
+    # the pass over y gives, running statistics updated the same way, and one kernel writes y and ELU(BN(y))
+    mom = ops.input_moments(cuda(x)).cpu()
+    xd = xr.double()
+    want_mom = torch.cat([xd.sum(1), torch.stack([(xd[f] * xd[h]).sum() for f in range(4) for h in range(f, 4)])])
+    assert rel_err(mom, want_mom) < 1e-6
+    gam, bet = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    rm0, rv0 = 0.1 * torch.randn(C, generator=g), 0.5 + torch.rand(C, generator=g)
+    rm_a, rv_a, rm_b, rv_b = cuda(rm0), cuda(rv0), cuda(rm0), cuda(rv0)
+    coef_stats = ops.bn_finalize(st, P, cuda(gam), cuda(bet), rm_a, rv_a)
+    coef_mom = ops.bn_from_input_moments(ops.input_moments(cuda(x)), P, cuda(w), cuda(b), cuda(gam), cuda(bet), rm_b, rv_b)
+    y64 = w.double() @ xd + b.double()[:, None]
+    mean64, var64 = y64.mean(1), y64.var(1, unbiased=False)
+    assert rel_err(coef_mom[2], mean64) < 1e-5 and rel_err(coef_mom[3], 1 / torch.sqrt(var64 + 1e-5)) < 1e-5
+    assert rel_err(coef_mom, coef_stats) < 1e-4 and rel_err(rm_b, rm_a) < 1e-5 and rel_err(rv_b, rv_a) < 1e-4
+    y2T, a2T = ops.pointnet_l1_fwd_bn_t(cuda(x), cuda(w), cuda(b), coef_mom)
+    assert torch.equal(y2T, yT) and _pad_is_zero(ops, a2T, P)
+    cm = coef_mom.cpu()
+    assert rel_err(_un(ops, a2T, P), O.elu(y_ref * cm[0][:, None] + cm[1][:, None])) < 1e-2
     # from here on the bf16-rounded y is the common input
     yb = _un(ops, yT, P)
     a_ref = O.elu(yb * sc + sh)

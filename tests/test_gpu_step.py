@@ -267,7 +267,11 @@ def test_checkpoint_files_are_the_reference_format_and_resume(tmp_path):
         ta.step(pcs.cuda(), gt.cuda(), *draws())
     d = save_checkpoint(ta, "PCAA_t", root=str(tmp_path))
     files = sorted(os.listdir(d))
-    assert files == ["PCAA_t_D.pt", "PCAA_t_E.pt", "PCAA_t_G.pt", "PCAA_t_GPH.pt", "PCAA_t_OPT.pt", "discriminator_means.pt"]
+    assert files == ["PCAA_t_D.pt", "PCAA_t_E.pt", "PCAA_t_G.pt", "PCAA_t_GPH.pt", "PCAA_t_OPT.pt", "config.pkl", "discriminator_means.pt"]
+    import pickle
+    with open(os.path.join(d, "config.pkl"), "rb") as f:                               # what CGAAE_inference_setup reads first (:63-67)
+        cfg = pickle.load(f)
+    assert cfg["MODEL_NAME"] == "PCAA_t" and cfg["NMAX"] == nmax and cfg["TRAIN_CLASSES"] == [0, 1]
     sd = torch.load(os.path.join(d, "PCAA_t_E.pt"), map_location="cpu")                 # weights_only default: plain tensors
     want = {k[2:]: v for k, v in p.items() if k.startswith("E.")}
     assert list(sd.keys()) == list(want.keys()) and all(sd[k].shape == want[k].shape for k in want)
@@ -311,9 +315,10 @@ def test_fit_epoch_loop_on_a_synthetic_split(tmp_path):
         assert 0.0 <= h["Train Accuracy"] <= 1.0 and 0.0 <= h["Valid Accuracy"] <= 1.0
     assert hist[-1]["Reconstruction Loss Train"] < hist[0]["Reconstruction Loss Train"]
     d = os.path.join(str(tmp_path), "models", "PCAA_fit")
-    assert os.path.exists(os.path.join(d, "discriminator_means.pt"))
+    assert os.path.exists(os.path.join(d, "discriminator_means.pt")) and os.path.exists(os.path.join(d, "config.pkl"))
     if any(h["saved"] for h in hist):
-        assert os.path.exists(os.path.join(d, "PCAA_fit_E.pt")) and os.path.exists(os.path.join(d, "PCAA_fit_GPH.pt"))
+        for suffix in ("E", "G", "D", "GPH", "DPH"):                                   # the five files of PCAA_ablation.py:1088-1112
+            assert os.path.exists(os.path.join(d, f"PCAA_fit_{suffix}.pt")), suffix
     # the saved flags follow the reference's rule: strictly better validation accuracy than the best so far (from 0)
     best = 0.0
     for h in hist:
