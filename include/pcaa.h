@@ -275,6 +275,9 @@ int pcaa_gather_rows(const void* src, const int64_t* idx, void* dst, int64_t n_i
  * over NVLink peer memory (the only exchange of the path; the reference is single-GPU).  n, src_stride
  * multiples of 4; 16-byte aligned buffers. */
 int pcaa_sum_into(float* dst, const float* src, int64_t n, int64_t src_stride, int nsrc, pcaa_stream stream);
+/* dst[i] = sum_k src[k*src_stride + i], k = 0 .. nsrc-1 in that order (overwrite): the one-shot reduction of a small span
+ * whose per-rank copies were gathered in RANK order, so that every rank computes bit-identical sums */
+int pcaa_sum_rows(float* dst, const float* src, int64_t n, int64_t src_stride, int nsrc, pcaa_stream stream);
 /* CUDA-graph form of the same update: the step counter lives on the device.  pcaa_adam_advance increments
  * step_dev[0] and writes coef_dev = { lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step) } (the bias corrections
  * torch.optim.Adam computes on the host); pcaa_adam_flat_dev reads them, so a captured train step advances the

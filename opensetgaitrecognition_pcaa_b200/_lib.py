@@ -67,6 +67,7 @@ SIGNATURES = {
     "pcaa_disc_fwd": [_p] * 10 + [_f, _p, _f, _l, _i, _p],
     "pcaa_adam_flat": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _i, _f, _p, _p],
     "pcaa_sum_into": [_p, _p, _l, _l, _i, _p],
+    "pcaa_sum_rows": [_p, _p, _l, _l, _i, _p],
     "pcaa_gather_rows": [_p, _p, _p, _l, _l, _l, _p],
     "pcaa_adam_advance": [_p, _p, _f, _f, _f, _p],
     "pcaa_adam_flat_dev": [_p, _p, _p, _p, _l, _f, _f, _f, _p, _f, _p, _p],

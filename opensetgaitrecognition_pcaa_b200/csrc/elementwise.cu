@@ -621,9 +621,9 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_
 // dst[i] += sum_k src[k * stride + i]: the local reduction of the copy-engine gradient exchange (dp.PeerExchange): the
 // chunks pulled from the peers' gradient buffers are added into this rank's chunk.  16-byte accesses, grid-stride.
 __global__ void __launch_bounds__(256)
-sum_into_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n4, int64_t stride, int nsrc) {
+sum_into_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n4, int64_t stride, int nsrc, int overwrite) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
-        float4 a = reinterpret_cast<float4*>(dst)[i];
+        float4 a = overwrite ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(dst)[i];
         for (int k = 0; k < nsrc; ++k) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(src + k * stride) + i);
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
@@ -1093,8 +1093,16 @@ int pcaa_sum_into(float* dst, const float* src, int64_t n, int64_t src_stride, i
     if (n == 0 || nsrc == 0) return PCAA_OK;
     PCAA_REQUIRE(n % 4 == 0 && src_stride % 4 == 0 && ((uintptr_t)dst | (uintptr_t)src) % 16 == 0 && nsrc > 0, PCAA_ERR_ALIGN,
                  "sum_into: n and the source stride must be multiples of 4 floats, buffers 16-byte aligned");
-    sum_into_kernel<<<ew_grid(n / 4), 256, 0, ST(stream)>>>(dst, src, n / 4, src_stride, nsrc);
+    sum_into_kernel<<<ew_grid(n / 4), 256, 0, ST(stream)>>>(dst, src, n / 4, src_stride, nsrc, 0);
     return check_launch("sum_into");
+}
+
+int pcaa_sum_rows(float* dst, const float* src, int64_t n, int64_t src_stride, int nsrc, pcaa_stream stream) {
+    if (n == 0) return PCAA_OK;
+    PCAA_REQUIRE(n % 4 == 0 && src_stride % 4 == 0 && ((uintptr_t)dst | (uintptr_t)src) % 16 == 0 && nsrc > 0, PCAA_ERR_ALIGN,
+                 "sum_rows: n and the source stride must be multiples of 4 floats, buffers 16-byte aligned");
+    sum_into_kernel<<<ew_grid(n / 4), 256, 0, ST(stream)>>>(dst, src, n / 4, src_stride, nsrc, 1);
+    return check_launch("sum_rows");
 }
 
 int pcaa_gather_rows(const void* src, const int64_t* idx, void* dst, int64_t n_idx, int64_t row_bytes, int64_t n_src,

@@ -1093,7 +1093,13 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
     if (tmode && !pooled) PCAA_REQUIRE(out_dtype == PCAA_BF16, PCAA_ERR_UNSUPPORTED, "gemm_tc: channel-major modes store bf16");
     if (mode == PCAA_TC_DGRAD_ELUOUT) PCAA_REQUIRE(yprev != nullptr, PCAA_ERR_SHAPE, "gemm_tc: mode 5 needs the saved activation");
     if (yprev) PCAA_REQUIRE(((uintptr_t)yprev & 15) == 0 && (tmode || ldy % 8 == 0), PCAA_ERR_ALIGN, "gemm_tc: yprev alignment");
-    constexpr int BN = 256;
+    // Output tile width.  256 columns everywhere, except for the row-major epilogue modes (decoder / TCN forward and data
+    // gradient) when 256-wide tiles would leave more than half of the SMs without a tile: the decoder's inner layers at
+    // batch 256 are M = 256 rows x N = 4500 / 9000 columns = 36 / 72 tiles of 128 x 256 on 148 SMs; 128-wide tiles double
+    // the CTAs that stream the weight matrix.
+    const int m_tiles_ = ceil_div(M, BM);
+    const bool narrow = !tmode && !wgrad && (long long)m_tiles_ * ceil_div(N, 256) * 2 <= num_sms() && N > 128;
+    const int BN = narrow ? 128 : 256;
     CUtensorMap ta, tb;
     int rc;
     if (a_tiled) rc = make_map_tiled(&ta, A, M, ceil_div(K, 256), BK, BM);                 // [K/256 tiles][M][256], k = points
@@ -1155,27 +1161,46 @@ static int gemm_tc_dispatch(const void* A, int64_t lda, int a_layout, const void
     p.pool_n = pooled ? (int)ldo : 0;
     p.pool_inv_n = pooled ? 1.f / (float)ldo : 0.f;
     const int key = (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
+    if (narrow) {
+        if (key == 0) {
+            switch (mode) {
+                case PCAA_TC_BIAS_STATS: return launch_tc<128, false, false, MODE_BIAS_STATS>(ta, tb, to, ty, p, st);
+                case PCAA_TC_BIAS_ELU: return launch_tc<128, false, false, MODE_BIAS_ELU>(ta, tb, to, ty, p, st);
+                case PCAA_TC_PLAIN: return launch_tc<128, false, false, MODE_PLAIN>(ta, tb, to, ty, p, st);
+                case PCAA_TC_DGRAD_ELUBN: return launch_tc<128, false, false, MODE_DGRAD_ELUBN>(ta, tb, to, ty, p, st);
+                default: break;
+            }
+        } else if (key == 1) {
+            switch (mode) {
+                case PCAA_TC_PLAIN: return launch_tc<128, false, true, MODE_PLAIN>(ta, tb, to, ty, p, st);
+                case PCAA_TC_DGRAD_ELUOUT: return launch_tc<128, false, true, MODE_DGRAD_ELUOUT>(ta, tb, to, ty, p, st);
+                default: break;
+            }
+        }
+        set_error("gemm_tc: operand layout (a=%d, b=%d) is not instantiated for mode %d (128-wide tiles)", a_layout, b_layout, mode);
+        return PCAA_ERR_UNSUPPORTED;
+    }
     if (key == 0) {
-        if (wgrad) return launch_tc<BN, false, false, MODE_WGRAD>(ta, tb, to, ty, p, st);
+        if (wgrad) return launch_tc<256, false, false, MODE_WGRAD>(ta, tb, to, ty, p, st);
         switch (mode) {
-            case PCAA_TC_BIAS_STATS: return launch_tc<BN, false, false, MODE_BIAS_STATS>(ta, tb, to, ty, p, st);
-            case PCAA_TC_BIAS_ELU: return launch_tc<BN, false, false, MODE_BIAS_ELU>(ta, tb, to, ty, p, st);
-            case PCAA_TC_PLAIN: return launch_tc<BN, false, false, MODE_PLAIN>(ta, tb, to, ty, p, st);
-            case PCAA_TC_DGRAD_ELUBN: return launch_tc<BN, false, false, MODE_DGRAD_ELUBN>(ta, tb, to, ty, p, st);
+            case PCAA_TC_BIAS_STATS: return launch_tc<256, false, false, MODE_BIAS_STATS>(ta, tb, to, ty, p, st);
+            case PCAA_TC_BIAS_ELU: return launch_tc<256, false, false, MODE_BIAS_ELU>(ta, tb, to, ty, p, st);
+            case PCAA_TC_PLAIN: return launch_tc<256, false, false, MODE_PLAIN>(ta, tb, to, ty, p, st);
+            case PCAA_TC_DGRAD_ELUBN: return launch_tc<256, false, false, MODE_DGRAD_ELUBN>(ta, tb, to, ty, p, st);
             default: break;
         }
     } else if (key == 1) {
         switch (mode) {
-            case PCAA_TC_PLAIN: return launch_tc<BN, false, true, MODE_PLAIN>(ta, tb, to, ty, p, st);
-            case PCAA_TC_DGRAD_ELUOUT: return launch_tc<BN, false, true, MODE_DGRAD_ELUOUT>(ta, tb, to, ty, p, st);
-            case PCAA_TC_T_BIAS_STATS: return launch_tc<BN, false, true, MODE_T_BIAS_STATS>(ta, tb, to, ty, p, st);
-            case PCAA_TC_T_AFFINE_ELU: return launch_tc<BN, false, true, MODE_T_AFFINE_ELU>(ta, tb, to, ty, p, st);
-            case PCAA_TC_T_AFFINE_ELU_POOL: return launch_tc<BN, false, true, MODE_T_AFFINE_ELU_POOL>(ta, tb, to, ty, p, st);
+            case PCAA_TC_PLAIN: return launch_tc<256, false, true, MODE_PLAIN>(ta, tb, to, ty, p, st);
+            case PCAA_TC_DGRAD_ELUOUT: return launch_tc<256, false, true, MODE_DGRAD_ELUOUT>(ta, tb, to, ty, p, st);
+            case PCAA_TC_T_BIAS_STATS: return launch_tc<256, false, true, MODE_T_BIAS_STATS>(ta, tb, to, ty, p, st);
+            case PCAA_TC_T_AFFINE_ELU: return launch_tc<256, false, true, MODE_T_AFFINE_ELU>(ta, tb, to, ty, p, st);
+            case PCAA_TC_T_AFFINE_ELU_POOL: return launch_tc<256, false, true, MODE_T_AFFINE_ELU_POOL>(ta, tb, to, ty, p, st);
             default: break;
         }
     } else if (key == 3) {
-        if (wgrad) return launch_tc<BN, true, true, MODE_WGRAD>(ta, tb, to, ty, p, st);
-        if (mode == PCAA_TC_T_DGRAD_ELUBN) return launch_tc<BN, true, true, MODE_T_DGRAD_ELUBN>(ta, tb, to, ty, p, st);
+        if (wgrad) return launch_tc<256, true, true, MODE_WGRAD>(ta, tb, to, ty, p, st);
+        if (mode == PCAA_TC_T_DGRAD_ELUBN) return launch_tc<256, true, true, MODE_T_DGRAD_ELUBN>(ta, tb, to, ty, p, st);
     }
     set_error("gemm_tc: operand layout (a=%d, b=%d) is not instantiated for mode %d", a_layout, b_layout, mode);
     return PCAA_ERR_UNSUPPORTED;

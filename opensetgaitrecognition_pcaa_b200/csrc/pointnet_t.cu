@@ -90,11 +90,7 @@ struct L1Coef { float w[4]; float bias, scale, shift, scale_l2, shift_l2, pad0, 
 __global__ void __launch_bounds__(256, 3)
 pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                          const float* __restrict__ scale, const float* __restrict__ shift,
-                         __nv_bfloat16* __restrict__ yT, __nv_bfloat16* __restrict__ aT, double* __restrict__ stats,
-                         int64_t P, int64_t TN, int Cout) {
-    // aT == nullptr: one output -- yT receives y = W x + b, or ELU(scale*y + shift) when scale is given (eval mode).
-    // aT != nullptr (train mode with BatchNorm coefficients known up front, pcaa_bn_from_input_moments): yT receives y
-    // AND aT receives ELU(scale*y + shift) in the same pass -- y is never re-read to form the activation.
+                         __nv_bfloat16* __restrict__ yT, double* __restrict__ stats, int64_t P, int64_t TN, int Cout) {
     __shared__ L1Coef coef[8 * L1_CH_PER_WARP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 8 * L1_CH_PER_WARP) {
@@ -144,12 +140,11 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
                 s2[k] = fmaf(v, v, s2[k]);
                 y[j] = v;
             }
-            if (aT != nullptr && c0 + k < Cout) *reinterpret_cast<uint4*>(yT + t256(p0, c0 + k, Cout)) = pack8(y);
             if (act) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) y[j] = j < vcnt ? elu_l2(fmaf(y[j], bk.y, bk.z), fmaf(y[j], bk.w, shl)) : 0.f;
             }
-            if (c0 + k < Cout) *reinterpret_cast<uint4*>((aT != nullptr ? aT : yT) + t256(p0, c0 + k, Cout)) = pack8(y);
+            if (c0 + k < Cout) *reinterpret_cast<uint4*>(yT + t256(p0, c0 + k, Cout)) = pack8(y);
         }
     }
     if (stats) {
@@ -160,6 +155,104 @@ pointnet_l1_fwd_t_kernel(const float* __restrict__ x, const float* __restrict__ 
                 atomicAdd(&stats[c0 + k], (double)a);
                 atomicAdd(&stats[Cout + c0 + k], (double)b);
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layer 1 forward, train mode
+// y1 = W1 x + b1 AND a1 = ELU(scale*y1 + shift) in one pass (the BatchNorm coefficients are known up front from the input
+// moments).  Two bf16 tensors are written per element computed, so this kernel is bound by instruction issue, not by HBM: all
+// fp32 arithmetic runs on packed fp32x2 instructions (two points per FFMA2 / FADD2), ELU is branch-free
+// (ELU(z) = max(z, min(2^(z log2 e), 1) - 1)), constants come duplicated from shared memory as ready 64-bit operands, full tiles
+// take a path without per-point validity selects.  The FMA order equals pointnet_l1_fwd_t_kernel's: y1 is bit-identical.
+struct L1Coef2 { float2 w[4]; float2 bias, scale, shift, scale_l2, shift_l2; };      // every constant as a (c, c) pair
+
+__device__ __forceinline__ unsigned long long f2u(float2 v) { return pk2f(v.x, v.y); }
+
+template <bool FULL>
+__device__ __forceinline__ void l1_bn_channel(const L1Coef2& c, const unsigned long long (&x)[4][4], int vcnt,
+                                              __nv_bfloat16* __restrict__ yp, __nv_bfloat16* __restrict__ ap) {
+    const unsigned long long w0 = f2u(c.w[0]), w1 = f2u(c.w[1]), w2 = f2u(c.w[2]), w3 = f2u(c.w[3]), b = f2u(c.bias);
+    const unsigned long long sc = f2u(c.scale), sh = f2u(c.shift), scl = f2u(c.scale_l2), shl = f2u(c.shift_l2);
+    const unsigned long long neg1 = pk2f(-1.f, -1.f);
+    uint4 yo, ao;
+    __nv_bfloat162* yh = reinterpret_cast<__nv_bfloat162*>(&yo);
+    __nv_bfloat162* ah = reinterpret_cast<__nv_bfloat162*>(&ao);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned long long y2 = fma2f(w3, x[3][q], b);
+        y2 = fma2f(w2, x[2][q], y2);
+        y2 = fma2f(w1, x[1][q], y2);
+        y2 = fma2f(w0, x[0][q], y2);
+        float ylo, yhi;
+        upk2f(y2, ylo, yhi);
+        if (!FULL) {                                               // pad points are stored as zeros
+            ylo = 2 * q < vcnt ? ylo : 0.f;
+            yhi = 2 * q + 1 < vcnt ? yhi : 0.f;
+            y2 = pk2f(ylo, yhi);
+        }
+        float zlo, zhi, llo, lhi;
+        upk2f(fma2f(y2, sc, sh), zlo, zhi);
+        upk2f(fma2f(y2, scl, shl), llo, lhi);
+        float elo, ehi;
+        upk2f(add2f(pk2f(fminf(ex2_fast(llo), 1.f), fminf(ex2_fast(lhi), 1.f)), neg1), elo, ehi);
+        float alo = fmaxf(zlo, elo), ahi = fmaxf(zhi, ehi);
+        if (!FULL) {
+            alo = 2 * q < vcnt ? alo : 0.f;
+            ahi = 2 * q + 1 < vcnt ? ahi : 0.f;
+        }
+        yh[q] = __floats2bfloat162_rn(ylo, yhi);
+        ah[q] = __floats2bfloat162_rn(alo, ahi);
+    }
+    *reinterpret_cast<uint4*>(yp) = yo;
+    *reinterpret_cast<uint4*>(ap) = ao;
+}
+
+__global__ void __launch_bounds__(256, 2)
+pointnet_l1_fwd_bn_t_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                            const float* __restrict__ scale, const float* __restrict__ shift,
+                            __nv_bfloat16* __restrict__ yT, __nv_bfloat16* __restrict__ aT, int64_t P, int64_t TN, int Cout) {
+    __shared__ L1Coef2 coef[8 * L1_CH_PER_WARP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 8 * L1_CH_PER_WARP) {
+        const int c = min(blockIdx.y * 8 * L1_CH_PER_WARP + (int)threadIdx.x, Cout - 1);
+        L1Coef2 k;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(w) + c);
+        k.w[0] = make_float2(t.x, t.x); k.w[1] = make_float2(t.y, t.y); k.w[2] = make_float2(t.z, t.z); k.w[3] = make_float2(t.w, t.w);
+        const float b = bias ? __ldg(bias + c) : 0.f, sc = __ldg(scale + c), sh = __ldg(shift + c);
+        k.bias = make_float2(b, b);
+        k.scale = make_float2(sc, sc);
+        k.shift = make_float2(sh, sh);
+        k.scale_l2 = make_float2(sc * LOG2E_F, sc * LOG2E_F);
+        k.shift_l2 = make_float2(sh * LOG2E_F, sh * LOG2E_F);
+        coef[threadIdx.x] = k;
+    }
+    __syncthreads();
+    const int c0 = (blockIdx.y * 8 + warp) * L1_CH_PER_WARP;
+    if (c0 >= Cout) return;
+    const L1Coef2* ck = coef + warp * L1_CH_PER_WARP;
+    const int64_t Ppad = (P + 255) & ~(int64_t)255;
+    const int64_t tile0 = (int64_t)blockIdx.x * L1_TILE_POINTS;
+    for (int ch = 0; ch < L1_TILE_POINTS / 256; ++ch) {
+        const int64_t p0 = tile0 + ch * 256 + lane * 8;
+        if (p0 >= Ppad) break;
+        float xv[4][8];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);
+        unsigned long long xp[4][4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xp[f][q] = pk2f(xv[f][2 * q], xv[f][2 * q + 1]);
+        const int vcnt = p0 + 8 <= P ? 8 : (p0 < P ? (int)(P - p0) : 0);
+        if (vcnt == 8) {
+#pragma unroll
+            for (int k = 0; k < L1_CH_PER_WARP; ++k)
+                if (c0 + k < Cout) l1_bn_channel<true>(ck[k], xp, 8, yT + t256(p0, c0 + k, Cout), aT + t256(p0, c0 + k, Cout));
+        } else {
+#pragma unroll
+            for (int k = 0; k < L1_CH_PER_WARP; ++k)
+                if (c0 + k < Cout) l1_bn_channel<false>(ck[k], xp, vcnt, yT + t256(p0, c0 + k, Cout), aT + t256(p0, c0 + k, Cout));
         }
     }
 }
@@ -261,6 +354,17 @@ __global__ void bn_from_input_moments_kernel(const double* __restrict__ mom, dou
 // layer 1 fused in: its dy is never written) or dy = dz when y is null.
 constexpr int L1W_CH_PER_WARP = 4;
 
+// two bf16 of one 32-bit word as a packed fp32x2 operand (lo = element 0, hi = element 1): two integer instructions
+__device__ __forceinline__ unsigned long long bf2_to_f2(uint32_t w) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(w << 16), "r"(w & 0xffff0000u));
+    return r;
+}
+
+// All arithmetic on packed fp32x2 instructions (FFMA2): per pair of points 2 FFMA2 form dy and 4 accumulate it against the
+// 4 input features -- the scalar version needed ~9 issue slots per element and was issue-bound at 4.0 TB/s.  Points beyond P
+// need no masking: their x reads as 0 and dz / y are the finite zero padding of the last tile.
+template <bool HAS_Y>
 __global__ void __launch_bounds__(256, 2)
 pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dzT,
                            const __nv_bfloat16* __restrict__ yT, const float* __restrict__ c1,
@@ -270,44 +374,48 @@ pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 8 * L1W_CH_PER_WARP) {
         const int c = min(blockIdx.y * 8 * L1W_CH_PER_WARP + (int)threadIdx.x, Cout - 1);
-        coef[threadIdx.x] = yT ? make_float4(__ldg(c1 + c), __ldg(c2 + c), __ldg(c3 + c), 0.f) : make_float4(1.f, 0.f, 0.f, 0.f);
+        coef[threadIdx.x] = HAS_Y ? make_float4(__ldg(c1 + c), __ldg(c2 + c), __ldg(c3 + c), 0.f) : make_float4(1.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     const int c0 = (blockIdx.y * 8 + warp) * L1W_CH_PER_WARP;
     if (c0 >= Cout) return;
-    float acc[L1W_CH_PER_WARP][4];
+    unsigned long long acc[L1W_CH_PER_WARP][4];
 #pragma unroll
     for (int k = 0; k < L1W_CH_PER_WARP; ++k)
 #pragma unroll
-        for (int f = 0; f < 4; ++f) acc[k][f] = 0.f;
+        for (int f = 0; f < 4; ++f) acc[k][f] = 0ull;
     const int64_t tile0 = (int64_t)blockIdx.x * L1_TILE_POINTS;
     for (int ch = 0; ch < L1_TILE_POINTS / 256; ++ch) {
         const int64_t p0 = tile0 + ch * 256 + lane * 8;
         if (p0 >= P) break;
-        // every global load of this step is issued before the first use (the kernel is latency bound)
+        // every global load of this step is issued before the first use
         uint4 rz[L1W_CH_PER_WARP], ry[L1W_CH_PER_WARP];
 #pragma unroll
         for (int k = 0; k < L1W_CH_PER_WARP; ++k) {
             const int64_t off = t256(p0, min(c0 + k, Cout - 1), Cout);
             rz[k] = __ldg(reinterpret_cast<const uint4*>(dzT + off));
-            if (yT) ry[k] = __ldg(reinterpret_cast<const uint4*>(yT + off));
+            if (HAS_Y) ry[k] = __ldg(reinterpret_cast<const uint4*>(yT + off));
         }
         float xv[4][8];
 #pragma unroll
         for (int f = 0; f < 4; ++f) load_x8(x, p0, P, TN, f, xv[f]);     // out-of-range points read as 0: they add nothing
-        const int vcnt = p0 + 8 <= P ? 8 : (int)(P - p0);
+        unsigned long long xp[4][4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xp[f][q] = pk2f(xv[f][2 * q], xv[f][2 * q + 1]);
 #pragma unroll
         for (int k = 0; k < L1W_CH_PER_WARP; ++k) {
             const float4 a = coef[warp * L1W_CH_PER_WARP + k];
-            float dz[8], yv[8];
-            unpack8(rz[k], dz);
-            if (yT) unpack8(ry[k], yv);
+            const unsigned long long a1 = pk2f(a.x, a.x), a2 = pk2f(a.y, a.y), a3 = pk2f(a.z, a.z);
+            const uint32_t* wz = reinterpret_cast<const uint32_t*>(&rz[k]);
+            const uint32_t* wy = reinterpret_cast<const uint32_t*>(&ry[k]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float d = yT ? fmaf(a.x, dz[j], fmaf(a.y, yv[j], a.z)) : dz[j];
-                d = j < vcnt ? d : 0.f;
+            for (int q = 0; q < 4; ++q) {
+                unsigned long long d = bf2_to_f2(wz[q]);
+                if (HAS_Y) d = fma2f(a1, d, fma2f(a2, bf2_to_f2(wy[q]), a3));
 #pragma unroll
-                for (int f = 0; f < 4; ++f) acc[k][f] = fmaf(d, xv[f][j], acc[k][f]);
+                for (int f = 0; f < 4; ++f) acc[k][f] = fma2f(d, xp[f][q], acc[k][f]);
             }
         }
     }
@@ -315,7 +423,9 @@ pointnet_l1_wgrad_t_kernel(const float* __restrict__ x, const __nv_bfloat16* __r
     for (int k = 0; k < L1W_CH_PER_WARP; ++k)
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-            const float t = warp_sum(acc[k][f]);
+            float lo, hi;
+            upk2f(acc[k][f], lo, hi);
+            const float t = warp_sum(lo + hi);
             if (lane == 0 && c0 + k < Cout) atomicAdd(dW + (c0 + k) * 4 + f, t);
         }
 }
@@ -912,7 +1022,7 @@ int pcaa_pointnet_l1_fwd_t(const float* x, const float* w, const float* bias, co
     PCAA_REQUIRE(((uintptr_t)yT & 15) == 0 && ((uintptr_t)w & 15) == 0 && Cout > 0, PCAA_ERR_ALIGN, "pointnet_l1_fwd_t: alignment / Cout");
     PCAA_REQUIRE((scale == nullptr) == (shift == nullptr), PCAA_ERR_SHAPE, "pointnet_l1_fwd_t: scale and shift go together");
     dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
-    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, nullptr, stats, P, TN, Cout);
+    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, stats, P, TN, Cout);
     return check_launch("pointnet_l1_fwd_t");
 }
 
@@ -924,7 +1034,7 @@ int pcaa_pointnet_l1_fwd_bn_t(const float* x, const float* w, const float* bias,
                  "pointnet_l1_fwd_bn_t: alignment / Cout");
     PCAA_REQUIRE(yT && aT && scale && shift, PCAA_ERR_SHAPE, "pointnet_l1_fwd_bn_t: needs both outputs and the BatchNorm coefficients");
     dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
-    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, (__nv_bfloat16*)aT, nullptr, P, TN, Cout);
+    pointnet_l1_fwd_bn_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, (__nv_bfloat16*)aT, P, TN, Cout);
     return check_launch("pointnet_l1_fwd_bn_t");
 }
 
@@ -957,7 +1067,10 @@ int pcaa_pointnet_l1_wgrad_t(const float* x, const void* dzT, const void* yT, co
     const int64_t P = B * TN;
     PCAA_REQUIRE(yT == nullptr || (c1 && c2 && c3), PCAA_ERR_SHAPE, "pointnet_l1_wgrad_t: y needs the BatchNorm-backward coefficients");
     dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1W_CH_PER_WARP));
-    pointnet_l1_wgrad_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, (const __nv_bfloat16*)dzT, (const __nv_bfloat16*)yT, c1, c2, c3, dW, P, TN, Cout);
+    if (yT != nullptr)
+        pointnet_l1_wgrad_t_kernel<true><<<grid, 256, 0, ST(stream)>>>(x, (const __nv_bfloat16*)dzT, (const __nv_bfloat16*)yT, c1, c2, c3, dW, P, TN, Cout);
+    else
+        pointnet_l1_wgrad_t_kernel<false><<<grid, 256, 0, ST(stream)>>>(x, (const __nv_bfloat16*)dzT, nullptr, c1, c2, c3, dW, P, TN, Cout);
     return check_launch("pointnet_l1_wgrad_t");
 }
 

@@ -112,7 +112,35 @@ class PeerExchange:
         self.peers = [(self.rank + k) % self.world for k in range(1, self.world)]
         self.streams = [torch.cuda.Stream(device=flat.device) for _ in self.peers]
         self.stage: Optional[torch.Tensor] = None
+        self.stage_small: Optional[torch.Tensor] = None
         self.bytes_pulled = 0
+
+    def all_reduce_small_(self, lo: int, hi: int) -> None:
+        """One-shot sum-all-reduce of a SMALL span (the critic's 4.5 k gradients): barrier, every rank copies every
+        rank's span (its own included) into a staging matrix whose rows are in RANK order, barrier (nobody may overwrite
+        its span while a peer still reads it), span = sum of the rows in that order -- all ranks compute bit-identical
+        sums.  Two barriers, w-1 small peer copies on their own streams, one tiny kernel; stream-ordered on the current
+        stream and capturable in a CUDA graph (no NCCL call, no host synchronisation)."""
+        from . import ops
+        n = hi - lo
+        if n <= 0:
+            return
+        if n % 4 or lo % 4:
+            raise ValueError("PeerExchange: spans must be multiples of 4 floats (16-byte copies)")
+        cur = torch.cuda.current_stream(self.flat.device)
+        if self.stage_small is None or self.stage_small.shape[1] < n:
+            self.stage_small = torch.empty((self.world, (n + 7) // 8 * 8), device=self.flat.device, dtype=torch.float32)
+        self.hdl.barrier(channel=0)
+        self.stage_small[self.rank, :n].copy_(self.flat[lo:hi])
+        for peer, st in zip(self.peers, self.streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                self.stage_small[peer, :n].copy_(self.hdl.get_buffer(peer, (n,), torch.float32, lo))
+            self.bytes_pulled += 4 * n
+        for st in self.streams:
+            cur.wait_stream(st)
+        self.hdl.barrier(channel=1)
+        ops.sum_rows(self.flat[lo:hi], self.stage_small[:, :n])
 
     def chunks(self, lo: int, hi: int) -> List[Tuple[int, int]]:
         n = hi - lo
@@ -155,7 +183,7 @@ class PeerExchange:
         self.hdl.barrier(channel=2)
 
 
-PEER_MIN = 1 << 20      # spans below 4 MB stay on NCCL (latency bound either way, and they overlap nothing)
+PEER_MIN = 1 << 20      # spans below 4 MB take the one-shot path (every rank pulls every rank's whole span): latency bound
 
 
 class GradExchange:
@@ -197,9 +225,13 @@ class GradExchange:
             ev.record()
             with torch.cuda.stream(self._stream):
                 self._stream.wait_event(ev)
-                if self.world > 1 and self.peer is not None and hi - lo >= PEER_MIN:
+                if self.world > 1 and self.peer is not None:
                     self.bytes_reduced += buf.numel() * buf.element_size()
-                    self.peer.all_reduce_(lo, hi)             # stream-ordered on the side stream: nothing to wait for
+                    # stream-ordered on the side stream: nothing to wait for
+                    if hi - lo >= PEER_MIN:
+                        self.peer.all_reduce_(lo, hi)
+                    else:
+                        self.peer.all_reduce_small_(lo, hi)
                 elif self.world > 1:
                     self.bytes_reduced += buf.numel() * buf.element_size()
                     w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -262,6 +294,22 @@ def _checksum(t: torch.Tensor) -> torch.Tensor:
     return torch.stack([v.sum(), (v * w).sum()])
 
 
+def per_tensor_relnorm(flat, a: torch.Tensor, b: torch.Tensor, floor: float = 1e-12):
+    """max over the tensors of a flat layout (train._Flat) of ||a_t - b_t|| / ||b_t||, and the name where it is reached;
+    tensors whose reference norm is below `floor` of the whole buffer's norm (identically-zero gradients) are skipped."""
+    worst, where = 0.0, ""
+    total = float(b.norm())
+    for name in flat.names:
+        ta, tb = flat.view(a, name), flat.view(b, name)
+        nb = float(tb.norm())
+        if nb <= floor * max(total, 1e-30):
+            continue
+        e = float((ta - tb).norm()) / nb
+        if e > worst:
+            worst, where = e, name
+    return worst, where
+
+
 @torch.no_grad()
 def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
     """Data-parallel parity of ONE iteration run the way the benchmark runs it (`trainer.step_graphed`: split CUDA graphs
@@ -271,11 +319,19 @@ def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
     Emulation (trainer built by `make_single()` with process_group=dp.SINGLE, stepped phase by phase from a snapshot of
     this trainer's state): pass A runs encoder forward + critic gradients on every rank's shard and sums the critic
     gradients; pass B repeats the forward per shard, installs the MEAN critic gradient (what the exchange + Adam give every
-    rank), runs the generator forward / backward and sums the generator gradients.  Expected:
-      rel_g, rel_d   ||g_dp - sum_shards g|| / ||sum_shards g||  (generator / critic flat gradients) ~ reduction-order noise
-      frac_p_off     fraction of generator weights that differ by > 2e-6 from Adam(snapshot, mean gradient)
-      replicas_identical   every rank holds bit-identical generator and critic weights after the iteration
-    Returns the dict (same on all ranks); `ok` is the verdict."""
+    rank), runs the generator forward / backward and sums the generator gradients; pass B is run TWICE, the deviation between
+    its two results is the run-to-run noise of the kernels themselves (atomically accumulated statistics and split-K sums
+    change the summation order, and a last-bit difference can flip the bf16 rounding of a stored activation).  Reported:
+      rel_g, rel_d   ||g_dp - sum_shards g|| / ||sum_shards g||  (generator / critic flat gradients)
+      worst_tensor   the same per parameter tensor, maximum (a wrong factor on a small tensor cannot hide in the flat norm)
+      noise_g, noise_tensor   the two emulation runs against each other: the floor the figures above are judged against
+      frac_p_off, max_dp     generator weights vs Adam(snapshot, mean gradient): fraction off by > 2e-6, largest deviation
+      replicas_identical     every rank holds bit-identical generator and critic weights after the iteration
+    Verdict `ok`: replicas identical, rel_g <= max(2e-3, 4 noise_g), worst_tensor <= max(2e-2, 8 noise_tensor) (a maximum over
+    ~100 tensors of a noise-limited quantity), rel_d <= 1e-3, max_dp <= 2.02 lr (an Adam step is at most ~lr; entries whose
+    gradient is noise may step the other way).  A wrong exchange (a missing rank, a wrong scale, a stale chunk) moves rel_g
+    and worst_tensor to O(1).
+    Returns the dict (same on all ranks)."""
     rank, world = world_info(group)
     dev = trainer.dev
     snap = trainer.snapshot()
@@ -299,18 +355,25 @@ def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
         phases, _ = ref._phases(*[g[r] for g in gathered])
         phases[0][1]()
         dsum += ref.D.g
-    gsum = torch.zeros_like(g_dp)
-    for r in range(world):                                             # pass B: generator gradients under the mean critic step
-        ref.restore(snap)
-        phases, _ = ref._phases(*[g[r] for g in gathered])
-        phases[0][1]()
-        ref.D.g.copy_(dsum / world)
-        for _, fn in phases[2:]:
-            fn()
-        gsum += ref.G.g
+    gsums = []
+    for _ in range(2):                                                 # pass B (twice): generator gradients under the mean critic step
+        gsum = torch.zeros_like(g_dp)
+        for r in range(world):
+            ref.restore(snap)
+            phases, _ = ref._phases(*[g[r] for g in gathered])
+            phases[0][1]()
+            ref.D.g.copy_(dsum / world)
+            for _, fn in phases[2:]:
+                fn()
+            gsum += ref.G.g
+        gsums.append(gsum)
     torch.cuda.synchronize(dev)
+    gsum = gsums[0]
     rel_g = float((g_dp - gsum).norm() / gsum.norm())
     rel_d = float((d_dp - dsum).norm() / dsum.norm())
+    noise_g = float((gsums[1] - gsum).norm() / gsum.norm())
+    worst_t, worst_name = per_tensor_relnorm(trainer.G, g_dp, gsum)
+    noise_t, _ = per_tensor_relnorm(trainer.G, gsums[1], gsum)
     # weights: Adam of the mean gradient from the snapshot, through the same fused kernel
     ref.restore(snap)
     ref.G.g.copy_(gsum / world)
@@ -319,7 +382,8 @@ def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
     b2_g = cfg.get("B2_G", cfg["B2"])
     ops.adam_advance(ref.G.step_dev, ref.G.coef_dev, cfg["LR"], cfg["B1"], b2_g)
     ops.adam_flat_dev(ref.G.p, ref.G.g, ref.G.m, ref.G.v, cfg["B1"], b2_g, 1e-8, ref.G.coef_dev, 1.0, ref.G.shadow)
-    frac_p_off = float(((trainer.G.p - ref.G.p).abs() > 2e-6).float().mean())
+    dp_abs = (trainer.G.p - ref.G.p).abs()
+    frac_p_off, max_dp = float((dp_abs > 2e-6).float().mean()), float(dp_abs.max())
     cs = torch.cat([_checksum(trainer.G.p), _checksum(trainer.D.p)])
     allcs = [torch.empty_like(cs) for _ in range(world)]
     if world > 1:
@@ -327,15 +391,18 @@ def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
     else:
         allcs = [cs]
     same = all(torch.equal(allcs[0], c) for c in allcs)
-    res = torch.tensor([rel_g, rel_d, frac_p_off], device=dev, dtype=torch.float64)
+    res = torch.tensor([rel_g, rel_d, frac_p_off, max_dp, noise_g, worst_t, noise_t], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(res, op=dist.ReduceOp.MAX, group=group)
-    rel_g, rel_d, frac_p_off = (float(x) for x in res)
+    rel_g, rel_d, frac_p_off, max_dp, noise_g, worst_t, noise_t = (float(x) for x in res)
     peer = getattr(trainer.G, "peer", None)
-    out = {"rel_g": rel_g, "rel_d": rel_d, "frac_p_off": frac_p_off, "replicas_identical": bool(same),
+    lr = float(cfg["LR"])
+    out = {"rel_g": rel_g, "rel_d": rel_d, "worst_tensor": worst_t, "worst_tensor_name": worst_name, "noise_g": noise_g,
+           "noise_tensor": noise_t, "frac_p_off": frac_p_off, "max_dp_over_lr": max_dp / lr, "replicas_identical": bool(same),
            "exchange": "peer" if peer is not None else ("nccl" if world > 1 else "none"), "world": world,
            "path": "step_graphed (split graphs)" if trainer.split_graphs else "step_graphed (one graph)",
-           "ok": bool(rel_g < 2e-3 and rel_d < 2e-3 and frac_p_off < 1e-2 and same)}
+           "ok": bool(same and rel_g <= max(2e-3, 4 * noise_g) and worst_t <= max(2e-2, 8 * noise_t) and rel_d <= 1e-3
+                      and max_dp <= 2.02 * lr)}
     del ref
     torch.cuda.empty_cache()
     return out

@@ -45,6 +45,36 @@ def _zeros_like_param(gradbuf, name, ref):
     return t
 
 
+class BnSync:
+    """SyncBN for data-parallel training: `reduce(t)` sums a statistics buffer over the ranks in place, `world`
+    scales the per-rank row counts.  With it every BatchNorm of the encoder normalises with GLOBAL-batch statistics, so an
+    N-rank iteration computes what one process would on the concatenated batch.  The reductions are NCCL all-reduces
+    issued between kernels (20 small ones per iteration): an eager-step option, not capturable in the step's CUDA graph."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.calls = 0
+
+    def reduce(self, t: torch.Tensor) -> torch.Tensor:
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        self.calls += 1
+        return t
+
+
+def _bn_bwd_coefs(st2, R, Rg, coef, dgamma_out, dbeta_out, bn: Optional[BnSync]):
+    """BatchNorm-backward coefficients c (for dy = c1*dz + c2*y + c3) and d gamma / d beta from the sums st2 = [sum dz,
+    sum dz*xhat] of THIS rank's rows.  SyncBN: d gamma / d beta stay the local sums (the gradient exchange adds the ranks'),
+    while c uses the sums and the row count of all ranks (the statistics couple every row of the global batch)."""
+    if bn is None:
+        return ops.bn_bwd_finalize(st2, R, coef, dgamma_out, dbeta_out)
+    _, dgam, dbet = ops.bn_bwd_finalize(st2, R, coef, dgamma_out, dbeta_out)
+    bn.reduce(st2)
+    c, _, _ = ops.bn_bwd_finalize(st2, Rg, coef)
+    return c, dgam, dbet
+
+
 def _stats_arena(sizes, device):
     """One zero-filled double buffer for several [2*C] BatchNorm statistics accumulators (one fill instead of one each)."""
     buf = torch.zeros(2 * sum(sizes), device=device, dtype=torch.float64)
@@ -61,7 +91,8 @@ def _conv_w(P: Params, pre: str, l: int):
     return W.view(W.shape[0], W.shape[1])
 
 
-def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_block.", wb16: Optional[dict] = None):
+def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_block.", wb16: Optional[dict] = None,
+                     bn: Optional[BnSync] = None):
     """x (B,4,T,N) fp32 -> pooled [B*T, 1024] fp32 (mean over the N points of ELU(BN(conv))), saved state.
 
     Activations are channel-major bf16 in 256-point tiles (T256 ``[tiles, C, 256]``): the tcgen05 GEMM of layer l
@@ -70,12 +101,15 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
     layer number to a ready bf16 copy of the [Cout, Cin] weight (the trainer's Adam-maintained shadow)."""
     B, F, T, N = x.shape
     R = B * T * N
-    sv = {"x": x, "N": N, "R": R, "G": B * T, "y": [None] * 5, "a": [None] * 5, "coef": [None] * 5, "wb": [None] * 5}
+    Rg = R * (bn.world if bn is not None else 1)          # rows behind the statistics (SyncBN: of all ranks)
+    sv = {"x": x, "N": N, "R": R, "Rg": Rg, "G": B * T, "y": [None] * 5, "a": [None] * 5, "coef": [None] * 5, "wb": [None] * 5}
 
     def bn_coef(l, stats):
         k = f"{pre}pointnet{l}.module.1."
         if training:
-            return ops.bn_finalize(stats, R, P[k + "weight"], P[k + "bias"], P[k + "running_mean"], P[k + "running_var"],
+            if bn is not None:
+                bn.reduce(stats)
+            return ops.bn_finalize(stats, Rg, P[k + "weight"], P[k + "bias"], P[k + "running_mean"], P[k + "running_var"],
                                    BN_MOMENTUM, BN_EPS)
         return ops.bn_eval_coeffs(P[k + "weight"], P[k + "bias"], P[k + "running_mean"], P[k + "running_var"], BN_EPS)
 
@@ -85,7 +119,10 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
         # (14 numbers), so the coefficients exist BEFORE y1 does and one pass writes y1 and a1 = ELU(BN(y1)) -- y1 is not
         # re-read for the activation (-2.4 GB of HBM traffic at B = 256)
         k1 = f"{pre}pointnet1.module.1."
-        coef = ops.bn_from_input_moments(ops.input_moments(x), R, _conv_w(P, pre, 1), b1, P[k1 + "weight"], P[k1 + "bias"],
+        mom = ops.input_moments(x)
+        if bn is not None:
+            bn.reduce(mom)
+        coef = ops.bn_from_input_moments(mom, Rg, _conv_w(P, pre, 1), b1, P[k1 + "weight"], P[k1 + "bias"],
                                          P[k1 + "running_mean"], P[k1 + "running_var"], BN_MOMENTUM, BN_EPS)
         y, a = ops.pointnet_l1_fwd_bn_t(x, _conv_w(P, pre, 1), b1, coef)
         sv["y"][1], sv["coef"][1], sv["a"][1] = y, coef, a
@@ -120,21 +157,23 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
 
 
 def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = None,
-                      pre: str = "pc_block.", side: Optional[torch.cuda.Stream] = None) -> Grads:
+                      pre: str = "pc_block.", side: Optional[torch.cuda.Stream] = None, bn: Optional[BnSync] = None) -> Grads:
     """gpool [B*T, 1024] fp32 = d loss / d pooled.  Returns parameter gradients (written into gradbuf when given).
 
     With a `side` stream the weight-gradient GEMM of layer l (tensor bound, reads dy_l and a_{l-1}) runs there while the
     current stream goes on with the data gradient's successor, the HBM-bound BatchNorm-backward pass of layer l-1: the
     two are independent and have complementary bottlenecks.  The current stream waits for `side` before returning."""
     G: Grads = {}
-    R, N = sv["R"], sv["N"]
+    R, N, Rg = sv["R"], sv["N"], sv["Rg"]
+    if (bn is not None) != (Rg != R):
+        raise RuntimeError("pointnet_backward: SyncBN must be used in both the forward and the backward")
     gpool = gpool.contiguous()
     main = torch.cuda.current_stream()
     # layer 4: the BatchNorm-backward statistics follow from the forward's group sums (no pass over y4), then ONE pass
     # forms dy4 = BN'(ELU'(pool'(gpool)))
     st2 = ops.pool_bwd_stats(gpool, sv["e1"], sv["e2"], N)
     kb = f"{pre}pointnet4.module.1."
-    c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][4], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
+    c, dgam, dbet = _bn_bwd_coefs(st2, R, Rg, sv["coef"][4], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"), bn)
     G[kb + "weight"], G[kb + "bias"] = dgam, dbet
     dy = ops.pool_bwd_apply_t(gpool, sv["y"][4], sv["coef"][4], c, N)
     arena = dict(zip((4, 3, 2), _stats_arena([P[f"{pre}pointnet{l}.module.0.weight"].shape[1] for l in (4, 3, 2)], gpool.device)))
@@ -162,7 +201,7 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
         dz = ops.gemm_tc(sv["wb"][l], dy, TC_T_DGRAD_ELUBN, Cin, R, Cout, a_mn=OP_MN, b_mn=OP_T256_MN, stats=st2,
                          yprev=sv["y"][l - 1], coef=sv["coef"][l - 1])
         kb = f"{pre}pointnet{l - 1}.module.1."
-        c, dgam, dbet = ops.bn_bwd_finalize(st2, R, sv["coef"][l - 1], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"))
+        c, dgam, dbet = _bn_bwd_coefs(st2, R, Rg, sv["coef"][l - 1], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"), bn)
         G[kb + "weight"], G[kb + "bias"] = dgam, dbet
         if l > 2:
             dy = ops.bn_bwd_apply_t(dz, sv["y"][l - 1], c, R, out=dz)
@@ -185,7 +224,8 @@ def _tcn_bn(P: Params, k: str):
     return (P[k + "batch_norm.weight"], P[k + "batch_norm.bias"], P[k + "batch_norm.running_mean"], P[k + "batch_norm.running_var"])
 
 
-def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block.", wb16: Optional[dict] = None):
+def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block.", wb16: Optional[dict] = None,
+                bn: Optional[BnSync] = None):
     """h [B, T, 1024] fp32 -> [B, T, 512]; causal dilated conv (bf16 im2col operand + tcgen05 GEMM, fp32 accumulate /
     output) + BatchNorm1d + ELU, six times.  ``wb16`` optionally maps the layer number to a ready bf16 copy of the
     [Cout, Cin*3] weight (the trainer's Adam-maintained shadow).
@@ -195,9 +235,10 @@ def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block
     im2col operand (the last layer writes the fp32 activation)."""
     B, T, _ = h.shape
     R = B * T
-    sv = {"B": B, "T": T, "col": [], "y": [], "coef": [], "cin": [], "wb": []}
-    if not TCN_FUSED:
-        return _tcn_forward_unfused(h, P, training, pre, wb16, sv)
+    sv = {"B": B, "T": T, "col": [], "y": [], "coef": [], "cin": [], "wb": [], "sync": bn is not None}
+    if not TCN_FUSED or (bn is not None and training):
+        # SyncBN: the statistics are all-reduced between the statistics kernel and the coefficient kernel of every layer
+        return _tcn_forward_unfused(h, P, training, pre, wb16, sv, bn)
     chans = [P[f"{pre}dtc{l}.conv1d.weight"].shape[0] for l in range(1, 7)]
     arena = _stats_arena(chans, h.device) if training else [None] * 6
     col = ops.tcn_im2col(h, DTC_DILATIONS[0], torch.bfloat16)
@@ -224,9 +265,10 @@ def tcn_forward(h: torch.Tensor, P: Params, training: bool, pre: str = "tc_block
     return act.view(B, T, -1), sv
 
 
-def _tcn_forward_unfused(h, P, training, pre, wb16, sv):
+def _tcn_forward_unfused(h, P, training, pre, wb16, sv, bn=None):
     B, T, _ = h.shape
     R = B * T
+    Rg = R * (bn.world if bn is not None else 1)
     for l in range(1, 7):
         k = f"{pre}dtc{l}."
         W = P[k + "conv1d.weight"]
@@ -236,7 +278,9 @@ def _tcn_forward_unfused(h, P, training, pre, wb16, sv):
         y = ops.gemm_tc(col, wb, TC_PLAIN, R, Cout, Cin * 3, bias=P[k + "conv1d.bias"], out_dtype=torch.float32)
         if training:
             st = ops.colstats(y)
-            coef = ops.bn_finalize(st, R, *_tcn_bn(P, k), BN_MOMENTUM, BN_EPS)
+            if bn is not None:
+                bn.reduce(st)
+            coef = ops.bn_finalize(st, Rg, *_tcn_bn(P, k), BN_MOMENTUM, BN_EPS)
         else:
             coef = ops.bn_eval_coeffs(*_tcn_bn(P, k), BN_EPS)
         a = ops.bn_elu_apply(y, coef[0], coef[1])
@@ -246,7 +290,7 @@ def _tcn_forward_unfused(h, P, training, pre, wb16, sv):
 
 
 def tcn_backward(dout: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = None, pre: str = "tc_block.",
-                 dout_is_frame_mean: bool = False):
+                 dout_is_frame_mean: bool = False, bn: Optional[BnSync] = None):
     """dout [B, T, 512] (or, with dout_is_frame_mean, the gradient [B, 512] of the mean over the T frames, whose broadcast
     is then formed inside the first kernel) -> (d input [B, T, 1024], parameter gradients).
 
@@ -256,10 +300,12 @@ def tcn_backward(dout: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = N
     G: Grads = {}
     B, T = sv["B"], sv["T"]
     R = B * T
-    if not TCN_FUSED:
+    if (bn is not None) != sv.get("sync", False):
+        raise RuntimeError("tcn_backward: SyncBN must be used in both the forward and the backward")
+    if not TCN_FUSED or bn is not None:
         if dout_is_frame_mean:
             dout = ops.mean_rows_bwd(dout, T)
-        return _tcn_backward_unfused(dout, sv, P, gradbuf, pre)
+        return _tcn_backward_unfused(dout, sv, P, gradbuf, pre, bn)
     chans = [P[f"{pre}dtc{l}.conv1d.weight"].shape[0] for l in range(1, 7)]
     arena = _stats_arena(chans, dout.device)
     src, mode, dil_up = dout.reshape(-1, dout.shape[-1]).contiguous(), (2 if dout_is_frame_mean else 0), 0
@@ -286,10 +332,11 @@ def tcn_backward(dout: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = N
     return d.view(B, T, -1), G
 
 
-def _tcn_backward_unfused(dout, sv, P, gradbuf, pre):
+def _tcn_backward_unfused(dout, sv, P, gradbuf, pre, bn=None):
     G: Grads = {}
     B, T = sv["B"], sv["T"]
     R = B * T
+    Rg = R * (bn.world if bn is not None else 1)
     d = dout.reshape(R, -1)
     for l in range(6, 0, -1):
         k = f"{pre}dtc{l}."
@@ -297,8 +344,7 @@ def _tcn_backward_unfused(dout, sv, P, gradbuf, pre):
         Cout, Cin, _ = W.shape
         y, coef, col, wb = sv["y"][l - 1], sv["coef"][l - 1], sv["col"][l - 1], sv["wb"][l - 1]
         dz, st2 = ops.elu_bwd_colstats(d, y, coef)
-        c, dgam, dbet = ops.bn_bwd_finalize(st2, R, coef, _out(gradbuf, k + "batch_norm.weight"),
-                                            _out(gradbuf, k + "batch_norm.bias"))
+        c, dgam, dbet = _bn_bwd_coefs(st2, R, Rg, coef, _out(gradbuf, k + "batch_norm.weight"), _out(gradbuf, k + "batch_norm.bias"), bn)
         G[k + "batch_norm.weight"], G[k + "batch_norm.bias"] = dgam, dbet
         dy = ops.bn_bwd_apply(dz, y, c, out_dtype=torch.bfloat16)
         dW = _zeros_like_param(gradbuf, k + "conv1d.weight", W)
@@ -361,21 +407,21 @@ def heads_backward(dlogits: Optional[torch.Tensor], dfv_ext: Optional[torch.Tens
 
 # ====================================================================================================== encoder
 def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_head: bool, wb16: Optional[dict] = None,
-                    tcn_wb16: Optional[dict] = None):
+                    tcn_wb16: Optional[dict] = None, bn: Optional[BnSync] = None):
     B, F, T, N = x.shape
-    pooled, sv_p = pointnet_forward(x, P, training, wb16=wb16)
-    h6, sv_t = tcn_forward(pooled.view(B, T, -1), P, training, wb16=tcn_wb16)
+    pooled, sv_p = pointnet_forward(x, P, training, wb16=wb16, bn=bn if training else None)
+    h6, sv_t = tcn_forward(pooled.view(B, T, -1), P, training, wb16=tcn_wb16, bn=bn if training else None)
     logits, fv, sv_h = heads_forward(h6, P, use_projection_head)
     return logits, fv, (sv_p, sv_t, sv_h)
 
 
 def encoder_backward(dlogits, dfv, saved, P: Params, gradbuf: Optional[Grads] = None,
-                     side: Optional[torch.cuda.Stream] = None) -> Grads:
+                     side: Optional[torch.cuda.Stream] = None, bn: Optional[BnSync] = None) -> Grads:
     sv_p, sv_t, sv_h = saved
     dg, G = heads_backward(dlogits, dfv, sv_h, P, gradbuf)
-    dpool, Gt = tcn_backward(dg, sv_t, P, gradbuf, dout_is_frame_mean=True)
+    dpool, Gt = tcn_backward(dg, sv_t, P, gradbuf, dout_is_frame_mean=True, bn=bn)
     G.update(Gt)
-    G.update(pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf, side=side))
+    G.update(pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf, side=side, bn=bn))
     return G
 
 

@@ -559,6 +559,12 @@ def sum_into(dst: torch.Tensor, src: torch.Tensor) -> None:
     call("pcaa_sum_into", _p(dst), _p(src), dst.numel(), src.stride(0), src.shape[0], _s())
 
 
+def sum_rows(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst[i] = sum_k src[k, i] in row order (overwrite; dst fp32 [n], src fp32 [nsrc, >= n] rows with a common stride)."""
+    _chk(dst, torch.float32), _chk(src, torch.float32, contiguous=False)
+    call("pcaa_sum_rows", _p(dst), _p(src), dst.numel(), src.stride(0), src.shape[0], _s())
+
+
 def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[r] = src[idx[r]] along dim 0 (idx int64 on the device); rows must be multiples of 16 bytes."""
     _chk(src), _chk(idx, torch.int64)

@@ -102,7 +102,7 @@ class PCAATrainer:
     """
 
     def __init__(self, encoder, decoder, discriminator, decoder_projection_head, means: torch.Tensor, config: dict,
-                 process_group=None, mean_learner=None, discriminator_projection_head=None):
+                 process_group=None, mean_learner=None, discriminator_projection_head=None, sync_bn: bool = False):
         if decoder is None and decoder_projection_head is not None:
             raise ValueError("PCAATrainer: a decoder projection head needs a decoder")
         self.enc, self.dec, self.dis, self.gph = encoder, decoder, discriminator, decoder_projection_head
@@ -131,7 +131,7 @@ class PCAATrainer:
         if decoder is not None:
             named += [("G." + k, p) for k, p in decoder.named_parameters() if k.startswith("dense")]
         self.G = _Flat(named, dev, process_group, exchanged=True, pad_rows=lambda n, t: n.startswith("G.dense"))
-        self.D = _Flat([("D." + k, p) for k, p in discriminator.named_parameters()], dev)
+        self.D = _Flat([("D." + k, p) for k, p in discriminator.named_parameters()], dev, process_group, exchanged=True)
         dec_names = [n for n in self.G.names if n.startswith("G.") or n.startswith("GPH.")]
         self._dec_span = self.G.span(dec_names) if dec_names else None
         self._enc_span = self.G.span([n for n in self.G.names if n.startswith("E.")])
@@ -148,7 +148,15 @@ class PCAATrainer:
         self._refresh_views()
         # gradient exchange (dp.py): decoder-side span first (overlaps the encoder backward), then the encoder span
         self.xG = dp.GradExchange(self.G.g, process_group, side_stream=True, peer=self.G.peer)
-        self.xD = dp.GradExchange(self.D.g, process_group)
+        self.xD = dp.GradExchange(self.D.g, process_group, peer=self.D.peer)
+        # sync_bn: every encoder BatchNorm normalises with the statistics of the GLOBAL batch (all-reduced sums), so
+        # N ranks compute what one process would on the concatenated batch; default is per-rank statistics (torch-DDP
+        # semantics).  Eager `step` only: the reductions are NCCL calls between kernels.
+        self.bn_sync = None
+        if sync_bn and self.world > 1:
+            if mean_learner is not None:
+                raise NotImplementedError("sync_bn: the variant-1 mean learner's BatchNorm is not synchronised")
+            self.bn_sync = engine.BnSync(None if isinstance(process_group, str) else process_group)
         self._one = torch.ones((), device=dev, dtype=torch.float32)
         self._zero_means = torch.zeros_like(self.means)
         # PCAA_WGRAD_OVERLAP=1 runs the PointNet weight-gradient GEMMs on their own stream, concurrently with the
@@ -163,7 +171,12 @@ class PCAATrainer:
         self._phase_events: List = []
         # data-parallel: never capture a collective (kernel phases -> graphs, exchanges eager in between);
         # PCAA_SPLIT_GRAPHS=1 forces that program structure on one rank (tests)
-        self.split_graphs = self.world > 1 or os.environ.get("PCAA_SPLIT_GRAPHS", "0") == "1"
+        # With the copy-engine exchange on BOTH gradient buffers the data-parallel step contains no NCCL call: it can be
+        # captured as ONE graph like the single-rank step (cross-rank ordering = the symmetric-memory barriers inside it).
+        # PCAA_DP_ONE_GRAPH=0 keeps the four-graph structure; any NCCL exchange forces it.
+        all_peer = self.G.peer is not None and self.D.peer is not None
+        one_graph = all_peer and os.environ.get("PCAA_DP_ONE_GRAPH", "0") == "1"
+        self.split_graphs = (self.world > 1 and not one_graph) or os.environ.get("PCAA_SPLIT_GRAPHS", "0") == "1"
 
     def _refresh_views(self):
         enc_t = {k: v for k, v in self.enc.named_parameters()}
@@ -223,7 +236,7 @@ class PCAATrainer:
                 self.dec.train()
             # encoder forward (train-mode BatchNorm; running statistics updated in place)
             st["logits"], st["fv"], st["saved"] = engine.encoder_forward(pcs, self.P_E, True, self.enc.use_projection_head,
-                                                                         self._enc_wb16, self._tcn_wb16)
+                                                                         self._enc_wb16, self._tcn_wb16, bn=self.bn_sync)
             torch._foreach_add_(self._nbt, 1)
             # critic step (PCAA_ablation.py:900-980): one fused kernel forms d_loss and its parameter gradients
             self.D.g.zero_()
@@ -280,7 +293,8 @@ class PCAATrainer:
 
         def encoder_backward():
             self.G.g[self._enc_span[0]:self._enc_span[1]].zero_()     # one fill instead of one per accumulated gradient
-            engine.encoder_backward(st["dlogits"], st["dfv"], st["saved"], self.P_E, self.gb_E, side=self._wgrad_stream)
+            engine.encoder_backward(st["dlogits"], st["dfv"], st["saved"], self.P_E, self.gb_E, side=self._wgrad_stream,
+                                    bn=self.bn_sync)
 
         def exchange_encoder_span():
             self.xG.start(*self._enc_span)
@@ -329,6 +343,8 @@ class PCAATrainer:
         second one captures; every call performs exactly one training iteration.  Inputs are copied into the graphs'
         static buffers unless they already are those buffers (`static_inputs`).  The returned tensors are graph-owned:
         read them before the next call."""
+        if self.bn_sync is not None:
+            return self.step(pcs, gt, z0, alphas, supervised)      # SyncBN's reductions are NCCL calls: not capturable
         if not supervised and not self._cls_diverged:
             self._cls_diverged = True
             self.set_cls_step(self.G._step)
@@ -654,7 +670,7 @@ def build_variant(variant: int, n_classes: int, nmax: int, config: Optional[dict
 
 
 def build_variant4(n_classes: int, nmax: int, config: Optional[dict] = None, device="cuda", seed: Optional[int] = None,
-                   process_group=None):
+                   process_group=None, sync_bn: bool = False):
     """Construct the variant-4 networks exactly as PCAA_ablation.py:764-786 does and wrap them in a PCAATrainer."""
     from . import models, utils
     if seed is not None:
@@ -668,4 +684,4 @@ def build_variant4(n_classes: int, nmax: int, config: Optional[dict] = None, dev
     gph = torch.nn.Sequential(torch.nn.Linear(cfg["SUP_LATENT_DIM"], cfg["SUP_LATENT_DIM"] * 2), torch.nn.ELU()).to(device).float()
     dph = torch.nn.Sequential(torch.nn.Linear(cfg["SUP_LATENT_DIM"] * 2, cfg["SUP_LATENT_DIM"]), torch.nn.ELU()).to(device).float()
     means = utils.sample_distant_points(cfg["SUP_LATENT_DIM"], n_classes, 10, 10).float()
-    return PCAATrainer(enc, dec, dis, gph, means, cfg, process_group, discriminator_projection_head=dph)
+    return PCAATrainer(enc, dec, dis, gph, means, cfg, process_group, discriminator_projection_head=dph, sync_bn=sync_bn)

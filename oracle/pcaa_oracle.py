@@ -506,11 +506,14 @@ def f1_scores(labels: np.ndarray, preds: np.ndarray) -> Dict[str, float]:
 
 
 def naive_sequential_procedure(k: int, test_emb, test_pred, test_labels, unseen_emb, unseen_pred, unseen_labels, means,
-                               seed: int = 0, unseen_valid_ratio: float = 0.2):
+                               seed: int = 0, unseen_valid_ratio: float = 0.2, vote_test_emb=None, vote_unseen_emb=None):
     """inference_PCAA.py:117-347 restated on per-crop embeddings / class predictions (the eval-mode encoder gives the
     same embedding for a crop whether it is encoded alone (phase 1) or inside a batch of k (phase 2)).
 
     test_* : the TEST split in `sequential=True` order; unseen_* : the UNSEEN split (labels = unseen subject ids).
+    vote_*_emb (optional): the embeddings of the SECOND encoding pass (batches of k, :251, :290) when they are available
+    separately -- the threshold is searched on the first pass (:195-231), the votes use the second (:255-263); the two can
+    differ in the last bits (batch-1 vs batch-k arithmetic).
     Returns dict(threshold, preds, labels, val_subjects, metrics)."""
     rng = np.random.default_rng(seed)                                             # :127
     test_labels, unseen_labels = np.asarray(test_labels), np.asarray(unseen_labels)
@@ -523,6 +526,10 @@ def naive_sequential_procedure(k: int, test_emb, test_pred, test_labels, unseen_
     det = np.concatenate([np.zeros(int(is_val.sum())), np.ones(len(lik_test))])
     thr = roc_youden_threshold(det, scores)                                       # :230-231
     n_labels = len(np.unique(test_labels))                                        # :237
+    if vote_test_emb is not None:
+        lik_test = joint_likelihood(vote_test_emb, means)                         # :255-257
+    if vote_unseen_emb is not None:
+        lik_unseen = joint_likelihood(vote_unseen_emb, means)                     # :293-295
     preds, labels = [], []
     test_pred, unseen_pred = np.asarray(test_pred), np.asarray(unseen_pred)
     for w in range(len(test_labels) // k):                                        # :241, DataLoader(batch_size=k, drop_last=True)

@@ -106,6 +106,15 @@ def main():
 
     wandb.init = init_and_tap
 
+    # every eval-mode encoder call of the inference procedure, in order: (logits, embedding) -- what the labels are made of
+    captured = []
+
+    def tap_encoder(mod, inputs, output):
+        if type(mod).__name__ == "CGEncoder" and not mod.training:
+            captured.append((output[0].detach().float().cpu().numpy().tolist(), output[1].detach().float().cpu().numpy().tolist()))
+
+    torch.nn.modules.module.register_module_forward_hook(tap_encoder)
+
     cfg = constants.CONFIG
     ks = [int(x) for x in args.ks.split(",") if x]
     result = {"impl": args.impl, "device": device, "workdir": workdir, "runs": []}
@@ -133,9 +142,15 @@ def main():
             rec["files"] = sorted(os.listdir(os.path.join("models", model_name)))
         if not args.skip_infer:
             t0 = time.time()
+            del captured[:]
             inference_PCAA.CGAAE_inference(model_names=[model_name], ks=ks_run, variation=inference_PCAA.VARIATION.V4)
             rec["infer_s"] = time.time() - t0
             rec["inference"] = {}
+            # the crops the procedure walked (sequential=True order) and everything its encoder returned
+            rec["test_labels"] = [int(v) for v in datasets.MSRadarDataset(constants.SPLIT.TEST, sequential=True).labels]
+            rec["unseen_labels"] = [int(v) for v in datasets.MSRadarDataset(constants.SPLIT.UNSEEN, sequential=True).labels]
+            rec["means"] = torch.load(os.path.join("models", model_name, "discriminator_means.pt")).float().cpu().numpy().tolist()
+            rec["encoder_calls"] = list(captured)
             for k in ks_run:
                 with open(os.path.join("models", model_name, f"naive_seq_log_{k}.json")) as f:
                     lg = json.load(f)
@@ -159,7 +174,7 @@ def main():
     if args.out:
         with open(args.out, "w") as f:
             f.write(out)
-    print("RESULT " + out[:2000])
+    print("RESULT " + out[:1500])
 
 
 if __name__ == "__main__":

@@ -24,7 +24,24 @@ def test_dp_parity_two_ranks(exchange):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "scripts", "dp_parity.py")],
                        capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    print("\n".join(l for l in r.stdout.splitlines() if l.startswith("dp_parity")))
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
-    line = [l for l in r.stdout.splitlines() if l.startswith("dp_parity")][-1]
+    line = [l for l in r.stdout.splitlines() if l.startswith("dp_parity world")][-1]
     assert line.endswith("-> OK"), line
     assert ("peer copies" in line) == (exchange == "peer"), line
+
+
+@pytest.mark.gpu
+def test_syncbn_two_ranks_equal_one_process_on_the_global_batch():
+    """PCAATrainer(sync_bn=True): BatchNorm statistics all-reduced over the ranks -> the 2-rank iteration is the
+    single-process iteration of the concatenated batch (gradients, running statistics, losses)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = 29900 + (os.getpid() % 90)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "scripts", "dp_parity.py"), "--sync-bn"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    print("\n".join(l for l in r.stdout.splitlines() if l.startswith("dp_parity")))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("dp_parity syncbn")][-1]
+    assert line.endswith("-> OK"), line

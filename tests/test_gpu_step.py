@@ -6,11 +6,16 @@ reference is fp32 throughout, so:
   embeddings / logits      : 3e-2 of max |ref|
   losses                   : 2e-2 relative
   decoder output           : 1e-2 of max |ref| (bf16 weights / activations on the tensor cores, fp32 accumulation)
-  gradients (per tensor)   : ||g - g_ref|| / ||g_ref|| <= 1e-1 (encoder: four bf16 BatchNorm layers deep), 4e-2 (decoder)
+  gradients (per tensor)   : ||g - g_ref|| / ||g_ref|| <= 1e-1 (encoder) / 4e-2 (decoder) at these B = 2..8 golden cases
+                             (measured 0.05-0.07; tests/test_gpu_baseline_sizes.py holds 6e-2 at B >= 16, measured 0.039-0.054).
+                             scripts/sim_bf16_rounding.py reproduces the magnitude on the CPU from the bf16 STORAGE roundings
+                             alone (weights, y_l, a_l, TCN operands: ~2 % each, 3-4.5 % together with this loss, whose gradient
+                             at the embedding is largely common to the batch and is projected out by the BatchNorm backward);
+                             the direction is checked separately: sign agreement >= 99 % on entries with |g_ref| > 10 % of max
   BatchNorm running stats  : 2e-2 of max |ref|
-  post-Adam weights        : every entry within 2*lr*steps (Adam's first steps are ~lr*sign(g); entries whose gradient
-                             is rounding noise may take the other sign), at most 10 % of the entries off by > 5e-6 (entries with
-                             |g| below the ~4 % bf16-path gradient error have an undetermined sign: ~3-5 % of a Gaussian)
+  post-Adam weights        : every entry within 2*lr*steps of the oracle's (an Adam step is at most ~lr); after the FIRST
+                             iteration every entry whose reference gradient is large (> 10 % of the tensor's max) has moved
+                             by -lr*sign(g_ref) within 1 % of lr -- direction and step size of the update, not just its bound
   class predictions        : exact, except samples whose top-2 logit gap is below the logit tolerance (listed)
 Conv biases that feed a train-mode BatchNorm have an identically-zero gradient; the reference computes fp32 noise
 there (~1e-9) -- excluded from gradient parity (oracle/gen_golden.py, bn_cancelled_bias).
@@ -138,6 +143,7 @@ def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
     tr = PCAATrainer(enc, dec, dis, gph, means, dict(CFG, B2_G=CFG["B1"]) if variant == 3 else CFG, mean_learner=ml)
     ost = {}
     rng = np.random.default_rng(999 + seed)
+    p_start = {n: tr.G.view(tr.G.p, n).clone() for n in tr.G.names}
     for s in range(nsteps):
         pcs, gt = O.synth_batch(B, nmax, C, seed=4321 + 10 * seed + s)
         z0 = torch.from_numpy(rng.normal(0, 1, (B, 32))).float()
@@ -172,9 +178,17 @@ def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
                 g = flat.view(flat.g, n)
                 tol = 1e-1 if n.startswith("E.") or n.startswith("D.") else 4e-2
                 assert relnorm(g, g_ref) < tol, (s, n, relnorm(g, g_ref))
+                if float(g_ref.abs().max()) == 0.0:
+                    continue
+                big = g_ref.abs() > 0.1 * g_ref.abs().max()
+                assert float((torch.sign(g.cpu())[big] == torch.sign(g_ref)[big]).float().mean()) >= 0.99, (s, n)
+                if flat is tr.G:
+                    # the first Adam update itself: -lr * sign(g) (bias-corrected m / sqrt(v) = sign at step 1), on those entries
+                    moved = (flat.view(flat.p, n) - p_start[n]).cpu()
+                    want = -CFG["LR"] * torch.sign(g_ref)
+                    assert float(((moved - want).abs()[big] <= 1e-2 * CFG["LR"] + 1e-9).float().mean()) >= 0.99, (s, n)
     # weights after the Adam updates
     lr = CFG["LR"]
-    nbad = ntot = 0
     for pre, m in (("E.", enc), ("G.", dec), ("D.", dis), ("GPH.", gph), ("ML.", ml)):
         for k, v in (m.state_dict().items() if m is not None else ()):
             if not v.dtype.is_floating_point:
@@ -185,10 +199,6 @@ def test_fused_train_step_vs_oracle_and_golden(golden_dir, name):
                 assert float(d.max()) <= 2e-2 * float(po[pre + k].abs().max()), k
                 continue
             assert float(d.max()) <= 2 * lr * nsteps * 1.01, (k, float(d.max()))
-            if not bn_cancelled_bias(k):
-                nbad += int((d > 5e-6).sum())
-                ntot += d.numel()
-    assert nbad / ntot < 0.10, nbad / ntot
 
 
 @pytest.mark.parametrize("split", [False, True])
