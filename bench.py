@@ -521,7 +521,7 @@ def run_b200(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
         peer = trainer.G.peer
-        exchange = {"mode": "peer (copy engines over NVLink symmetric memory) + NCCL for spans < 4 MB" if peer is not None else "nccl",
+        exchange = {"mode": "peer (copy engines over NVLink symmetric memory: chunked reduce-scatter / all-gather, one-shot for spans < 4 MB)" if peer is not None else "nccl",
                     "bytes_reduced_per_step": trainer.xG.bytes_reduced / max(1, trainer.G.step),
                     "bytes_pulled_per_step": (peer.bytes_pulled / max(1, trainer.G.step)) if peer is not None else 0}
 
@@ -588,7 +588,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic("train", B, NMAX),
-                     "traffic_source": "profiles/traffic.json (ncu --set full capture of this command; scripts/ncu_traffic.py)",
+                     "traffic_source": "profiles/traffic.json (regenerated from an ncu --set full capture of this command by scripts/roofline_table.py --write-traffic)",
                      "kernel": "gemm_tc_kernel (tcgen05 PointNet fwd/dgrad/wgrad GEMMs)",
                      "launches_timed": len(tc_events), "share_of_step": tc_ms / (ms_eager * tc_steps) if tc_events else None,
                      "timed_in": ("eager pass after the timed region (CUDA events around each launch; %.3f ms/step eager)" % ms_eager)

@@ -169,7 +169,7 @@ struct L1Coef2 { float2 w[4]; float2 bias, scale, shift, scale_l2, shift_l2; }; 
 
 __device__ __forceinline__ unsigned long long f2u(float2 v) { return pk2f(v.x, v.y); }
 
-template <bool FULL>
+template <bool FULL, bool BOTH>
 __device__ __forceinline__ void l1_bn_channel(const L1Coef2& c, const unsigned long long (&x)[4][4], int vcnt,
                                               __nv_bfloat16* __restrict__ yp, __nv_bfloat16* __restrict__ ap) {
     const unsigned long long w0 = f2u(c.w[0]), w1 = f2u(c.w[1]), w2 = f2u(c.w[2]), w3 = f2u(c.w[3]), b = f2u(c.bias);
@@ -201,13 +201,15 @@ __device__ __forceinline__ void l1_bn_channel(const L1Coef2& c, const unsigned l
             alo = 2 * q < vcnt ? alo : 0.f;
             ahi = 2 * q + 1 < vcnt ? ahi : 0.f;
         }
-        yh[q] = __floats2bfloat162_rn(ylo, yhi);
+        if (BOTH) yh[q] = __floats2bfloat162_rn(ylo, yhi);
         ah[q] = __floats2bfloat162_rn(alo, ahi);
     }
-    *reinterpret_cast<uint4*>(yp) = yo;
+    if (BOTH) *reinterpret_cast<uint4*>(yp) = yo;
     *reinterpret_cast<uint4*>(ap) = ao;
 }
 
+// BOTH = true: train mode (y1 and a1); BOTH = false: eval mode (only a1 = ELU(scale*y1 + shift), running statistics)
+template <bool BOTH>
 __global__ void __launch_bounds__(256, 2)
 pointnet_l1_fwd_bn_t_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                             const float* __restrict__ scale, const float* __restrict__ shift,
@@ -248,11 +250,11 @@ pointnet_l1_fwd_bn_t_kernel(const float* __restrict__ x, const float* __restrict
         if (vcnt == 8) {
 #pragma unroll
             for (int k = 0; k < L1_CH_PER_WARP; ++k)
-                if (c0 + k < Cout) l1_bn_channel<true>(ck[k], xp, 8, yT + t256(p0, c0 + k, Cout), aT + t256(p0, c0 + k, Cout));
+                if (c0 + k < Cout) l1_bn_channel<true, BOTH>(ck[k], xp, 8, yT + t256(p0, c0 + k, Cout), aT + t256(p0, c0 + k, Cout));
         } else {
 #pragma unroll
             for (int k = 0; k < L1_CH_PER_WARP; ++k)
-                if (c0 + k < Cout) l1_bn_channel<false>(ck[k], xp, vcnt, yT + t256(p0, c0 + k, Cout), aT + t256(p0, c0 + k, Cout));
+                if (c0 + k < Cout) l1_bn_channel<false, BOTH>(ck[k], xp, vcnt, yT + t256(p0, c0 + k, Cout), aT + t256(p0, c0 + k, Cout));
         }
     }
 }
@@ -1022,7 +1024,10 @@ int pcaa_pointnet_l1_fwd_t(const float* x, const float* w, const float* bias, co
     PCAA_REQUIRE(((uintptr_t)yT & 15) == 0 && ((uintptr_t)w & 15) == 0 && Cout > 0, PCAA_ERR_ALIGN, "pointnet_l1_fwd_t: alignment / Cout");
     PCAA_REQUIRE((scale == nullptr) == (shift == nullptr), PCAA_ERR_SHAPE, "pointnet_l1_fwd_t: scale and shift go together");
     dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
-    pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, stats, P, TN, Cout);
+    if (scale != nullptr && stats == nullptr)      // eval mode: the packed-arithmetic kernel, one output
+        pointnet_l1_fwd_bn_t_kernel<false><<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, (__nv_bfloat16*)yT, P, TN, Cout);
+    else
+        pointnet_l1_fwd_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, stats, P, TN, Cout);
     return check_launch("pointnet_l1_fwd_t");
 }
 
@@ -1034,7 +1039,7 @@ int pcaa_pointnet_l1_fwd_bn_t(const float* x, const float* w, const float* bias,
                  "pointnet_l1_fwd_bn_t: alignment / Cout");
     PCAA_REQUIRE(yT && aT && scale && shift, PCAA_ERR_SHAPE, "pointnet_l1_fwd_bn_t: needs both outputs and the BatchNorm coefficients");
     dim3 grid((unsigned)ceil_div(P, L1_TILE_POINTS), (unsigned)ceil_div(Cout, 8 * L1_CH_PER_WARP));
-    pointnet_l1_fwd_bn_t_kernel<<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, (__nv_bfloat16*)aT, P, TN, Cout);
+    pointnet_l1_fwd_bn_t_kernel<true><<<grid, 256, 0, ST(stream)>>>(x, w, bias, scale, shift, (__nv_bfloat16*)yT, (__nv_bfloat16*)aT, P, TN, Cout);
     return check_launch("pointnet_l1_fwd_bn_t");
 }
 

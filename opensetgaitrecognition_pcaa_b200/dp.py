@@ -363,7 +363,7 @@ def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
             phases, _ = ref._phases(*[g[r] for g in gathered])
             phases[0][1]()
             ref.D.g.copy_(dsum / world)
-            for _, fn in phases[2:]:
+            for _, fn in phases[1:]:                                   # (the exchange phases are no-ops on one rank)
                 fn()
             gsum += ref.G.g
         gsums.append(gsum)

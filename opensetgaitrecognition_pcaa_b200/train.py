@@ -173,7 +173,7 @@ class PCAATrainer:
         # PCAA_SPLIT_GRAPHS=1 forces that program structure on one rank (tests)
         # With the copy-engine exchange on BOTH gradient buffers the data-parallel step contains no NCCL call: it can be
         # captured as ONE graph like the single-rank step (cross-rank ordering = the symmetric-memory barriers inside it).
-        # PCAA_DP_ONE_GRAPH=0 keeps the four-graph structure; any NCCL exchange forces it.
+        # PCAA_DP_ONE_GRAPH=0 (default) keeps the five-graph structure; any NCCL exchange forces it.
         all_peer = self.G.peer is not None and self.D.peer is not None
         one_graph = all_peer and os.environ.get("PCAA_DP_ONE_GRAPH", "0") == "1"
         self.split_graphs = (self.world > 1 and not one_graph) or os.environ.get("PCAA_SPLIT_GRAPHS", "0") == "1"
@@ -248,11 +248,31 @@ class PCAATrainer:
                 z0_eff, means_eff = z0 + mus, self._zero_means        # z = z0 + mus enters the kernel as its noise input
             st["d_losses"] = ops.wgangp_dstep(st["fv"], z0_eff, means_eff, gt, alphas.reshape(-1), *self.Dw, cfg["GP_WEIGHT"], self.Dg)
 
-        def exchange_critic():
+        def exchange_critic_start():
+            # the critic's 4.5 k gradients are reduced on the exchange stream WHILE the decoder forward / Chamfer / decoder
+            # backward below run: none of them needs the updated critic (only the adversarial term does), so the latency of this
+            # small exchange -- two cross-rank barriers, i.e. also the skew between the ranks' encoder forwards -- is hidden
             self.xD.start(0, self.D.size)
+
+        def decoder_forward_and_backward():
+            fv = st["fv"]
+            if self.dec is None:                                 # variant 3: tot = loss_g + sup (PCAA_ablation.py:640)
+                st["rec_loss"] = torch.zeros((), device=self.dev, dtype=torch.float32)
+                return
+            st["h0"] = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU) if self.gph is not None else fv
+            wb = self._decoder_weights_bf16()
+            rec, acts = engine.decoder_forward_tc(st["h0"], self.P_G, wb)
+            rec4 = rec.view(pcs.shape)
+            frame_loss, i1, i2 = ops.chamfer_fwd(rec4, pcs)
+            st["rec_loss"] = ops.chamfer_reduce(frame_loss, True)
+            drec = ops.chamfer_bwd(rec4, pcs, i1, i2, self._one, True)
+            # backward: Chamfer -> decoder (the projection head follows once the adversarial gradient exists)
+            st["dh0"], _ = engine.decoder_backward_tc(drec.view(B, S), acts, self.P_G, wb, self.gb_G)
+
+        def exchange_critic_finish():
             self.xD.finish()
 
-        def generator_forward_and_decoder_backward():
+        def critic_update_and_generator_losses():
             fv, logits = st["fv"], st["logits"]
             ops.adam_advance(self.D.step_dev, self.D.coef_dev, cfg["LR"], cfg["B1"], cfg["B2"])
             ops.adam_flat_dev(self.D.p, self.D.g, self.D.m, self.D.v, cfg["B1"], cfg["B2"], 1e-8, self.D.coef_dev, gscale)
@@ -263,24 +283,15 @@ class PCAATrainer:
             # cross-entropy term only on iterations with i % SUPERVISION_FREQUENCY == 0 (PCAA_ablation.py:1005-1018): on the
             # others tot = rec + loss_g, the classifier head receives no gradient (sup_loss is still reported)
             st["sup_loss"], st["dlogits"], st["pred"] = ops.softmax_ce(logits, gt, want_grad=supervised)
-            if self.dec is None:                                 # variant 3: tot = loss_g + sup (PCAA_ablation.py:640)
-                st["rec_loss"] = torch.zeros((), device=self.dev, dtype=torch.float32)
-            else:
-                h0 = engine.linear_forward(fv, self.P_GPH["0.weight"], self.P_GPH["0.bias"], ACT_ELU) if self.gph is not None else fv
-                wb = self._decoder_weights_bf16()
-                rec, acts = engine.decoder_forward_tc(h0, self.P_G, wb)
-                rec4 = rec.view(pcs.shape)
-                frame_loss, i1, i2 = ops.chamfer_fwd(rec4, pcs)
-                st["rec_loss"] = ops.chamfer_reduce(frame_loss, True)
-                drec = ops.chamfer_bwd(rec4, pcs, i1, i2, self._one, True)
-                # backward: Chamfer -> decoder -> projection head (+ adversarial gradient)
-                G_unused: Dict[str, torch.Tensor] = {}
-                dh0, _ = engine.decoder_backward_tc(drec.view(B, S), acts, self.P_G, wb, self.gb_G)
-                if self.gph is not None:
-                    engine.linear_backward(dh0, fv, h0, self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused, self.gb_GPH,
-                                           dx_out=st["dfv"], dx_acc=True)
+            if self.dec is not None:
+                dh0 = st.pop("dh0")
+                if self.gph is not None:                         # projection head: its gradient + the adversarial one into d fv
+                    G_unused: Dict[str, torch.Tensor] = {}
+                    engine.linear_backward(dh0, fv, st.pop("h0"), self.P_GPH["0.weight"], "0.weight", "0.bias", G_unused,
+                                           self.gb_GPH, dx_out=st["dfv"], dx_acc=True)
                 else:                                            # train_CGAAE: the decoder reads sup_fv (train_AAE.py:243)
                     st["dfv"] = ops.ew(EW_ADD, st["dfv"], dh0)
+                    st.pop("h0", None)
             ops.adam_advance(self.G.step_dev, self.G.coef_dev, cfg["LR"], cfg["B1"], b2_g)
             if supervised and cls_split:
                 ops.adam_advance(self._cls_step_dev, self._cls_coef_dev, cfg["LR"], cfg["B1"], b2_g)
@@ -312,8 +323,9 @@ class PCAATrainer:
                          "fv": st["fv"]}
             st.pop("saved", None)
 
-        return [("kernels", encoder_and_critic), ("exchange", exchange_critic),
-                ("kernels", generator_forward_and_decoder_backward), ("exchange", exchange_decoder_span),
+        return [("kernels", encoder_and_critic), ("exchange", exchange_critic_start),
+                ("kernels", decoder_forward_and_backward), ("exchange", exchange_critic_finish),
+                ("kernels", critic_update_and_generator_losses), ("exchange", exchange_decoder_span),
                 ("kernels", encoder_backward), ("exchange", exchange_encoder_span), ("kernels", encoder_update)], st
 
     def step(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor,
@@ -336,7 +348,7 @@ class PCAATrainer:
         """`step` replayed from CUDA graphs (captured once per input shape).  The ~200 launches of an iteration become
         one graph launch: no per-kernel host cost, back-to-back kernel scheduling on the device -- what the launch-bound
         small-batch configurations need.  With one rank the whole iteration is ONE graph (the side-stream Adam update
-        is a fork inside it); data-parallel, the kernel phases between the gradient exchanges are four graphs that
+        is a fork inside it); data-parallel, the kernel phases between the gradient exchanges are five graphs that
         share a memory pool and the NCCL all-reduces (+ the decoder span's Adam update on the side stream) are issued
         eagerly between their replays, so no collective is ever captured.
         The first call with a new shape runs eagerly (it also initialises the library's per-kernel attributes), the
