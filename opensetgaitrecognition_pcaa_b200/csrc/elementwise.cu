@@ -304,6 +304,45 @@ tcn_bn_elu_next_kernel(const float* __restrict__ y, const double* __restrict__ s
         }
     }
     __syncthreads();
+    if (C % 8 == 0) {
+        // 8 channels per thread: 32-byte reads of the (up to three) source rows, the im2col row written as one 48-byte run
+        const int ncg = C / 8;
+        const int64_t total = R * ncg;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int c0 = (int)(i % ncg) * 8;
+            const int64_t r = i / ncg;
+            const int t = (int)(r % T);
+            float a[3][8];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int ts = t - (2 - k) * dil_next;
+                if ((k == 2 || col != nullptr) && ts >= 0) {
+                    float v[8];
+                    V8<float>::load(y + (r - t + ts) * C + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[k][j] = elu_f(fmaf(v[j], sc[c0 + j], sh[c0 + j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[k][j] = 0.f;
+                }
+            }
+            if (act) V8<float>::store(act + r * C + c0, a[2]);
+            if (col) {
+                __nv_bfloat16* dst = col + (r * C + c0) * 3;
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    float w8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = g * 8 + j;              // element e of the 24: channel e / 3, tap e % 3
+                        w8[j] = a[e % 3][e / 3];
+                    }
+                    V8<__nv_bfloat16>::store(dst + g * 8, w8);
+                }
+            }
+        }
+        return;
+    }
     const int64_t total = R * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -537,6 +576,43 @@ __global__ void tcn_im2col_kernel(const float* __restrict__ x, TO* __restrict__ 
         int t = (int)(bt % T);
         int ts = t - (2 - k) * dil;
         st_from_float<TO>(col + i, ts >= 0 ? x[(bt - t + ts) * Cin + ci] : 0.f);
+    }
+}
+
+// bf16 im2col, 8 channels per thread (Cin % 8 == 0): three 32-byte reads of the shifted rows, one 48-byte run of the
+// output row (24 consecutive bf16: channels c0 .. c0+7, taps interleaved) as three 16-byte stores
+__global__ void __launch_bounds__(256)
+tcn_im2col_bf16x8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int64_t BT, int T, int Cin, int dil) {
+    const int ncg = Cin / 8;
+    const int64_t total = BT * ncg;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % ncg);
+        const int64_t bt = i / ncg;
+        const int t = (int)(bt % T);
+        float v[3][8];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int ts = t - (2 - k) * dil;
+            if (ts >= 0) {
+                V8<float>::load(x + (bt - t + ts) * Cin + cg * 8, v[k]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+            }
+        }
+        float o[24];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[j * 3 + k] = v[k][j];
+        __nv_bfloat16* dst = col + (bt * Cin + cg * 8) * 3;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            float w8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w8[j] = o[g * 8 + j];
+            V8<__nv_bfloat16>::store(dst + g * 8, w8);
+        }
     }
 }
 
@@ -1001,7 +1077,9 @@ int pcaa_pack_bf16(const float* in, int64_t R, int64_t C, int64_t ld_in, void* o
 int pcaa_tcn_im2col(const float* x, void* col, int col_dtype, int64_t B, int T, int Cin, int dil, pcaa_stream stream) {
     int64_t total = B * T * Cin * 3;
     if (total == 0) return PCAA_OK;
-    if (col_dtype == PCAA_BF16)
+    if (col_dtype == PCAA_BF16 && Cin % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)col & 15) == 0)
+        tcn_im2col_bf16x8_kernel<<<ew_grid(B * T * (Cin / 8)), 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)col, B * T, T, Cin, dil);
+    else if (col_dtype == PCAA_BF16)
         tcn_im2col_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)col, B * T, T, Cin, dil);
     else
         tcn_im2col_kernel<float><<<ew_grid(total), 256, 0, ST(stream)>>>(x, (float*)col, B * T, T, Cin, dil);
@@ -1027,7 +1105,7 @@ int pcaa_tcn_bn_elu_next(const float* y, const double* stats, const float* gamma
     PCAA_REQUIRE(col != nullptr || act != nullptr, PCAA_ERR_SHAPE, "tcn_bn_elu_next: no output requested");
     PCAA_REQUIRE(col == nullptr || dil_next > 0, PCAA_ERR_SHAPE, "tcn_bn_elu_next: the im2col output needs the next layer's dilation");
     const double unbias = R > 1 ? (double)R / (double)(R - 1) : 1.0;
-    int grid = ew_grid((R * C + 3) / 4);
+    int grid = ew_grid(C % 8 == 0 ? R * (C / 8) : (R * C + 3) / 4);
     tcn_bn_elu_next_kernel<<<grid, 256, 2 * C * sizeof(float), ST(stream)>>>(y, stats, 1.0 / (double)R, unbias, gamma, beta,
                                                                            running_mean, running_var, momentum, eps, scale,
                                                                            shift, coef_out, R, T, C, dil_next,

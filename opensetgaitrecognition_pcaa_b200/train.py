@@ -603,9 +603,21 @@ def fit(trainer: PCAATrainer, train, valid, config: dict, model_name: str, root:
         if shuffle_gen is None:
             shuffle_gen = torch.Generator()
             shuffle_gen.manual_seed(int(config.get("SHUFFLE_SEED", 0)))
-        state = shuffle_gen.get_state().to(trainer.dev if trainer.dev.type == "cuda" and torch.distributed.get_backend(trainer.pg) == "nccl" else "cpu")
+        on_dev = trainer.dev if torch.distributed.get_backend(trainer.pg) == "nccl" else "cpu"
+        state = shuffle_gen.get_state().to(on_dev)
         torch.distributed.broadcast(state, 0, group=trainer.pg)
         shuffle_gen.set_state(state.cpu())
+        if np_rng is None or torch_gen is None:
+            # the reference draws z0 / alphas from the GLOBAL numpy / torch generators; N processes cannot share those, so
+            # rank 0 picks a seed and every rank builds the same private generators from it
+            seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64).to(on_dev)
+            torch.distributed.broadcast(seed, 0, group=trainer.pg)
+            if np_rng is None:
+                import numpy as np
+                np_rng = np.random.default_rng(int(seed))
+            if torch_gen is None:
+                torch_gen = torch.Generator()
+                torch_gen.manual_seed(int(seed))
     os.makedirs(os.path.join(root, "models", model_name), exist_ok=True)
     if rank == 0:
         write_config(trainer, config, model_name, root)                                                            # :754-757

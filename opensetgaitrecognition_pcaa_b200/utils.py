@@ -25,8 +25,12 @@ class _ChamferFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         preds, gts, i1, i2 = ctx.saved_tensors
-        g = ops.chamfer_bwd(preds, gts, i1, i2, gout.contiguous().float(), ctx.avg_out)
-        return g, None, None          # gts are data: no gradient (as in the reference's use)
+        gout = gout.contiguous().float()
+        g = ops.chamfer_bwd(preds, gts, i1, i2, gout, ctx.avg_out) if ctx.needs_input_grad[0] else None
+        # the loss is symmetric in its two clouds: the gradient with respect to gts (only asked for when a caller makes the
+        # "ground truth" differentiable; the reference's trainers never do) is the same kernel with the roles exchanged
+        g_gts = ops.chamfer_bwd(gts, preds, i2, i1, gout, ctx.avg_out) if ctx.needs_input_grad[1] else None
+        return g, g_gts, None
 
 
 class SeqChamferLoss(torch.nn.Module):

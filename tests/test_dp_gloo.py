@@ -92,7 +92,49 @@ def _w_sharded_mean_gradient(rank, world, out_dir):
     assert torch.allclose(flat * x.grad_scale, gg.reshape(-1), atol=1e-12)
 
 
+def _w_syncbn_math(rank, world, out_dir):
+    """The SyncBN arithmetic of engine.BnSync / engine._bn_bwd_coefs in plain torch (float64): all-reduced sums + global row
+    count give the concatenated batch's statistics; backward with LOCAL d gamma / d beta (the gradient exchange adds the
+    ranks') and GLOBAL dy coefficients equals autograd through BatchNorm on the concatenated batch."""
+    from opensetgaitrecognition_pcaa_b200 import dp, engine
+    torch.manual_seed(7)
+    R, C, eps = 12, 5, 1e-5
+    y_all = torch.randn(world * R, C, dtype=torch.float64) * 1.3 + 0.2
+    dz_all = torch.randn(world * R, C, dtype=torch.float64)
+    gamma, beta = torch.rand(C, dtype=torch.float64) + 0.5, torch.randn(C, dtype=torch.float64)
+    y, dz = y_all[rank * R:(rank + 1) * R], dz_all[rank * R:(rank + 1) * R]
+    bn = engine.BnSync()
+    assert bn.world == world
+    st = torch.cat([y.sum(0), (y * y).sum(0)])
+    bn.reduce(st)
+    Rg = R * bn.world
+    mean = st[:C] / Rg
+    var = st[C:] / Rg - mean * mean
+    invstd = 1.0 / torch.sqrt(var + eps)
+    xh = (y - mean) * invstd
+    st2 = torch.cat([dz.sum(0), (dz * xh).sum(0)])
+    dbeta_local, dgamma_local = st2[:C].clone(), st2[C:].clone()          # BEFORE the reduction
+    bn.reduce(st2)
+    dy = gamma * invstd * (dz - st2[:C] / Rg - xh * st2[C:] / Rg)         # dy = c1*dz + c2*y + c3 with the global sums
+    # reference: autograd through BatchNorm on the concatenated batch
+    ya = y_all.clone().requires_grad_(True)
+    ga, ba = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    out = torch.nn.functional.batch_norm(ya, None, None, ga, ba, training=True, eps=eps)
+    out.backward(dz_all)
+    assert torch.allclose(dy, ya.grad[rank * R:(rank + 1) * R], atol=1e-12)
+    flat = torch.cat([dgamma_local, dbeta_local])
+    x = dp.GradExchange(flat)
+    x.start(0, flat.numel())
+    x.finish()
+    assert torch.allclose(flat[:C], ga.grad, atol=1e-12) and torch.allclose(flat[C:], ba.grad, atol=1e-12)
+    assert bn.calls == 2
+
+
 # ------------------------------------------------------------------------------------------------ tests
+def test_syncbn_sums_and_backward_world2(tmp_path):
+    _spawn("_w_syncbn_math", tmp_path)
+
+
 def test_grad_exchange_world2(tmp_path):
     _spawn("_w_grad_exchange", tmp_path)
     a, b = torch.load(tmp_path / "flat0.pt"), torch.load(tmp_path / "flat1.pt")

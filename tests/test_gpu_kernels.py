@@ -310,6 +310,25 @@ def test_chamfer(ops, B, N):
         assert rel_err(grad, pp.grad) < 1e-5
 
 
+def test_chamfer_module_gradients_for_both_clouds():
+    """SeqChamferLoss through autograd (utils.py:98-107): gradient w.r.t. the predictions and, when asked for, w.r.t. the
+    other cloud -- against autograd through the oracle's formulation."""
+    from opensetgaitrecognition_pcaa_b200.utils import SeqChamferLoss
+    g = torch.Generator().manual_seed(5)
+    B, N = 2, 37
+    p, q = torch.randn(B, 4, 30, N, generator=g), torch.randn(B, 4, 30, N, generator=g)
+    for avg_out in (True, False):
+        pr, qr = p.clone().requires_grad_(True), q.clone().requires_grad_(True)
+        ref, _, _ = O.chamfer(pr, qr, avg_out)
+        w = torch.ones_like(ref) if avg_out else torch.arange(1, B + 1).float()
+        (ref * w).sum().backward()
+        pc, qc = cuda(p).requires_grad_(True), cuda(q).requires_grad_(True)
+        out = SeqChamferLoss()(pc, qc, avg_out=avg_out)
+        (out * cuda(w)).sum().backward()
+        assert rel_err(out.detach(), ref.detach()) < 1e-5
+        assert rel_err(pc.grad, pr.grad) < 1e-5 and rel_err(qc.grad, qr.grad) < 1e-5
+
+
 def test_chamfer_golden(ops, golden_dir):
     for name in ("n50_c2_b4", "n70_c4_b3"):
         gd = np.load(os.path.join(golden_dir, f"modules_{name}.npz"))
