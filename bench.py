@@ -523,7 +523,9 @@ def run_b200(args):
         peer = trainer.G.peer
         exchange = {"mode": "peer (copy engines over NVLink symmetric memory: chunked reduce-scatter / all-gather, one-shot for spans < 4 MB)" if peer is not None else "nccl",
                     "bytes_reduced_per_step": trainer.xG.bytes_reduced / max(1, trainer.G.step),
-                    "bytes_pulled_per_step": (peer.bytes_pulled / max(1, trainer.G.step)) if peer is not None else 0}
+                    "bytes_pulled_per_step": (peer.bytes_pulled / max(1, trainer.G.step)) if peer is not None else 0,
+                    "spans": ["critic", "decoder + projection head"] + (["encoder"] if trainer.enc_buckets == 1 else
+                                                                        ["encoder: heads, TCN, PointNet 4-3", "encoder: PointNet 2-1"])}
 
     # ---- optional: where the step spends its time, phase by phase (CUDA events on the main stream, max over ranks)
     phases_ms = None

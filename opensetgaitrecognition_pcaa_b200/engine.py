@@ -157,13 +157,33 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
 
 
 def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = None,
-                      pre: str = "pc_block.", side: Optional[torch.cuda.Stream] = None, bn: Optional[BnSync] = None) -> Grads:
+                      pre: str = "pc_block.", side: Optional[torch.cuda.Stream] = None, bn: Optional[BnSync] = None,
+                      pause_after: Optional[int] = None):
     """gpool [B*T, 1024] fp32 = d loss / d pooled.  Returns parameter gradients (written into gradbuf when given).
 
     With a `side` stream the weight-gradient GEMM of layer l (tensor bound, reads dy_l and a_{l-1}) runs there while the
     current stream goes on with the data gradient's successor, the HBM-bound BatchNorm-backward pass of layer l-1: the
-    two are independent and have complementary bottlenecks.  The current stream waits for `side` before returning."""
+    two are independent and have complementary bottlenecks.  The current stream waits for `side` before returning.
+
+    `pause_after=l` (4, 3 or 2) returns ``(G, resume)`` once the weight AND data gradient of layer l are enqueued: at that
+    point the gradients of layers >= l are final and W_l is no longer read, so a data-parallel trainer can start exchanging
+    (and updating) them while ``resume()`` -- the rest of the backward -- runs."""
     G: Grads = {}
+    steps = _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G)
+    for l in steps:
+        if pause_after is not None and l == pause_after:
+            def resume():
+                for _ in steps:
+                    pass
+                return G
+            return G, resume
+    if pause_after is not None:
+        raise ValueError("pointnet_backward: pause_after must be 4, 3 or 2")
+    return G
+
+
+def _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G):
+    """Generator behind pointnet_backward: yields l after the weight and data gradients of layer l (4, 3, 2) are enqueued."""
     R, N, Rg = sv["R"], sv["N"], sv["Rg"]
     if (bn is not None) != (Rg != R):
         raise RuntimeError("pointnet_backward: SyncBN must be used in both the forward and the backward")
@@ -203,6 +223,7 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
         kb = f"{pre}pointnet{l - 1}.module.1."
         c, dgam, dbet = _bn_bwd_coefs(st2, R, Rg, sv["coef"][l - 1], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"), bn)
         G[kb + "weight"], G[kb + "bias"] = dgam, dbet
+        yield l
         if l > 2:
             dy = ops.bn_bwd_apply_t(dz, sv["y"][l - 1], c, R, out=dz)
     kc = f"{pre}pointnet1.module.0."
@@ -216,7 +237,6 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
         main.wait_stream(side)
         for l in (1, 2, 3):
             sv["a"][l].record_stream(side)
-    return G
 
 
 # ====================================================================================================== TCN
@@ -416,13 +436,24 @@ def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_h
 
 
 def encoder_backward(dlogits, dfv, saved, P: Params, gradbuf: Optional[Grads] = None,
-                     side: Optional[torch.cuda.Stream] = None, bn: Optional[BnSync] = None) -> Grads:
+                     side: Optional[torch.cuda.Stream] = None, bn: Optional[BnSync] = None, pause_after: Optional[int] = None):
+    """Backward of the whole encoder.  With `pause_after=l` returns ``(G, resume)`` after PointNet layer l (see
+    pointnet_backward): heads, TCN and the PointNet layers >= l are then final; ``resume()`` finishes and returns G."""
     sv_p, sv_t, sv_h = saved
     dg, G = heads_backward(dlogits, dfv, sv_h, P, gradbuf)
     dpool, Gt = tcn_backward(dg, sv_t, P, gradbuf, dout_is_frame_mean=True, bn=bn)
     G.update(Gt)
-    G.update(pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf, side=side, bn=bn))
-    return G
+    r = pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf, side=side, bn=bn, pause_after=pause_after)
+    if pause_after is None:
+        G.update(r)
+        return G
+    Gp, resume_p = r
+    G.update(Gp)
+
+    def resume():
+        G.update(resume_p())
+        return G
+    return G, resume
 
 
 # ====================================================================================================== decoder

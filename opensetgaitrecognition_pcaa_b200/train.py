@@ -138,6 +138,13 @@ class PCAATrainer:
         # the classifier layers (MLP_head, MLP_sup2: the last encoder parameters) only receive a gradient on supervised
         # iterations; torch.optim.Adam skips parameters without one, moments and per-parameter step count included
         # (PCAA_ablation.py:1005-1021 with SUPERVISION_FREQUENCY > 1), so they carry their own Adam step counter
+        # [upper, end of the encoder span) = PointNet layers 3, 4, the TCN and the heads: final (and W3 / W4 no longer read) once
+        # the data gradient of layer 3 is enqueued -- the data-parallel step exchanges and updates that part while the
+        # backward of layers 2 and 1 still runs; only pointnet1 + pointnet2 (1 MB) are exchanged at the very end
+        self._enc_upper = self.G.slices["E.pc_block.pointnet3.module.0.weight"][0]
+        self.enc_buckets = int(os.environ.get("PCAA_DP_ENC_BUCKETS", "2"))       # 1: one exchange of the whole encoder span
+        if self.enc_buckets not in (1, 2):
+            raise ValueError("PCAA_DP_ENC_BUCKETS must be 1 or 2")
         self._cls_span = self.G.span([n for n in self.G.names if n.startswith("E.MLP_head.") or n.startswith("E.MLP_sup2.")])
         assert self._cls_span[1] == self._enc_span[1], "classifier layers must close the encoder span"
         self._cls_step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -173,7 +180,7 @@ class PCAATrainer:
         # PCAA_SPLIT_GRAPHS=1 forces that program structure on one rank (tests)
         # With the copy-engine exchange on BOTH gradient buffers the data-parallel step contains no NCCL call: it can be
         # captured as ONE graph like the single-rank step (cross-rank ordering = the symmetric-memory barriers inside it).
-        # PCAA_DP_ONE_GRAPH=0 (default) keeps the five-graph structure; any NCCL exchange forces it.
+        # PCAA_DP_ONE_GRAPH=0 (default) keeps the split-graph structure; any NCCL exchange forces it.
         all_peer = self.G.peer is not None and self.D.peer is not None
         one_graph = all_peer and os.environ.get("PCAA_DP_ONE_GRAPH", "0") == "1"
         self.split_graphs = (self.world > 1 and not one_graph) or os.environ.get("PCAA_SPLIT_GRAPHS", "0") == "1"
@@ -302,31 +309,59 @@ class PCAATrainer:
             if self._dec_span is not None:
                 self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
 
-        def encoder_backward():
+        def encoder_backward_upper():
             self.G.g[self._enc_span[0]:self._enc_span[1]].zero_()     # one fill instead of one per accumulated gradient
-            engine.encoder_backward(st["dlogits"], st["dfv"], st["saved"], self.P_E, self.gb_E, side=self._wgrad_stream,
-                                    bn=self.bn_sync)
+            _, st["resume"] = engine.encoder_backward(st["dlogits"], st["dfv"], st["saved"], self.P_E, self.gb_E,
+                                                      side=self._wgrad_stream, bn=self.bn_sync, pause_after=3)
+
+        def encoder_backward():
+            encoder_backward_upper()
+            st.pop("resume")()
 
         def exchange_encoder_span():
             self.xG.start(*self._enc_span)
             self.xG.finish()
 
-        def encoder_update():
+        def encoder_update_whole():
+            adam_upper()
+            encoder_update()
+
+        def adam_upper():
             if not cls_split:
-                adam_span(*self._enc_span)
+                adam_span(self._enc_upper, self._enc_span[1])
             else:
-                adam_span(self._enc_span[0], self._cls_span[0])
+                adam_span(self._enc_upper, self._cls_span[0])
                 if supervised:
                     adam_span(*self._cls_span, coef=self._cls_coef_dev)
+
+        def exchange_encoder_upper():
+            # heads, TCN, PointNet layers 4 and 3 (8.6 of the encoder's 9.6 MB): exchanged and updated on the side stream
+            # while the backward of layers 2 and 1 (~2 ms) runs on the main one
+            self.xG.start(self._enc_upper, self._enc_span[1], then=adam_upper)
+
+        def encoder_backward_lower():
+            st.pop("resume")()
+
+        def exchange_encoder_lower():
+            self.xG.start(self._enc_span[0], self._enc_upper)
+            self.xG.finish()
+
+        def encoder_update():
+            adam_span(self._enc_span[0], self._enc_upper)
             st["out"] = {"rec_loss": st["rec_loss"], "d_loss": st["d_losses"][0], "gp": st["d_losses"][1],
                          "loss_g": st["loss_g"], "sup_loss": st["sup_loss"], "pred": st["pred"], "logits": st["logits"],
                          "fv": st["fv"]}
             st.pop("saved", None)
 
-        return [("kernels", encoder_and_critic), ("exchange", exchange_critic_start),
+        head = [("kernels", encoder_and_critic), ("exchange", exchange_critic_start),
                 ("kernels", decoder_forward_and_backward), ("exchange", exchange_critic_finish),
-                ("kernels", critic_update_and_generator_losses), ("exchange", exchange_decoder_span),
-                ("kernels", encoder_backward), ("exchange", exchange_encoder_span), ("kernels", encoder_update)], st
+                ("kernels", critic_update_and_generator_losses), ("exchange", exchange_decoder_span)]
+        if self.enc_buckets == 1:
+            return head + [("kernels", encoder_backward), ("exchange", exchange_encoder_span),
+                           ("kernels", encoder_update_whole)], st
+        return head + [("kernels", encoder_backward_upper), ("exchange", exchange_encoder_upper),
+                       ("kernels", encoder_backward_lower), ("exchange", exchange_encoder_lower),
+                       ("kernels", encoder_update)], st
 
     def step(self, pcs: torch.Tensor, gt: torch.Tensor, z0: torch.Tensor, alphas: torch.Tensor,
              supervised: bool = True) -> Dict[str, torch.Tensor]:
@@ -391,7 +426,7 @@ class PCAATrainer:
         """Mean milliseconds per phase over the iterations run since the last reset with phase_timing on (synchronises).
         Measured between events on the MAIN stream: a phase that forks work to the side stream (the decoder-span exchange +
         its Adam update) shows only its enqueue cost; the wait for that work shows up in the phase that joins it
-        (exchange_encoder_span / the end of the step)."""
+        (exchange_encoder_lower / the end of the step)."""
         torch.cuda.synchronize(self.dev)
         acc: Dict[str, List[float]] = {}
         for name, e0, e1 in self._phase_events:

@@ -279,12 +279,16 @@ def test_small_helpers(ops):
 
 # ------------------------------------------------------------------------------------------------ Chamfer
 def _check_idx(P, idx, ref_idx, dim):
-    """argmins equal, or (listed exception class: fp near-ties) the chosen distances agree to 1e-5 relative."""
+    """argmins equal, or (listed exception class: fp near-ties) the chosen distances agree to 1e-4 relative; every
+    exception is LISTED: (b, t, point) -> ours / reference index and the two distances."""
     idx, ref_idx = idx.cpu().long(), ref_idx.long()
     bad = idx != ref_idx
     if bad.any():
         d_ours = torch.gather(P, dim, idx.unsqueeze(dim)).squeeze(dim)
         d_ref = torch.gather(P, dim, ref_idx.unsqueeze(dim)).squeeze(dim)
+        for b, t, n in torch.nonzero(bad).tolist()[:50]:
+            print(f"  arg-min exception (dim {dim}) at b={b} t={t} point={n}: ours {int(idx[b, t, n])} (d={float(d_ours[b, t, n]):.7g}) "
+                  f"vs reference {int(ref_idx[b, t, n])} (d={float(d_ref[b, t, n]):.7g})")
         assert float(((d_ours - d_ref).abs()[bad] / (d_ref.abs()[bad] + 1e-6)).max()) < 1e-4
     return int(bad.sum())
 

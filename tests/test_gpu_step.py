@@ -217,7 +217,7 @@ def test_graphed_step_is_the_eager_step(split):
         enc, dec, dis, gph = build(p, C, nmax)
         trs.append((PCAATrainer(enc, dec, dis, gph, means, CFG), enc))
     (ta, ea), (tb, eb) = trs
-    # split: the data-parallel program structure (five kernel-phase graphs, gradient exchanges issued eagerly between
+    # split: the data-parallel program structure (six kernel-phase graphs, gradient exchanges issued eagerly between
     # their replays) on one rank
     tb.split_graphs = split
     rng = np.random.default_rng(5)
@@ -250,7 +250,7 @@ def test_graphed_step_is_the_eager_step(split):
         assert 0.5 * lr < float(moved.max()) <= lr * 1.5           # |Adam update| ~ lr: bias corrections applied
     assert tb.graph_launches((B, 4, 30, nmax)) > 100 and tb.G.step == ta.G.step == 4 and tb.D.step == 4
     prog = tb._graphs[((B, 4, 30, nmax), (B, 32))]["program"]
-    assert [k for k, _ in prog] == (["graph", "exchange"] * 4 + ["graph"] if split else ["graph"])
+    assert [k for k, _ in prog] == (["graph", "exchange"] * (3 + tb.enc_buckets) + ["graph"] if split else ["graph"])
     assert int(tb.G.step_dev) == 4 and int(tb.D.step_dev) == 4 and int(ta.G.step_dev) == 4
     sd = eb.state_dict()
     assert int(sd["pc_block.pointnet1.module.1.num_batches_tracked"]) == 4
