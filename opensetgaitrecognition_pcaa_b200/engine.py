@@ -169,7 +169,7 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
     point the gradients of layers >= l are final and W_l is no longer read, so a data-parallel trainer can start exchanging
     (and updating) them while ``resume()`` -- the rest of the backward -- runs."""
     G: Grads = {}
-    steps = _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G)
+    steps = _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G, pause_after)
     for l in steps:
         if pause_after is not None and l == pause_after:
             def resume():
@@ -182,7 +182,7 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
     return G
 
 
-def _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G):
+def _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G, pause_after=None):
     """Generator behind pointnet_backward: yields l after the weight and data gradients of layer l (4, 3, 2) are enqueued."""
     R, N, Rg = sv["R"], sv["N"], sv["Rg"]
     if (bn is not None) != (Rg != R):
@@ -223,6 +223,8 @@ def _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G):
         kb = f"{pre}pointnet{l - 1}.module.1."
         c, dgam, dbet = _bn_bwd_coefs(st2, R, Rg, sv["coef"][l - 1], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"), bn)
         G[kb + "weight"], G[kb + "bias"] = dgam, dbet
+        if side is not None and l == pause_after:
+            main.wait_stream(side)                    # the caller hands these gradients on: the weight gradients must be in
         yield l
         if l > 2:
             dy = ops.bn_bwd_apply_t(dz, sv["y"][l - 1], c, R, out=dz)
