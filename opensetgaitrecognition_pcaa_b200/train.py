@@ -383,7 +383,7 @@ class PCAATrainer:
         """`step` replayed from CUDA graphs (captured once per input shape).  The ~200 launches of an iteration become
         one graph launch: no per-kernel host cost, back-to-back kernel scheduling on the device -- what the launch-bound
         small-batch configurations need.  With one rank the whole iteration is ONE graph (the side-stream Adam update
-        is a fork inside it); data-parallel, the kernel phases between the gradient exchanges are five graphs that
+        is a fork inside it); data-parallel, the kernel phases between the gradient exchanges are six graphs that
         share a memory pool and the NCCL all-reduces (+ the decoder span's Adam update on the side stream) are issued
         eagerly between their replays, so no collective is ever captured.
         The first call with a new shape runs eagerly (it also initialises the library's per-kernel attributes), the
