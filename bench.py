@@ -321,7 +321,7 @@ def run_infer(args, world, rank, local, dev):
     if rank != 0:
         return
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_infer_rate(args.nmax, args.k)
+        line["cpu_baseline"] = cpu_infer_rate(args.nmax, args.k, n=480)
     print(json.dumps(line))
 
 
@@ -604,10 +604,10 @@ def run_b200(args):
     if world == 1 and not args.no_cpu:
         # the reference's own loop on the host cores (bounded sample: batch 32, 1 warm-up + 2 timed iterations) and on cuda:0
         # (stock torch eager, same batch as this arm), each in a fresh process: `bench.py --impl reference`
-        cpu = sub_bench(["--impl", "reference", "--steps", "2", "--warmup", "1", "--nmax", str(NMAX)])
+        cpu = sub_bench(["--impl", "reference", "--steps", "5", "--warmup", "1", "--nmax", str(NMAX)])     # ~12 s of CPU work
         line["cpu_baseline"] = cpu.get("cpu_baseline", cpu)
         if inference_rec is not None:
-            inference_rec["cpu_baseline"] = cpu_infer_rate(NMAX, args.k)
+            inference_rec["cpu_baseline"] = cpu_infer_rate(NMAX, args.k, n=480)                              # ~10 s
         torch.cuda.empty_cache()
         eager = sub_bench(["--impl", "reference", "--device", "cuda", "--batch", str(B), "--steps", "5", "--warmup", "2", "--nmax", str(NMAX)])
         if "error" in eager:
