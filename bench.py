@@ -521,7 +521,9 @@ def run_b200(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
         peer = trainer.G.peer
-        exchange = {"mode": "peer (copy engines over NVLink symmetric memory: chunked reduce-scatter / all-gather, one-shot for spans < 4 MB)" if peer is not None else "nccl",
+        exchange = {"mode": ("peer (copy engines over NVLink symmetric memory: chunked reduce-scatter / all-gather, one-shot for spans < 4 MB"
+                             + ("; decoder span: reduce-scatter of gradients, Adam on the owned 1/world, all-gather of the updated fp32 weights and bf16 copies)"
+                                if trainer.shard_adam else ")")) if peer is not None else "nccl",
                     "bytes_reduced_per_step": trainer.xG.bytes_reduced / max(1, trainer.G.step),
                     "bytes_pulled_per_step": (peer.bytes_pulled / max(1, trainer.G.step)) if peer is not None else 0,
                     "spans": ["critic", "decoder + projection head"] + (["encoder"] if trainer.enc_buckets == 1 else

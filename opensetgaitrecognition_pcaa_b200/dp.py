@@ -76,22 +76,28 @@ def exchange_mode() -> str:
     return os.environ.get("PCAA_DP_EXCHANGE", "peer").lower()
 
 
-def alloc_exchange_buffer(n: int, device, group=None):
-    """fp32 zeros(n) for a gradient buffer that will be exchanged, plus a PeerExchange when the peer mode is on and the
-    symmetric-memory rendezvous succeeds (one process per GPU of one NVLink domain); otherwise (tensor, None) and the
-    exchange goes through NCCL.  Collective when world > 1 and the peer mode is on."""
+def alloc_symmetric(n: int, dtype, device, group=None):
+    """zeros(n) of `dtype` in symmetric (peer-mapped) memory plus its rendezvous handle, or (plain zeros, None) when the peer
+    mode is off / not possible.  Collective when world > 1 and the peer mode is on: all ranks must call it in the same order."""
     rank, world = world_info(group)
     if world > 1 and exchange_mode() == "peer" and torch.device(device).type == "cuda":
         try:
             import torch.distributed._symmetric_memory as symm
-            t = symm.empty(n, dtype=torch.float32, device=torch.device(device))
+            t = symm.empty(n, dtype=dtype, device=torch.device(device))
             t.zero_()
-            hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
-            return t, PeerExchange(t, hdl)
-        except Exception as e:                       # noqa: BLE001 -- any failure here means "no peer access": NCCL still works
+            return t, symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+        except Exception as e:                       # noqa: BLE001 -- any failure here means "no peer access"
             if rank == 0:
-                print(f"[pcaa dp] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
-    return torch.zeros(n, device=device, dtype=torch.float32), None
+                print(f"[pcaa dp] symmetric memory unavailable ({type(e).__name__}: {e})", flush=True)
+    return torch.zeros(n, device=device, dtype=dtype), None
+
+
+def alloc_exchange_buffer(n: int, device, group=None):
+    """fp32 zeros(n) for a gradient buffer that will be exchanged, plus a PeerExchange when the peer mode is on and the
+    symmetric-memory rendezvous succeeds (one process per GPU of one NVLink domain); otherwise (tensor, None) and the
+    exchange goes through NCCL.  Collective when world > 1 and the peer mode is on."""
+    t, hdl = alloc_symmetric(n, torch.float32, device, group)
+    return t, (PeerExchange(t, hdl) if hdl is not None else None)
 
 
 class PeerExchange:
@@ -147,10 +153,10 @@ class PeerExchange:
         c = ((n + self.world - 1) // self.world + 7) // 8 * 8
         return [(min(hi, lo + r * c), min(hi, lo + (r + 1) * c)) for r in range(self.world)]
 
-    def all_reduce_(self, lo: int, hi: int) -> None:
+    def reduce_scatter_(self, lo: int, hi: int) -> List[Tuple[int, int]]:
+        """First half of `all_reduce_`: afterwards flat[chunk of this rank] holds the sum over ranks (the other chunks keep this
+        rank's own values).  Returns the chunk list (index = rank)."""
         from . import ops
-        if hi <= lo:
-            return
         if (hi - lo) % 4 or lo % 4:
             raise ValueError("PeerExchange: spans must be multiples of 4 floats (16-byte copies)")
         cur = torch.cuda.current_stream(self.flat.device)
@@ -169,6 +175,15 @@ class PeerExchange:
             for st in self.streams:
                 cur.wait_stream(st)
             ops.sum_into(self.flat[mlo:mhi], self.stage[:, :mhi - mlo])
+        return ch
+
+    def all_gather_(self, ch: List[Tuple[int, int]], bufs=None) -> None:
+        """Second half: every rank pulls chunk k of each buffer from rank k.  `bufs` = [(local tensor, symmetric-memory handle)],
+        all indexed like the gradient buffer; default = the gradient buffer itself (all-reduce).  Barrier before (every chunk
+        is final on its owner) and after (nobody still reads this rank's chunk when its owner next overwrites it)."""
+        cur = torch.cuda.current_stream(self.flat.device)
+        if bufs is None:
+            bufs = [(self.flat, self.hdl)]
         self.hdl.barrier(channel=1)
         for peer, st in zip(self.peers, self.streams):
             b, e = ch[peer]
@@ -176,11 +191,17 @@ class PeerExchange:
                 continue
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                self.flat[b:e].copy_(self.hdl.get_buffer(peer, (e - b,), torch.float32, b))
-            self.bytes_pulled += 4 * (e - b)
+                for t, h in bufs:
+                    t[b:e].copy_(h.get_buffer(peer, (e - b,), t.dtype, b))
+                    self.bytes_pulled += t.element_size() * (e - b)
         for st in self.streams:
             cur.wait_stream(st)
         self.hdl.barrier(channel=2)
+
+    def all_reduce_(self, lo: int, hi: int) -> None:
+        if hi <= lo:
+            return
+        self.all_gather_(self.reduce_scatter_(lo, hi))
 
 
 PEER_MIN = 1 << 20      # spans below 4 MB take the one-shot path (every rank pulls every rank's whole span): latency bound
@@ -249,6 +270,32 @@ class GradExchange:
                 then()
             else:
                 self._pending.append(w)
+
+    def start_sharded(self, lo: int, hi: int, update, bufs) -> None:
+        """Sharded-optimizer variant of ``start(lo, hi, then=update)`` for the peer exchange (ZeRO-1 over NVLink peer memory):
+        reduce-scatter flat[lo:hi], call ``update(b, e)`` for THIS rank's chunk only (its Adam step: parameters, moments and
+        the bf16 operand copy of [b, e)), then all-gather the UPDATED buffers `bufs` = [(tensor, symmetric handle)] instead
+        of the reduced gradient.  Every rank ends with identical parameters, and an optimizer pass over 1/world of the
+        span instead of all of it -- on the side stream like `start`.  The reduced gradient exists only chunk-wise on its
+        owners afterwards (PCAATrainer.reduced_gradient assembles it for diagnostics)."""
+        if hi <= lo:
+            return
+        if self.world == 1 or self.peer is None or self._stream is None:
+            raise RuntimeError("start_sharded needs the peer exchange on more than one rank")
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(ev)
+            self.bytes_reduced += 4 * (hi - lo)
+            if _SKIP_EXCHANGE:                          # timing probe only (wrong numerics)
+                b, e = self.peer.chunks(lo, hi)[self.rank]
+                update(b, e)
+                return
+            ch = self.peer.reduce_scatter_(lo, hi)
+            b, e = ch[self.rank]
+            if e > b:
+                update(b, e)
+            self.peer.all_gather_(ch, bufs)
 
     def finish(self) -> None:
         for w in self._pending:
@@ -334,10 +381,13 @@ def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
     Returns the dict (same on all ranks)."""
     rank, world = world_info(group)
     dev = trainer.dev
+    if hasattr(trainer, "sync_optimizer_state"):
+        trainer.sync_optimizer_state()                                 # sharded optimizer: moments live on their chunk's owner
     snap = trainer.snapshot()
     trainer.step_graphed(*inputs)
     torch.cuda.synchronize(dev)
-    g_dp, d_dp = trainer.G.g.clone(), trainer.D.g.clone()
+    g_dp = trainer.reduced_gradient() if hasattr(trainer, "reduced_gradient") else trainer.G.g.clone()
+    d_dp = trainer.D.g.clone()
     gathered = []
     for t in inputs:
         outs = [torch.empty_like(t) for _ in range(world)]
@@ -399,7 +449,8 @@ def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
     lr = float(cfg["LR"])
     out = {"rel_g": rel_g, "rel_d": rel_d, "worst_tensor": worst_t, "worst_tensor_name": worst_name, "noise_g": noise_g,
            "noise_tensor": noise_t, "frac_p_off": frac_p_off, "max_dp_over_lr": max_dp / lr, "replicas_identical": bool(same),
-           "exchange": "peer" if peer is not None else ("nccl" if world > 1 else "none"), "world": world,
+           "exchange": ("peer, sharded decoder update" if getattr(trainer, "shard_adam", False) else "peer") if peer is not None
+                       else ("nccl" if world > 1 else "none"), "world": world,
            "path": "step_graphed (split graphs)" if trainer.split_graphs else "step_graphed (one graph)",
            "ok": bool(same and rel_g <= max(2e-3, 4 * noise_g) and worst_t <= max(2e-2, 8 * noise_t) and rel_d <= 1e-3
                       and max_dp <= 2.02 * lr)}

@@ -30,8 +30,9 @@ class _Flat:
     re-packing.  The parameter is the [out, in] strided view; the pad columns are zero and stay zero (their gradient is
     never written, so Adam leaves them alone)."""
 
-    def __init__(self, named: List, device, group=None, exchanged: bool = False, pad_rows=None):
+    def __init__(self, named: List, device, group=None, exchanged: bool = False, pad_rows=None, shared_params: bool = False):
         self.names, self.slices = [], {}
+        self._group, self._shared = group, shared_params
         off = 0
         for name, t in named:
             ld = None
@@ -42,7 +43,13 @@ class _Flat:
             self.slices[name] = (off, n, tuple(t.shape), ld)
             off += (n + 7) // 8 * 8                     # 16-byte alignment of every tensor, also in the bf16 shadow
         self.size = off
-        self.p = torch.zeros(off, device=device, dtype=torch.float32)
+        # shared_params: parameters (and their bf16 copy, make_shadow) in symmetric memory too, so that the rank that owns a
+        # chunk of the optimizer state can update it and the others pull the result (dp.GradExchange.start_sharded)
+        self.p_hdl = self.shadow_hdl = None
+        if shared_params:
+            self.p, self.p_hdl = dp.alloc_symmetric(off, torch.float32, device, group)
+        else:
+            self.p = torch.zeros(off, device=device, dtype=torch.float32)
         # the gradient buffer of a data-parallel run may live in symmetric (peer-mapped) memory: dp.PeerExchange
         self.g, self.peer = dp.alloc_exchange_buffer(off, device, group) if exchanged else (torch.zeros(off, device=device, dtype=torch.float32), None)
         self.m = torch.zeros(off, device=device, dtype=torch.float32)
@@ -68,8 +75,14 @@ class _Flat:
         self.step_dev.fill_(int(n))
 
     def make_shadow(self):
-        """bf16 copy of the whole flat parameter buffer (same indexing); kept current by the fused Adam kernel."""
-        self.shadow = ops.convert(self.p, torch.bfloat16)
+        """bf16 copy of the whole flat parameter buffer (same indexing); kept current by the fused Adam kernel.  Allocated
+        once (collectively in symmetric memory when the parameters are), refreshed in place afterwards."""
+        if self.shadow is None:
+            if self._shared and self.p_hdl is not None:
+                self.shadow, self.shadow_hdl = dp.alloc_symmetric(self.size, torch.bfloat16, self.p.device, self._group)
+            else:
+                self.shadow = torch.empty(self.size, device=self.p.device, dtype=torch.bfloat16)
+        ops.convert_into(self.p, self.shadow)
         return self.shadow
 
     def view(self, buf, name):
@@ -130,7 +143,12 @@ class PCAATrainer:
             named += [("GPH." + k, p) for k, p in decoder_projection_head.named_parameters()]
         if decoder is not None:
             named += [("G." + k, p) for k, p in decoder.named_parameters() if k.startswith("dense")]
-        self.G = _Flat(named, dev, process_group, exchanged=True, pad_rows=lambda n, t: n.startswith("G.dense"))
+        # PCAA_DP_SHARD_ADAM=1 (default) with the peer exchange: the decoder span's Adam update is sharded over the ranks
+        # (each rank updates 1/world of it and the others pull the updated weights; `exchange_decoder_span` below)
+        want_shard = (self.world > 1 and decoder is not None and dp.exchange_mode() == "peer"
+                      and os.environ.get("PCAA_DP_SHARD_ADAM", "1") == "1")
+        self.G = _Flat(named, dev, process_group, exchanged=True, pad_rows=lambda n, t: n.startswith("G.dense"),
+                       shared_params=want_shard)
         self.D = _Flat([("D." + k, p) for k, p in discriminator.named_parameters()], dev, process_group, exchanged=True)
         dec_names = [n for n in self.G.names if n.startswith("G.") or n.startswith("GPH.")]
         self._dec_span = self.G.span(dec_names) if dec_names else None
@@ -153,6 +171,13 @@ class PCAATrainer:
         self._cls_diverged = False          # set by the first unsupervised iteration; until then one Adam call covers both
         self.G.make_shadow()
         self._refresh_views()
+        self.shard_adam = False
+        if want_shard:
+            # every rank must take the same path: sharded only if all three symmetric allocations worked everywhere
+            ok = torch.tensor([int(self.G.peer is not None and self.G.p_hdl is not None and self.G.shadow_hdl is not None)], device=dev)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN,
+                                         group=None if isinstance(process_group, str) else process_group)
+            self.shard_adam = bool(int(ok))
         # gradient exchange (dp.py): decoder-side span first (overlaps the encoder backward), then the encoder span
         self.xG = dp.GradExchange(self.G.g, process_group, side_stream=True, peer=self.G.peer)
         self.xD = dp.GradExchange(self.D.g, process_group, peer=self.D.peer)
@@ -306,7 +331,15 @@ class PCAATrainer:
         def exchange_decoder_span():
             # decoder-side gradients (99 % of the bytes) are final: reduce them AND apply their Adam update (HBM bound)
             # on the side stream while the encoder backward (tensor bound) runs on the main one
-            if self._dec_span is not None:
+            if self._dec_span is None:
+                return
+            if self.shard_adam:
+                # ZeRO-1 over NVLink peer memory: reduce-scatter, Adam on this rank's 1/world of the span, all-gather of the
+                # updated fp32 weights and their bf16 copies -- 1/world of the optimizer's HBM traffic per GPU and no
+                # all-gather of gradients
+                self.xG.start_sharded(*self._dec_span, update=adam_span,
+                                      bufs=[(self.G.p, self.G.p_hdl), (self.G.shadow, self.G.shadow_hdl)])
+            else:
                 self.xG.start(*self._dec_span, then=lambda: adam_span(*self._dec_span))
 
         def encoder_backward_upper():
@@ -485,6 +518,34 @@ class PCAATrainer:
         self._cls_step_dev.fill_(int(n))
 
     # ------------------------------------------------------------------------------------------------------------
+    def _dp_src(self, r: int) -> int:
+        g = None if isinstance(self.pg, str) else self.pg
+        return r if g is None else torch.distributed.get_global_rank(g, r)
+
+    def _owner_chunks(self):
+        """[(owner rank, lo, hi)] of the decoder span under the sharded optimizer; empty otherwise."""
+        if not self.shard_adam or self._dec_span is None:
+            return []
+        return [(r, b, e) for r, (b, e) in enumerate(self.G.peer.chunks(*self._dec_span)) if e > b]
+
+    def reduced_gradient(self) -> torch.Tensor:
+        """The generator-side flat gradient of the last iteration summed over the ranks, on every rank (a copy).  With the
+        sharded decoder update the reduced gradient exists only chunk-wise on the chunks' owners: assembled here by
+        broadcasts (collective; diagnostics and parity checks only, not part of the step)."""
+        g = self.G.g.clone()
+        grp = None if isinstance(self.pg, str) else self.pg
+        for r, b, e in self._owner_chunks():
+            torch.distributed.broadcast(g[b:e], src=self._dp_src(r), group=grp)
+        return g
+
+    def sync_optimizer_state(self) -> None:
+        """Make the Adam moments of the decoder span complete on every rank (sharded optimizer: each rank only advances the
+        moments of the chunk it owns).  Collective; called before a checkpoint is written or a snapshot is compared."""
+        grp = None if isinstance(self.pg, str) else self.pg
+        for r, b, e in self._owner_chunks():
+            for buf in (self.G.m, self.G.v):
+                torch.distributed.broadcast(buf[b:e], src=self._dp_src(r), group=grp)
+
     def snapshot(self) -> Dict:
         """Clone of everything one iteration changes: both optimizers' weights / moments / step counts and the encoder's
         BatchNorm running statistics (+ the mean learner's).  `restore` puts it back (also into another trainer of the
@@ -557,7 +618,8 @@ def save_checkpoint(trainer: PCAATrainer, model_name: str, root: str = ".", conf
     <name>_E.pt, _G.pt, _D.pt, _GPH.pt, _DPH.pt (state_dicts with the reference's keys) and discriminator_means.pt, so that
     inference_PCAA.CGAAE_inference_setup loads the folder as it is; plus <name>_OPT.pt with both Adam states (the reference
     does not checkpoint its optimizers; this is what makes a run resumable).  config.pkl is (re)written when `config` is
-    given or the file does not exist yet (the trainer's own hyper-parameters then)."""
+    given or the file does not exist yet (the trainer's own hyper-parameters then).  Data-parallel with the sharded decoder
+    update: call `trainer.sync_optimizer_state()` on ALL ranks first (fit does), the moments are complete only then."""
     from . import utils
     d, paths = _ckpt_paths(root, model_name)
     os.makedirs(d, exist_ok=True)
@@ -690,6 +752,8 @@ def fit(trainer: PCAATrainer, train, valid, config: dict, model_name: str, root:
                  "Cross Entropy Loss Valid": v[1], "Discriminator Loss": s[2], "Total Loss Train": s[3],
                  "Train Accuracy": int(correct) / max(n_it * (hi - lo), 1), "Valid Accuracy": int(vcorrect) / max(n_v * (hi - lo), 1),
                  "saved": False}
+        if epoch % int(config.get("CHECKPOINT_FREQUENCY", 1)) == 0:
+            trainer.sync_optimizer_state()              # collective, so outside the (per-rank) accuracy condition
         if epoch % int(config.get("CHECKPOINT_FREQUENCY", 1)) == 0 and rec_e["Valid Accuracy"] > best_valid_accuracy:
             best_valid_accuracy = rec_e["Valid Accuracy"]
             if rank == 0:

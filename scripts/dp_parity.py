@@ -46,9 +46,10 @@ def syncbn_check():
     ref.restore(snap)
     oref = ref.step(pcs.to(dev), gt.to(dev), z0_g.to(dev), al_g.to(dev))
     torch.cuda.synchronize()
-    rel_g = float((tr.G.g / world - ref.G.g).norm() / ref.G.g.norm())
+    g_red = tr.reduced_gradient()                 # (assembled from the owners' chunks under the sharded decoder update)
+    rel_g = float((g_red / world - ref.G.g).norm() / ref.G.g.norm())
     rel_d = float((tr.D.g / world - ref.D.g).norm() / ref.D.g.norm())
-    worst_t, worst_name = dp.per_tensor_relnorm(tr.G, tr.G.g / world, ref.G.g)
+    worst_t, worst_name = dp.per_tensor_relnorm(tr.G, g_red / world, ref.G.g)
     # noise floor: the single-process iteration repeated from the same state (atomics / bf16 rounding flips, see dp.graphed_step_parity)
     g_first = ref.G.g.clone()
     ref.restore(snap)
@@ -71,7 +72,7 @@ def syncbn_check():
     tr.restore(snap)
     tr.step(*sh)
     torch.cuda.synchronize()
-    g_sync = tr.G.g / world
+    g_sync = tr.reduced_gradient() / world
     ref.restore(snap)
     ref.step(*sh)
     torch.cuda.synchronize()
@@ -114,7 +115,7 @@ p0, d0 = tr.G.p.clone(), tr.D.p.clone()
 bufs0 = [b.clone() for b in tr.enc.buffers()]
 out = tr.step(pcs[s:e].to(dev), gt[s:e].to(dev), z0_l.to(dev), al_l.to(dev))
 torch.cuda.synchronize()
-g_dp, p_dp = tr.G.g.clone(), tr.G.p.clone()                       # g holds the all-reduced SUM
+g_dp, p_dp = tr.reduced_gradient(), tr.G.p.clone()                 # the all-reduced SUM
 
 # single-process reference on every shard, from the same initial state (no process group: world 1)
 import opensetgaitrecognition_pcaa_b200.dp as dpm
@@ -155,6 +156,8 @@ if rank == 0:
     print("dp_parity graphed: " + ", ".join(f"{k}={v:.3g}" if isinstance(v, float) else f"{k}={v}" for k, v in gp.items()))
 if rank == 0:
     xch = "peer copies (copy engines, symmetric memory)" if tr.G.peer is not None else "NCCL all-reduce"
+    if tr.shard_adam:
+        xch += ", sharded decoder update"
     print(f"dp_parity world={world} [{xch}, {tr.xG.bytes_reduced / 1e6:.1f} MB reduced]: ||g_dp - sum_shards g|| / ||.|| = {rel_g:.2e}, fraction of weights off Adam(mean grad) by > 2e-6 = {rel_p:.2e}, "
           f"replicas identical after the step: {same} -> {'OK' if ok and same else 'FAIL'}")
 dist.destroy_process_group()
