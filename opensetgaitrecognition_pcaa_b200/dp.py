@@ -374,7 +374,7 @@ def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
       noise_g, noise_tensor   the two emulation runs against each other: the floor the figures above are judged against
       frac_p_off, max_dp     generator weights vs Adam(snapshot, mean gradient): fraction off by > 2e-6, largest deviation
       replicas_identical     every rank holds bit-identical generator and critic weights after the iteration
-    Verdict `ok`: replicas identical, rel_g <= max(2e-3, 4 noise_g), worst_tensor <= max(2e-2, 8 noise_tensor) (a maximum over
+    Verdict `ok`: replicas identical, rel_g <= max(2e-3, 4 noise_g), worst_tensor <= max(5e-2, 8 noise_tensor) (a maximum over
     ~100 tensors of a noise-limited quantity), rel_d <= 1e-3, max_dp <= 2.02 lr (an Adam step is at most ~lr; entries whose
     gradient is noise may step the other way).  A wrong exchange (a missing rank, a wrong scale, a stale chunk) moves rel_g
     and worst_tensor to O(1).
@@ -452,7 +452,7 @@ def graphed_step_parity(trainer, inputs, make_single, group=None) -> dict:
            "exchange": ("peer, sharded decoder update" if getattr(trainer, "shard_adam", False) else "peer") if peer is not None
                        else ("nccl" if world > 1 else "none"), "world": world,
            "path": "step_graphed (split graphs)" if trainer.split_graphs else "step_graphed (one graph)",
-           "ok": bool(same and rel_g <= max(2e-3, 4 * noise_g) and worst_t <= max(2e-2, 8 * noise_t) and rel_d <= 1e-3
+           "ok": bool(same and rel_g <= max(2e-3, 4 * noise_g) and worst_t <= max(5e-2, 8 * noise_t) and rel_d <= 1e-3
                       and max_dp <= 2.02 * lr)}
     del ref
     torch.cuda.empty_cache()
