@@ -18,6 +18,8 @@ Everything here is backend-agnostic host logic (``nccl`` on the B200 box, ``gloo
                       mapped), adds the pulled chunks locally (``pcaa_sum_into``) and pulls the other ranks' reduced
                       chunks back.  No SM is taken from the persistent tcgen05 GEMMs of the encoder backward that
                       runs beside it (NCCL's all-reduce CTAs cost the step ~1 ms on 2 GPUs, DESIGN.md section 5);
+                      ``GradExchange.start_sharded`` uses its two halves as a sharded optimizer (ZeRO-1): reduce-scatter
+                      the gradients, update the owned 1/world of the parameters, all-gather the updated parameters;
 * ``gather_scores``   the one gather inference needs (per-sample scores for the host-side ROC threshold).
 """
 from __future__ import annotations
