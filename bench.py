@@ -604,7 +604,7 @@ def run_b200(args):
     if inference_rec is not None:
         line["inference"] = inference_rec
     if world == 1 and not args.no_cpu:
-        # the reference's own loop on the host cores (bounded sample: batch 32, 1 warm-up + 2 timed iterations) and on cuda:0
+        # the reference's own loop on the host cores (bounded sample: batch 32, 1 warm-up + 5 timed iterations) and on cuda:0
         # (stock torch eager, same batch as this arm), each in a fresh process: `bench.py --impl reference`
         cpu = sub_bench(["--impl", "reference", "--steps", "5", "--warmup", "1", "--nmax", str(NMAX)])     # ~12 s of CPU work
         line["cpu_baseline"] = cpu.get("cpu_baseline", cpu)
