@@ -173,3 +173,20 @@ def test_shard_range_properties():
     assert dp.split_spans(0, 20, 8) == [(0, 8), (8, 16), (16, 20)]
     assert dp.split_spans(3, 3, 8) == []
     assert dp.world_info() == (0, 1)
+
+
+def test_peer_exchange_chunks_partition_the_span():
+    """The chunk of the decoder span a rank reduces -- and, with the sharded optimizer, updates and serves to its peers:
+    chunks tile [lo, hi) in rank order, start on multiples of 8 elements relative to lo (16-byte aligned in the fp32
+    buffers AND in the bf16 operand copy) and may be empty at the tail."""
+    from opensetgaitrecognition_pcaa_b200 import dp
+    for world in (2, 3, 4, 8):
+        px = object.__new__(dp.PeerExchange)
+        px.world = world
+        for lo, hi in ((0, 8), (16, 16 + 217_767_240), (24, 24 + 4484), (8, 8 + 40), (0, 12)):
+            ch = px.chunks(lo, hi)
+            assert len(ch) == world and ch[0][0] == lo and ch[-1][1] == hi
+            assert all(ch[i][1] == ch[i + 1][0] for i in range(world - 1))
+            assert all(b <= e for b, e in ch) and all((b - lo) % 8 == 0 for b, e in ch if e > b)
+            sizes = [e - b for b, e in ch]
+            assert max(sizes) <= ((hi - lo + world - 1) // world + 7) // 8 * 8
