@@ -548,7 +548,8 @@ class PCAATrainer:
 
     def snapshot(self) -> Dict:
         """Clone of everything one iteration changes: both optimizers' weights / moments / step counts and the encoder's
-        BatchNorm running statistics (+ the mean learner's).  `restore` puts it back (also into another trainer of the
+        BatchNorm running statistics (+ the mean learner's; data-parallel with the sharded decoder update the moments of the
+        decoder span are complete only after `sync_optimizer_state()`).  `restore` puts it back (also into another trainer of the
         same architecture: data-parallel parity checks, resumable probes)."""
         snap = {"G": (self.G.p.clone(), self.G.m.clone(), self.G.v.clone(), self.G.step),
                 "D": (self.D.p.clone(), self.D.m.clone(), self.D.v.clone(), self.D.step),
