@@ -167,9 +167,13 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
 
     `pause_after=l` (4, 3 or 2) returns ``(G, resume)`` once the weight AND data gradient of layer l are enqueued: at that
     point the gradients of layers >= l are final and W_l is no longer read, so a data-parallel trainer can start exchanging
-    (and updating) them while ``resume()`` -- the rest of the backward -- runs."""
+    (and updating) them while ``resume()`` -- the rest of the backward -- runs.
+
+    `after_dy4()` (optional) is called once the HBM-bound passes at the head of the backward (pooled-layer BatchNorm / ELU /
+    pool backward) are enqueued and the tensor-bound layer-4 GEMMs come next: the point where a caller forks HBM-bound side
+    work (the decoder's optimizer update) so that it runs beside tensor-bound kernels instead of competing for HBM."""
     G: Grads = {}
-    steps = _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G, pause_after)
+    steps = _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G, pause_after, after_dy4)
     for l in steps:
         if pause_after is not None and l == pause_after:
             def resume():

@@ -351,9 +351,14 @@ class PCAATrainer:
 
         def encoder_backward_upper():
             self.G.g[self._enc_span[0]:self._enc_span[1]].zero_()     # one fill instead of one per accumulated gradient
+            def fork_update():
+                st["update_forked"] = True
+                exchange_decoder_span(True)
             _, st["resume"] = engine.encoder_backward(st["dlogits"], st["dfv"], st["saved"], self.P_E, self.gb_E,
                                                       side=self._wgrad_stream, bn=self.bn_sync, pause_after=3,
-                                                      after_dy4=(lambda: exchange_decoder_span(True)) if late_update else None)
+                                                      after_dy4=fork_update if late_update else None)
+            if late_update and not st.pop("update_forked", False):
+                raise RuntimeError("late update: the encoder backward never reached its fork point")
 
         def encoder_backward():
             encoder_backward_upper()
