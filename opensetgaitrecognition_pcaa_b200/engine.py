@@ -158,7 +158,7 @@ def pointnet_forward(x: torch.Tensor, P: Params, training: bool, pre: str = "pc_
 
 def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grads] = None,
                       pre: str = "pc_block.", side: Optional[torch.cuda.Stream] = None, bn: Optional[BnSync] = None,
-                      pause_after: Optional[int] = None, after_dy4=None):
+                      pause_after: Optional[int] = None):
     """gpool [B*T, 1024] fp32 = d loss / d pooled.  Returns parameter gradients (written into gradbuf when given).
 
     With a `side` stream the weight-gradient GEMM of layer l (tensor bound, reads dy_l and a_{l-1}) runs there while the
@@ -167,13 +167,9 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
 
     `pause_after=l` (4, 3 or 2) returns ``(G, resume)`` once the weight AND data gradient of layer l are enqueued: at that
     point the gradients of layers >= l are final and W_l is no longer read, so a data-parallel trainer can start exchanging
-    (and updating) them while ``resume()`` -- the rest of the backward -- runs.
-
-    `after_dy4()` (optional) is called once the HBM-bound passes at the head of the backward (pooled-layer BatchNorm / ELU /
-    pool backward) are enqueued and the tensor-bound layer-4 GEMMs come next: the point where a caller forks HBM-bound side
-    work (the decoder's optimizer update) so that it runs beside tensor-bound kernels instead of competing for HBM."""
+    (and updating) them while ``resume()`` -- the rest of the backward -- runs."""
     G: Grads = {}
-    steps = _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G, pause_after, after_dy4)
+    steps = _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G, pause_after)
     for l in steps:
         if pause_after is not None and l == pause_after:
             def resume():
@@ -186,7 +182,7 @@ def pointnet_backward(gpool: torch.Tensor, sv, P: Params, gradbuf: Optional[Grad
     return G
 
 
-def _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G, pause_after=None, after_dy4=None):
+def _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G, pause_after=None):
     """Generator behind pointnet_backward: yields l after the weight and data gradients of layer l (4, 3, 2) are enqueued."""
     R, N, Rg = sv["R"], sv["N"], sv["Rg"]
     if (bn is not None) != (Rg != R):
@@ -200,8 +196,6 @@ def _pointnet_backward_steps(gpool, sv, P, gradbuf, pre, side, bn, G, pause_afte
     c, dgam, dbet = _bn_bwd_coefs(st2, R, Rg, sv["coef"][4], _out(gradbuf, kb + "weight"), _out(gradbuf, kb + "bias"), bn)
     G[kb + "weight"], G[kb + "bias"] = dgam, dbet
     dy = ops.pool_bwd_apply_t(gpool, sv["y"][4], sv["coef"][4], c, N)
-    if after_dy4 is not None:
-        after_dy4()
     arena = dict(zip((4, 3, 2), _stats_arena([P[f"{pre}pointnet{l}.module.0.weight"].shape[1] for l in (4, 3, 2)], gpool.device)))
     for l in (4, 3, 2):
         kc = f"{pre}pointnet{l}.module.0."
@@ -444,16 +438,14 @@ def encoder_forward(x: torch.Tensor, P: Params, training: bool, use_projection_h
 
 
 def encoder_backward(dlogits, dfv, saved, P: Params, gradbuf: Optional[Grads] = None,
-                     side: Optional[torch.cuda.Stream] = None, bn: Optional[BnSync] = None, pause_after: Optional[int] = None,
-                     after_dy4=None):
+                     side: Optional[torch.cuda.Stream] = None, bn: Optional[BnSync] = None, pause_after: Optional[int] = None):
     """Backward of the whole encoder.  With `pause_after=l` returns ``(G, resume)`` after PointNet layer l (see
     pointnet_backward): heads, TCN and the PointNet layers >= l are then final; ``resume()`` finishes and returns G."""
     sv_p, sv_t, sv_h = saved
     dg, G = heads_backward(dlogits, dfv, sv_h, P, gradbuf)
     dpool, Gt = tcn_backward(dg, sv_t, P, gradbuf, dout_is_frame_mean=True, bn=bn)
     G.update(Gt)
-    r = pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf, side=side, bn=bn, pause_after=pause_after,
-                          after_dy4=after_dy4)
+    r = pointnet_backward(dpool.reshape(-1, dpool.shape[-1]), sv_p, P, gradbuf, side=side, bn=bn, pause_after=pause_after)
     if pause_after is None:
         G.update(r)
         return G

@@ -195,9 +195,6 @@ class PCAATrainer:
         # BatchNorm-backward passes (engine.pointnet_backward).  Off by default: measured on B200 the step is power
         # capped (sw_power_cap, ~1.6-1.7 GHz under load) and the overlap buys nothing (21.99 vs 22.07 ms at B=256).
         self._wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("PCAA_WGRAD_OVERLAP", "0") == "1" else None
-        # PCAA_LATE_UPDATE=1: on one rank fork the decoder span's Adam update behind the HBM-bound head of the encoder backward
-        # instead of at its start (see _phases)
-        self._late_update = os.environ.get("PCAA_LATE_UPDATE", "0") == "1"
         self._graphs: Dict = {}
         self._warm = set()
         # phase_timing = True: step / step_graphed (split graphs) bracket every phase of `_phases` with CUDA events on the
@@ -331,14 +328,10 @@ class PCAATrainer:
             if supervised and cls_split:
                 ops.adam_advance(self._cls_step_dev, self._cls_coef_dev, cfg["LR"], cfg["B1"], b2_g)
 
-        # one rank, one graph: the decoder span's Adam update (HBM bound) is forked INSIDE the encoder backward, behind its
-        # HBM-bound head (TCN backward, pooled-layer backward pass), so that it runs beside the tensor-bound layer-4 GEMMs
-        late_update = self._late_update and self.world == 1 and not self.split_graphs and self._dec_span is not None
-
-        def exchange_decoder_span(forked_late: bool = False):
+        def exchange_decoder_span():
             # decoder-side gradients (99 % of the bytes) are final: reduce them AND apply their Adam update (HBM bound)
             # on the side stream while the encoder backward (tensor bound) runs on the main one
-            if self._dec_span is None or (late_update and not forked_late):
+            if self._dec_span is None:
                 return
             if self.shard_adam:
                 # ZeRO-1 over NVLink peer memory: reduce-scatter, Adam on this rank's 1/world of the span, all-gather of the
@@ -351,14 +344,8 @@ class PCAATrainer:
 
         def encoder_backward_upper():
             self.G.g[self._enc_span[0]:self._enc_span[1]].zero_()     # one fill instead of one per accumulated gradient
-            def fork_update():
-                st["update_forked"] = True
-                exchange_decoder_span(True)
             _, st["resume"] = engine.encoder_backward(st["dlogits"], st["dfv"], st["saved"], self.P_E, self.gb_E,
-                                                      side=self._wgrad_stream, bn=self.bn_sync, pause_after=3,
-                                                      after_dy4=fork_update if late_update else None)
-            if late_update and not st.pop("update_forked", False):
-                raise RuntimeError("late update: the encoder backward never reached its fork point")
+                                                      side=self._wgrad_stream, bn=self.bn_sync, pause_after=3)
 
         def encoder_backward():
             encoder_backward_upper()
